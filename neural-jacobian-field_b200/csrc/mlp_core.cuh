@@ -1,0 +1,288 @@
+// Warp-specialised tcgen05 "layer chain" machinery shared by the render kernels
+// and the self-test.
+//
+// One CTA = 320 threads:
+//   warps 0-3  : epilogue warpgroup of tile slot 0 (thread = one sample point = one TMEM lane)
+//   warps 4-7  : epilogue warpgroup of tile slot 1
+//   warp  8    : MMA issuer (one elected thread issues every tcgen05.mma / commit)
+//   warp  9    : weight loader (one elected thread streams packed layer images with
+//                cp.async.bulk into a 2-stage shared-memory ring)
+// Both slots run the SAME step program, so one weight stage feeds two 128-row tiles
+// and the tensor pipe works on one slot while the other slot's warpgroup runs its
+// epilogue (ping-pong).
+//
+// Per slot TMEM: 256 fp32 columns (x: [0,128) residual stream, net: [128,256)).
+#pragma once
+#include "ptx.cuh"
+
+namespace njf {
+
+constexpr int kRows = 128;
+constexpr int kSlots = 2;
+constexpr int kEpiThreads = 256;
+constexpr int kIssuerWarp = 8;
+constexpr int kLoaderWarp = 9;
+constexpr int kThreads = 320;
+constexpr int kStages = 2;
+constexpr uint32_t kStageBytes = 32768;  // up to N=128 x K=128 fp16
+constexpr uint32_t kATileBytes = 32768;  // 128 rows x 128 cols fp16 (2 K-blocks of 16 KB)
+constexpr uint32_t kAKbStride = kRows * 128;  // bytes between K-blocks of an A tile
+constexpr uint32_t kTzBytes = 32768;     // 128 rows x 128 ch fp16 (256 B rows, chunk-swizzled)
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kSlotCols = 256;
+constexpr int kMaxSteps = 48;
+
+struct MmaStep {
+  uint32_t w_off;    // byte offset of the layer image inside the packed blob (16 B aligned)
+  uint32_t w_bytes;  // n * kblocks * 128
+  uint16_t n;        // MMA N (multiple of 16, <= 128)
+  uint8_t kblocks;   // K / 64 (1 or 2)
+  uint8_t acc;       // 1: accumulate onto d_col
+  uint16_t d_col;    // TMEM column offset inside the slot
+  uint16_t pad_;
+};
+struct Program {
+  int nsteps;
+  MmaStep steps[kMaxSteps];
+};
+
+// dynamic shared memory map (base aligned to 1024 B)
+struct SmemMap {
+  static constexpr uint32_t kA = 0;                                 // 2 x 32 KB
+  static constexpr uint32_t kW = kA + kSlots * kATileBytes;         // 2 x 32 KB
+  static constexpr uint32_t kTz = kW + kStages * kStageBytes;       // 2 x 32 KB
+  static constexpr uint32_t kMisc = kTz + kSlots * kTzBytes;        // barriers etc.
+  static constexpr uint32_t kMiscBytes = 1024;
+  static constexpr uint32_t kScratch = kMisc + kMiscBytes;          // kernel-specific
+};
+struct Barriers {
+  uint64_t a_ready[kSlots];    // 128 arrivals: slot's A tile written (+ TMEM reads drained)
+  uint64_t acc_ready[kSlots];  // tcgen05.commit: slot's accumulator complete
+  uint64_t w_full[kStages];    // bulk-copy transaction bytes landed
+  uint64_t w_empty[kStages];   // tcgen05.commit: both slots' MMAs done with the stage
+  uint32_t tmem_base;
+};
+
+struct CtaCtx {
+  uint8_t* smem;
+  Barriers* bars;
+  uint32_t tmem_base;
+};
+
+// all 320 threads
+__device__ __forceinline__ CtaCtx cta_setup(uint8_t* smem_raw) {
+  CtaCtx c;
+  c.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                      ~static_cast<uintptr_t>(1023));
+  c.bars = reinterpret_cast<Barriers*>(c.smem + SmemMap::kMisc);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&c.bars->a_ready[s], kRows);
+      mbar_init(&c.bars->acc_ready[s], 1);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&c.bars->w_full[s], 1);
+      mbar_init(&c.bars->w_empty[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == kIssuerWarp) tmem_alloc(&c.bars->tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem_base = c.bars->tmem_base;
+  return c;
+}
+__device__ __forceinline__ void cta_teardown(const CtaCtx& c) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == kIssuerWarp) tmem_dealloc(c.tmem_base, kTmemCols);
+}
+
+// ----------------------------------------------------------------------------- loader
+// `nrun` = how many times the program is executed by this CTA (items x tiles-per-item).
+__device__ __forceinline__ void loader_role(const CtaCtx& c, const Program& prog,
+                                            const uint8_t* __restrict__ blob, int nrun) {
+  uint32_t cnt = 0;
+  for (int run = 0; run < nrun; ++run) {
+    for (int s = 0; s < prog.nsteps; ++s, ++cnt) {
+      const uint32_t stage = cnt % kStages, par = (cnt / kStages) & 1u;
+      mbar_wait(&c.bars->w_empty[stage], par ^ 1u);
+      const uint32_t bytes = prog.steps[s].w_bytes;
+      mbar_arrive_expect_tx(&c.bars->w_full[stage], bytes);
+      bulk_g2s(c.smem + SmemMap::kW + stage * kStageBytes, blob + prog.steps[s].w_off, bytes,
+               &c.bars->w_full[stage]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- issuer
+// `nact(run)` = number of active slots for that run (slot 1 idles on an odd tail).
+template <class NActFn>
+__device__ __forceinline__ void issuer_role(const CtaCtx& c, const Program& prog, int nrun,
+                                            NActFn nact) {
+  uint32_t cnt = 0;
+  uint32_t apar[kSlots] = {0, 0};
+  const uint32_t a_base = smem_u32(c.smem + SmemMap::kA);
+  const uint32_t w_base = smem_u32(c.smem + SmemMap::kW);
+  for (int run = 0; run < nrun; ++run) {
+    const int na = nact(run);
+    for (int s = 0; s < prog.nsteps; ++s, ++cnt) {
+      const MmaStep st = prog.steps[s];
+      const uint32_t stage = cnt % kStages, par = (cnt / kStages) & 1u;
+      const uint32_t idesc = make_idesc_f16(st.n);
+      const uint32_t w_kb_stride = static_cast<uint32_t>(st.n) * 128u;
+      for (int slot = 0; slot < na; ++slot) {
+        mbar_wait(&c.bars->a_ready[slot], apar[slot]);
+        apar[slot] ^= 1u;
+        if (slot == 0) mbar_wait(&c.bars->w_full[stage], par);
+        tc_fence_after();
+        const uint32_t d_tmem = c.tmem_base + slot * kSlotCols + st.d_col;
+        const uint32_t a0 = a_base + slot * kATileBytes;
+        const uint32_t w0 = w_base + stage * kStageBytes;
+        uint32_t acc = st.acc;
+        for (int kb = 0; kb < st.kblocks; ++kb) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(d_tmem, make_sw128_desc(a0 + kb * kAKbStride + k * 32),
+                     make_sw128_desc(w0 + kb * w_kb_stride + k * 32), idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&c.bars->acc_ready[slot]);
+      }
+      umma_commit(&c.bars->w_empty[stage]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- epilogue-side helpers
+struct EpiCtx {
+  uint8_t* a_tile;    // this slot's A tile (generic pointer)
+  uint8_t* tz;        // this slot's 32 KB staging buffer
+  uint64_t* a_ready;
+  uint64_t* acc_ready;
+  uint32_t tmem;      // TMEM address of this thread's lane, column 0 of the slot
+  uint32_t acc_par;
+  int row;            // 0..127 (== TMEM lane)
+  int slot;
+};
+__device__ __forceinline__ EpiCtx epi_ctx(const CtaCtx& c) {
+  EpiCtx e;
+  const int warp = threadIdx.x >> 5;
+  e.slot = warp >> 2;
+  e.row = threadIdx.x & 127;
+  e.a_tile = c.smem + SmemMap::kA + e.slot * kATileBytes;
+  e.tz = c.smem + SmemMap::kTz + e.slot * kTzBytes;
+  e.a_ready = &c.bars->a_ready[e.slot];
+  e.acc_ready = &c.bars->acc_ready[e.slot];
+  e.tmem = c.tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + e.slot * kSlotCols;
+  e.acc_par = 0;
+  return e;
+}
+// A tile fully written (generic proxy) and all of this thread's TMEM accesses retired
+__device__ __forceinline__ void epi_publish(EpiCtx& e) {
+  fence_proxy_async_smem();
+  tc_fence_before();
+  mbar_arrive(e.a_ready);
+}
+__device__ __forceinline__ void epi_wait_acc(EpiCtx& e) {
+  mbar_wait(e.acc_ready, e.acc_par);
+  e.acc_par ^= 1u;
+  tc_fence_after();
+}
+// 32 packed fp16x2 words (64 columns? no: 16 words = 32 columns) -> A tile columns [c0, c0+32)
+__device__ __forceinline__ void a_store32(const EpiCtx& e, int c0, const uint32_t (&p)[16]) {
+  uint8_t* base = e.a_tile + (c0 >> 6) * kAKbStride + e.row * 128;
+  const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 v = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+    *reinterpret_cast<uint4*>(base + (((ch0 + j) ^ (e.row & 7)) << 4)) = v;
+  }
+}
+// zero-fill A tile columns [c0, c0+32)
+__device__ __forceinline__ void a_zero32(const EpiCtx& e, int c0) {
+  uint8_t* base = e.a_tile + (c0 >> 6) * kAKbStride + e.row * 128;
+  const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(base + (((ch0 + j) ^ (e.row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+}
+
+// staging buffer: row r = 256 B (128 fp16), 16 B chunk c stored at chunk (c ^ (r & 7))
+__device__ __forceinline__ uint32_t tz_offset(int row, int chunk) {
+  return row * 256 + ((chunk ^ (row & 7)) << 4);
+}
+
+// acc[c0..c0+32) of this slot (+ bias) -> ReLU -> fp16 -> A tile.  `col` = TMEM column of c0.
+__device__ __forceinline__ void epi_relu_to_a(const EpiCtx& e, int tcol, int c0,
+                                              const float* __restrict__ bias) {
+  uint32_t r[32];
+  tmem_ld32(e.tmem + tcol, r);
+  tmem_ld_wait();
+  uint32_t p[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+    const float v0 = fminf(__uint_as_float(r[4 * j + 0]) + b.x, kF16Max);
+    const float v1 = fminf(__uint_as_float(r[4 * j + 1]) + b.y, kF16Max);
+    const float v2 = fminf(__uint_as_float(r[4 * j + 2]) + b.z, kF16Max);
+    const float v3 = fminf(__uint_as_float(r[4 * j + 3]) + b.w, kF16Max);
+    p[2 * j] = pack_relu_f16x2(v0, v1);
+    p[2 * j + 1] = pack_relu_f16x2(v2, v3);
+  }
+  a_store32(e, c0, p);
+}
+
+// x[c0..c0+32) += tz_staging[row][c0..] + bias ; write the sum back to TMEM (so later
+// accumulating MMAs see it) ; ReLU -> fp16 -> A tile.  `extra` (optional, per-thread
+// fp32[32]) is added as well (raw-xyz columns of lin_in kept in fp32).
+template <bool kHasTz, bool kHasExtra>
+__device__ __forceinline__ void epi_x_update(const EpiCtx& e, int c0,
+                                             const float* __restrict__ bias,
+                                             const float* extra) {
+  uint32_t r[32];
+  tmem_ld32(e.tmem + c0, r);
+  tmem_ld_wait();
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+  }
+  if (kHasTz) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 q = *reinterpret_cast<const uint4*>(e.tz + tz_offset(e.row, (c0 >> 3) + j));
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h[t]);
+        v[8 * j + 2 * t] += f.x;
+        v[8 * j + 2 * t + 1] += f.y;
+      }
+    }
+  }
+  if (kHasExtra) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += extra[j];
+  }
+  if (kHasTz || kHasExtra) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+    tmem_st32(e.tmem + c0, r);
+  }
+  uint32_t p[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    p[j] = pack_relu_f16x2(fminf(v[2 * j], kF16Max), fminf(v[2 * j + 1], kF16Max));
+  a_store32(e, c0, p);
+  if (kHasTz || kHasExtra) tmem_st_wait();
+}
+
+}  // namespace njf
