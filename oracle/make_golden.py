@@ -1,0 +1,154 @@
+"""TEST INFRASTRUCTURE: generate tests/golden/*.npz by running the UNMODIFIED reference
+(imported from /root/reference through oracle/ref_shim.py) on seeded synthetic inputs.
+
+Run in the build container only:   python oracle/make_golden.py
+Weights are not stored: they are re-created from ``oracle/synth.py`` (seed + state-dict key).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+import synth  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def scene(action_dim: int, rays_hw=(6, 8), img_hw=(24, 32), view=1, near=0.5, far=3.0, seed=2, batch=1):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(batch, 3, *img_hw, generator=g)
+    K = synth.normalized_intrinsics(**synth.ALLEGRO_INTRINSICS_PX)[None].repeat(batch, 1, 1)
+    ctxt = torch.eye(4)[None].repeat(batch, 1, 1)
+    trgt = torch.stack([synth.relative_target_pose(view + b) for b in range(batch)])
+    coords = synth.pixel_grid(*rays_hw)
+    rays = [synth.world_rays(coords, K[b], trgt[b]) for b in range(batch)]
+    o = torch.stack([r[0] for r in rays])
+    d = torch.stack([r[1] for r in rays])
+    kpx = K.clone()
+    kpx[:, 0, :] *= 640
+    kpx[:, 1, :] *= 480
+    act = 0.1 * torch.randn(batch, action_dim, generator=g)
+    zn = torch.full((batch,), near) + 0.05 * torch.arange(batch)
+    zf = torch.full((batch,), far) + 0.1 * torch.arange(batch)
+    return dict(image=img, ctxt_c2w=ctxt, ctxt_k=K, trgt_c2w=trgt, trgt_k_px=kpx, origins=o, dirs=d,
+                z_near=zn, z_far=zf, action=act)
+
+
+def render_fixture(name, head, action_dim, s_prop, s_nerf, wseed, regime="trained", **scene_kw):
+    m = ref_shim.reference_modules()
+    cfg = ref_shim.build_reference_cfg(action_dim, head, s_prop, s_nerf)
+    model = m.Model(cfg).eval()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(synth.synth_state_dict(shapes, wseed, regime))
+    sc = scene(action_dim, **scene_kw)
+    cam = m.CameraInput(sc["image"], sc["ctxt_c2w"], sc["ctxt_k"], sc["trgt_c2w"], sc["trgt_k_px"])
+    rin = m.RenderingInput(sc["origins"], sc["dirs"], sc["z_near"], sc["z_far"])
+    rob = m.RobotInput(sc["action"])
+    rec = {}
+    real_ss = torch.searchsorted
+
+    def spy(*a, **k):
+        r = real_ss(*a, **k)
+        rec.setdefault("inds", []).append(r.clone())
+        return r
+
+    with torch.no_grad():
+        feat = model.encoder(sc["image"])
+        torch.searchsorted = spy
+        try:
+            out = model.forward(cam, rin, rob, compute_vis_features=True)
+        finally:
+            torch.searchsorted = real_ss
+        enc = model.encode_image(cam, rin, rob)
+        flow2 = model.infer_optical_flow(enc, cam, m.RobotInput(sc["action"] * 0.5 + 0.02))
+        # per-sample intermediates through the reference's own sub-calls (model.py:323-351)
+        from neural_jacobian_field.models.decoder.action_decoder import PixelEncoding  # type: ignore
+
+        pe = PixelEncoding(features=feat, extrinsics=sc["ctxt_c2w"], intrinsics=sc["ctxt_k"], action=sc["action"])
+        rs, pos, dirs, wl, rsl = model.compute_proposal(model.compute_ray_bundle(rin), pe)
+        dec = model.decoder.forward(world_space_xyz=pos, world_space_dir=dirs, pixel_encoding=pe)
+    so, vo = out.standard_output, out.vis_output
+    fix = {k: v.numpy() for k, v in sc.items()}
+    fix.update(
+        feat=feat.numpy(), head=head, action_dim=action_dim, s_prop=np.array(s_prop), s_nerf=s_nerf,
+        wseed=wseed, regime=regime,
+        rgb=so.rgb.numpy(), depth=so.depth.numpy(), optical_flow=so.optical_flow.numpy(),
+        action_features=vo.action_features.numpy(), steps=vo.steps.numpy(), weights=vo.weights.numpy(),
+        ray_positions=vo.ray_positions.numpy(), ray_positions_warped=vo.ray_positions_warped.numpy(),
+        final_bins=torch.cat([rs.spacing_starts[..., 0], rs.spacing_ends[..., -1:, 0]], -1).numpy(),
+        proposal_weights=wl[-1][..., 0].numpy(), sigma=dec.density.numpy(), jacobian=dec.action_features.numpy(),
+        rgb_samples=dec.color.numpy(), positions=pos.numpy(),
+        enc_density=enc.density.numpy(), enc_jacobian=enc.action_features.numpy(), enc_weights=enc.weights.numpy(),
+        enc_positions=enc.ray_samples_positions.numpy(), action2=(sc["action"] * 0.5 + 0.02).numpy(),
+        flow2=flow2.numpy(),
+    )
+    for i, t in enumerate(rec["inds"]):
+        fix[f"inds_{i + 1}"] = t.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **fix)
+    print(name, {k: getattr(v, "shape", v) for k, v in fix.items() if k in ("rgb", "feat", "sigma", "inds_1")})
+
+
+def pdf_fixture():
+    """Reference PDFSampler (rendering/ray_samplers.py:326-451) in eval mode on hand-made histograms."""
+    ref_shim.install()
+    from neural_jacobian_field.rendering import ray_samplers as rsm  # type: ignore
+
+    g = torch.Generator().manual_seed(5)
+    cases = {}
+    for s_in, s_out in ((16, 24), (64, 64), (128, 128), (256, 256), (48, 32)):
+        R = 64
+        wts = torch.rand(R, s_in, generator=g) ** 4
+        wts[0] = 0.0                      # zero-weight ray -> eps padding branch
+        wts[1] = 0.0
+        wts[1, s_in // 3] = 1.0           # single spike
+        wts[2] = 1.0 / s_in               # flat
+        wts[3, : s_in // 2] = 0.0         # half empty
+        wts[4] = torch.linspace(0, 1, s_in) * 1e-4   # tiny but non-zero
+        bundle = rsm.RayBundle(origins=torch.zeros(R, 3), directions=torch.ones(R, 3),
+                               nears=torch.full((R, 1), 0.5), fars=torch.full((R, 1), 3.0))
+        uni = rsm.UniformSampler().eval()
+        rs0 = uni(bundle, num_samples=s_in)
+        pdf = rsm.PDFSampler(include_original=False).eval()
+        rec = []
+        real_ss = torch.searchsorted
+
+        def spy(*a, **k):
+            r = real_ss(*a, **k)
+            rec.append(r.clone())
+            return r
+
+        torch.searchsorted = spy
+        try:
+            rs1 = pdf(bundle, rs0, wts[..., None], num_samples=s_out)
+        finally:
+            torch.searchsorted = real_ss
+        tag = f"{s_in}_{s_out}"
+        cases[f"w_{tag}"] = wts.numpy()
+        cases[f"bins_in_{tag}"] = torch.cat([rs0.spacing_starts[..., 0], rs0.spacing_ends[..., -1:, 0]], -1).numpy()
+        cases[f"bins_out_{tag}"] = torch.cat([rs1.spacing_starts[..., 0], rs1.spacing_ends[..., -1:, 0]], -1).numpy()
+        cases[f"inds_{tag}"] = rec[0].numpy()
+        cases[f"starts_{tag}"] = rs1.starts[..., 0].numpy()
+        cases[f"ends_{tag}"] = rs1.ends[..., 0].numpy()
+        # transmittance weights of the reference for sigma = wts*20 on the input samples
+        cases[f"tw_{tag}"] = rs0.get_weights(wts[..., None] * 20.0)[..., 0].numpy()
+        cases[f"deltas_{tag}"] = rs0.deltas[..., 0].numpy()
+    np.savez_compressed(os.path.join(OUT, "pdf_sampler.npz"), **cases)
+    print("pdf_sampler", len(cases))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    pdf_fixture()
+    render_fixture("render_transformer", "jacobian_transformer", 8, (16,), 24, wseed=11)
+    render_fixture("render_mlp", "jacobian_mlp", 6, (16,), 24, wseed=12)
+    render_fixture("render_transformer_2prop_b2", "jacobian_transformer", 8, (16, 12), 16, wseed=13, batch=2,
+                   rays_hw=(4, 6))
+    render_fixture("render_transformer_initlike", "jacobian_transformer", 8, (32,), 32, wseed=14,
+                   regime="init_like", rays_hw=(4, 4), view=0)

@@ -50,10 +50,22 @@ def synth_tensor(key: str, shape: Tuple[int, ...], seed: int, regime: str = "tra
         if "density_head.lin_out" in key:
             scale *= 0.35
         if "jacobian_head" in key or "jacobian_query_mlp" in key:
-            scale *= 1e-4 / scale if regime == "init_like" and "jacobian_head" in key else 0.5
+            if regime == "init_like" and "jacobian_head" in key:
+                scale = 1e-4          # the reference's own init (action_decoder_jacobian.py:78-83)
+            else:
+                scale *= 0.5
+            if key in ("decoder.jacobian_head.weight", "decoder.jacobian_head.lin_out.weight") and regime != "init_like":
+                scale *= 0.1          # keeps composited flows at a few pixels
         if ".to_q." in key or ".to_kv." in key or ".to_out." in key or ".net." in key:
             scale = np.sqrt(1.0 / fan_in)
         v = n() * np.float32(scale)
+        # Spectral decay over the 10 positional-encoding octaves (columns are dim-major,
+        # freq-minor, sin block then cos block then raw xyz): a trained field is smooth, a white
+        # spectrum makes every per-sample value hang on fp32 noise x 2*pi*512 (chaotic parity).
+        if regime == "trained" and (key.endswith("lin_in.weight") or key.endswith("jacobian_query_mlp.weight")):
+            decay = np.ones(shape[1], dtype=np.float32)
+            decay[:60] = 2.0 ** (-(np.arange(60) % 10)).astype(np.float32)
+            v = v * decay[None, :] * np.float32(2.0)
     elif len(shape) == 1:
         v = 0.05 * n()
         if "jacobian_head" in key and regime == "init_like":
@@ -137,7 +149,7 @@ def look_at_c2w(eye, target, up=(0.0, -1.0, 0.0)) -> torch.Tensor:
     eye = np.asarray(eye, dtype=np.float64)
     f = np.asarray(target, dtype=np.float64) - eye
     f /= np.linalg.norm(f)
-    r = np.cross(f, -np.asarray(up, dtype=np.float64))
+    r = np.cross(-np.asarray(up, dtype=np.float64), f)   # x = y(down) x z(forward)
     r /= np.linalg.norm(r)
     d = np.cross(f, r)
     m = np.eye(4)

@@ -1,0 +1,70 @@
+"""Pin the CPU oracle (oracle/njf_oracle.py) to the golden vectors produced by the UNMODIFIED
+reference (oracle/make_golden.py).  CPU-only."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, RENDER_FIXTURES, load_fixture, oracle_render, GOLDEN
+import os
+
+
+@pytest.mark.parametrize("name", RENDER_FIXTURES)
+def test_render_matches_reference(name):
+    fxt = load_fixture(name)
+    fx = fxt[0]
+    out = oracle_render(fxt)
+    # integer sample indexing: bit-exact
+    lvl = 1
+    while f"inds_{lvl}" in fx:
+        assert np.array_equal(out[f"inds_{lvl}"].numpy(), fx[f"inds_{lvl}"]), f"inds level {lvl}"
+        lvl += 1
+    tol = dict(rgb=3e-5, depth=1e-4, action_features=2e-4, steps=1e-5, weights=5e-5, ray_positions=1e-4,
+               ray_positions_warped=1e-4, final_bins=5e-6, proposal_weights=5e-5, sigma=5e-4,
+               rgb_samples=5e-4, positions=1e-5)  # per-sample values sit on the 2*pi*512*x fp32 noise floor
+    for k, atol in tol.items():
+        ref = fx[k]
+        got = out[k].numpy()
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert got.shape == ref.shape, k
+        np.testing.assert_allclose(got, ref, rtol=0, atol=atol * scale, err_msg=k)
+    ref, got = fx["jacobian"], out["jacobian"].numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=5e-4 * max(float(np.abs(ref).max()), 1e-6))
+    ref, got = fx["optical_flow"], out["optical_flow"].numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=3e-5 * max(1.0, float(np.abs(ref).max())) + 2e-2)
+
+
+@pytest.mark.parametrize("name", ["render_transformer", "render_mlp"])
+def test_encode_image_and_inverse_flow(name):
+    fx, t, head, A, s_prop, s_nerf, w = load_fixture(name)
+    out = oracle_render((fx, t, head, A, s_prop, s_nerf, w))
+    np.testing.assert_allclose(out["sigma"].numpy(), fx["enc_density"], atol=2e-4 * float(np.abs(fx["enc_density"]).max()))
+    np.testing.assert_allclose(out["positions"].numpy(), fx["enc_positions"], atol=1e-5)
+    flow = O.infer_optical_flow(t("enc_jacobian"), t("enc_weights"), t("enc_positions"), t("action2"),
+                                t("trgt_c2w"), t("trgt_k_px"))
+    np.testing.assert_allclose(flow.numpy(), fx["flow2"], atol=2e-2)
+
+
+@pytest.mark.parametrize("tag", ["16_24", "64_64", "128_128", "256_256", "48_32"])
+def test_pdf_sampler_bit_exact(tag):
+    z = np.load(os.path.join(GOLDEN, "pdf_sampler.npz"))
+    s_out = int(tag.split("_")[1])
+    bins, inds = O.pdf_resample(torch.from_numpy(z[f"w_{tag}"]), torch.from_numpy(z[f"bins_in_{tag}"]), s_out)
+    assert np.array_equal(inds.numpy(), z[f"inds_{tag}"])
+    assert np.array_equal(bins.numpy(), z[f"bins_out_{tag}"])
+    e = O.spacing_to_euclid(bins, torch.tensor(0.5), torch.tensor(3.0))
+    assert np.array_equal(e[..., :-1].numpy(), z[f"starts_{tag}"])
+    tw = O.transmittance_weights(torch.from_numpy(z[f"deltas_{tag}"])[..., None],
+                                 torch.from_numpy(z[f"w_{tag}"])[..., None] * 20.0)[..., 0]
+    assert np.array_equal(tw.numpy(), z[f"tw_{tag}"])
+
+
+def test_encodings_known_values():
+    x = torch.tensor([[0.0, 0.25, -0.5]])
+    e = O.posenc(x)
+    assert e.shape == (1, 63)
+    # dim-major, freq-minor: column 10 is sin(2*pi*0.25*2^0) = 1 ; column 30+10 its cosine = 0
+    assert abs(float(e[0, 10]) - 1.0) < 1e-6 and abs(float(e[0, 40])) < 1e-6
+    assert torch.equal(e[0, 60:], x[0])
+    s = O.sh4(torch.tensor([[0.5, 0.5, 1.0]]), fp16_round=False)  # direction (0,0,1)
+    assert abs(float(s[0, 0]) - 0.2820948) < 1e-6 and abs(float(s[0, 2]) - 0.4886025) < 1e-6
+    assert abs(float(s[0, 6]) - (0.9461747 - 0.3153916)) < 1e-6 and abs(float(s[0, 12]) - 0.3731763 * 2.0) < 1e-6
