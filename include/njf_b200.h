@@ -1,0 +1,158 @@
+/* njf_b200.h -- C ABI of libnjf_b200.so: the B200-native (sm_100a) volumetric-rendering hot path
+ * of neural-jacobian-field.
+ *
+ * The reference (sizhe-li/neural-jacobian-field) has NO native boundary: its plugin surface is
+ * the Python `Model` nn.Module plus the DENSITY_DECODERS / ACTION_DECODERS registries
+ * (project/neural_jacobian_field/models/decoder/__init__.py:11-44).  The host-side mirror
+ * (`neural-jacobian-field_b200/njf_b200`) keeps that surface and calls THIS library for all
+ * rendering arithmetic.  Every entry point cites the reference code it replaces (paths relative
+ * to project/neural_jacobian_field/).
+ *
+ * Conventions: plain pointers and sizes only; all tensors fp32, contiguous, row-major; pointers
+ * are DEVICE pointers unless a parameter says "host"; every call enqueues on `stream`
+ * (a cudaStream_t passed as void*) and returns 0 on success, non-zero on failure with a message
+ * in njf_last_error().  Nothing is allocated behind the caller's back except inside NjfField.
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef NJF_B200_H_
+#define NJF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NJF_MAX_LEVELS 4 /* proposal levels (the shipped configs use 1: rendering.num_proposal_samples=[256]) */
+
+const char* njf_last_error(void);
+int njf_version(void);
+
+/* ---- field = packed weights of the decoder + proposal networks ------------------------------
+ * Replaces: nn.Module parameter storage of ActionDecoderJacobian{MLP,Transformer}
+ * (models/decoder/action_decoder_jacobian.py:261-416) and DensityDecoderMlp
+ * (models/decoder/density_decoder.py:23-43); architecture constants are the shipped ones
+ * (configurations/model/model_allegro.yaml, model_toy_arm.yaml): ResnetFC 5 blocks x 128,
+ * combine_layer 3, 10 frequencies, geometry_feature_dim 15, transformer 64/64/8 heads/3 layers/64.
+ * Anything else is rejected. */
+typedef struct NjfField NjfField;
+
+enum { NJF_HEAD_TRANSFORMER = 0, NJF_HEAD_MLP = 1 };
+
+typedef struct NjfFieldDesc {
+  int head;          /* NJF_HEAD_*  (ACTION_DECODERS key "jacobian_transformer" / "jacobian_mlp") */
+  int action_dim;    /* A: transformer head A <= 8, MLP head A <= 10 */
+  int n_proposal;    /* number of proposal networks, 1..NJF_MAX_LEVELS */
+  int encoder_dim;   /* must be 512 (EncoderResnet.get_output_dim, models/encoder/encoder_resnet.py:88) */
+  int sh_fp16_round; /* 1: round the SH-16 direction encoding through fp16 like tiny-cuda-nn does */
+} NjfFieldDesc;
+
+typedef struct NjfTensor {
+  const char* name;  /* reference state-dict key without the "model." prefix, e.g.
+                        "decoder.density_head.lin_z.0.weight", "proposal_networks.0.density_head.lin_in.bias" */
+  const float* data; /* HOST pointer, fp32, contiguous, the module's native shape */
+  int64_t numel;
+} NjfTensor;
+
+/* Packs the named fp32 host tensors into device-resident tcgen05 operand images (fp16, K-major,
+ * 128B-swizzled), folds the cross-attention key/value projections of the index embedding, and
+ * builds the per-kernel step programs.  Synchronous. */
+int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tensors, int n_tensors, NjfField** out);
+void njf_field_destroy(NjfField* f);
+
+/* ---- hoisted feature maps ---------------------------------------------------------------------
+ * Replaces the three `lin_z[k](z)` Linear(512->128) layers of every ResnetFC
+ * (model_components/resnet_fc.py:139-143) and the 512-column part of jacobian_query_mlp
+ * (action_decoder_jacobian.py:423-430): bilinear interpolation is linear, so these layers are
+ * applied ONCE per image to the encoder output (NCHW fp32, models/encoder/encoder_resnet.py:53-86)
+ * and the render kernels gather the transformed channels.  Output: fp16 pixel-major maps. */
+size_t njf_hoisted_bytes(const NjfField* f, int B, int Hf, int Wf);
+int njf_hoist_features(const NjfField* f, const float* feat_nchw, int B, int Hf, int Wf, void* maps_out,
+                       void* stream);
+
+/* ---- cameras ---------------------------------------------------------------------------------- */
+typedef struct NjfCameras {
+  const float* ctxt_w2c;  /* [B][16] inverse of CameraInput.ctxt_extrinsics (rendering/geometry.py:59-65) */
+  const float* ctxt_k;    /* [B][9]  normalised intrinsics (pixel_aligned_features.py:21) */
+  const float* trgt_w2c;  /* [B][16] inverse of CameraInput.trgt_extrinsics (geometry.py:206-215) */
+  const float* trgt_k_px; /* [B][9]  pixel-unit intrinsics (models/model.py:305-312) */
+} NjfCameras;
+
+/* ---- Model.forward / encode_image ------------------------------------------------------------
+ * Replaces models/model.py:316-396 (forward, eval mode) and :458-495 (encode_image):
+ * ProposalNetworkSampler.generate_ray_samples (rendering/ray_samplers.py:497-552), the decoder
+ * forward (action_decoder_jacobian.py:147-215), RaySamples.get_weights (:77-101) and the
+ * render_* reductions (model.py:257-314).  Any output pointer may be NULL. */
+typedef struct NjfRenderArgs {
+  int B, R;                       /* views, rays per view */
+  int n_levels;                   /* proposal levels */
+  int s_prop[NJF_MAX_LEVELS];     /* RenderingCfg.num_proposal_samples */
+  int s_nerf;                     /* RenderingCfg.num_nerf_samples */
+  const float* origins;           /* [B][R][3] */
+  const float* dirs;              /* [B][R][3] */
+  const float* z_near;            /* [B] */
+  const float* z_far;             /* [B] */
+  const float* action;            /* [B][A] */
+  const float* bins0;             /* level-0 spacing bins: [s_prop[0]+1] shared (stride 0) or per ray */
+  int bins0_stride;               /* 0 or s_prop[0]+1 (train-mode stratified jitter comes in this way) */
+  const float* u[NJF_MAX_LEVELS]; /* PDF sample positions per resampling level: [n+1], n = next level's count */
+  int u_stride[NJF_MAX_LEVELS];   /* 0 (shared, eval mode) or n+1 (per ray, train mode) */
+  float anneal;                   /* ProposalNetworkSampler._anneal (1.0 at inference) */
+  int sum_vec_width;              /* 0: exact sum; 8/16: reproduce ATen's vectorised CPU fp32 sum order */
+  const void* maps;               /* njf_hoist_features output */
+  int Hf, Wf;
+  /* per-ray outputs */
+  float* rgb;                     /* [B][R][3]   render_rgb */
+  float* depth;                   /* [B][R][1]   render_depth (clipped to the call-global [min,max] of steps) */
+  float* flow;                    /* [B][R][2]   render_optical_flow */
+  float* jbar;                    /* [B][R][3A]  render_action_features */
+  float* p;                       /* [B][R][3]   sum w x */
+  float* pw;                      /* [B][R][3]   sum w (x + J u) */
+  /* per-sample outputs (compute_vis_features / encode_image) */
+  float* steps;                   /* [B][R][S] */
+  float* weights;                 /* [B][R][S] */
+  float* sigma;                   /* [B][R][S] */
+  float* jac;                     /* [B][R][S][3A] */
+  float* positions;               /* [B][R][S][3] */
+  float* rgb_samples;             /* [B][R][S][3] */
+  /* sampler intermediates (ModelTrainingOutput / tests) */
+  float* prop_weights[NJF_MAX_LEVELS]; /* [B][R][s_prop[l]] */
+  float* level_bins[NJF_MAX_LEVELS];   /* REQUIRED workspace: [B][R][n_l+1], bins produced by level l's PDF step */
+  int32_t* level_inds[NJF_MAX_LEVELS]; /* [B][R][n_l+1] searchsorted results */
+  float* minmax;                  /* REQUIRED workspace: 2 floats */
+} NjfRenderArgs;
+
+int njf_render_forward(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* args, void* stream);
+
+/* Stage entry points (the same kernels njf_render_forward chains; exposed for stage-wise parity). */
+int njf_proposal_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* args, int level,
+                      const float* bins_in, int bins_in_stride, void* stream);
+int njf_field_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* args, const float* bins,
+                   int bins_stride, void* stream);
+int njf_finish_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* args, void* stream);
+
+/* ---- PDFSampler alone (rendering/ray_samplers.py:351-451, eval/train u supplied by the caller) */
+int njf_pdf_sample(const float* weights, const float* bins_in, int bins_in_stride, const float* u, int u_stride,
+                   int n_rays, int s_in, int n_out, float anneal, int sum_vec_width, float* bins_out,
+                   int32_t* inds_out, void* stream);
+
+/* ---- RaySamples.get_weights alone (rendering/ray_samplers.py:77-101) */
+int njf_transmittance_weights(const float* deltas, const float* sigma, int n_rays, int s, float* weights_out,
+                              void* stream);
+
+/* ---- Model.infer_optical_flow (models/model.py:497-525) on the collapsed encoding:
+ * jbar [N][3A], p [N][3], action [B][A] (rays_per_view rays per action row) -> flow [N][2], pw [N][3] */
+int njf_flow_from_encoding(const float* jbar, const float* p, const float* action, const float* trgt_w2c,
+                           const float* trgt_k_px, int n_rays, int rays_per_view, int action_dim, float* flow,
+                           float* pw, void* stream);
+
+/* ---- self-test of the tcgen05 layer-chain machinery (tests only; weights/bias are HOST pointers) */
+int njf_selftest_chain(const float* w0, const float* w1, const float* w2, const float* w3, const float* bias,
+                       const float* a_in, const float* tz_in, float* x_out, float* y_out, int ntiles, int grid,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NJF_B200_H_ */

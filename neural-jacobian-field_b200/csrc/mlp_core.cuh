@@ -39,8 +39,10 @@ struct MmaStep {
   uint8_t kblocks;   // K / 64 (1 or 2)
   uint8_t acc;       // 1: accumulate onto d_col
   uint16_t d_col;    // TMEM column offset inside the slot
-  uint16_t pad_;
+  uint16_t flags;    // kStepReuseA: same A tile as the previous step (no a_ready wait);
+                     // kStepNoCommit: the NEXT step's commit also covers this accumulator
 };
+constexpr uint16_t kStepReuseA = 1, kStepNoCommit = 2;
 struct Program {
   int nsteps;
   MmaStep steps[kMaxSteps];
@@ -134,8 +136,10 @@ __device__ __forceinline__ void issuer_role(const CtaCtx& c, const Program& prog
       const uint32_t idesc = make_idesc_f16(st.n);
       const uint32_t w_kb_stride = static_cast<uint32_t>(st.n) * 128u;
       for (int slot = 0; slot < na; ++slot) {
-        mbar_wait(&c.bars->a_ready[slot], apar[slot]);
-        apar[slot] ^= 1u;
+        if (!(st.flags & kStepReuseA)) {
+          mbar_wait(&c.bars->a_ready[slot], apar[slot]);
+          apar[slot] ^= 1u;
+        }
         if (slot == 0) mbar_wait(&c.bars->w_full[stage], par);
         tc_fence_after();
         const uint32_t d_tmem = c.tmem_base + slot * kSlotCols + st.d_col;
@@ -150,7 +154,7 @@ __device__ __forceinline__ void issuer_role(const CtaCtx& c, const Program& prog
             acc = 1;
           }
         }
-        umma_commit(&c.bars->acc_ready[slot]);
+        if (!(st.flags & kStepNoCommit)) umma_commit(&c.bars->acc_ready[slot]);
       }
       umma_commit(&c.bars->w_empty[stage]);
     }

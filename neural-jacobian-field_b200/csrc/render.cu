@@ -1,0 +1,938 @@
+// The render kernels of libnjf_b200.so (sm_100a):
+//   proposal_kernel : uniform/PDF bins -> positions -> gather + posenc -> ResnetFC (tcgen05) ->
+//                     sigma -> transmittance weights -> PDF resampling  (one proposal level)
+//   field_kernel    : final bins -> gather + posenc -> density trunk, colour head, Jacobian head
+//                     (cross-attention or MLP) -> transmittance weights -> alpha compositing
+//   finish_kernel   : call-global depth clip, J.u flow, projection to the target camera
+//   hoist_kernel    : lin_z / query 1x1 "convolutions" applied once per image (fp32 SIMT GEMM)
+// plus the standalone sampler kernels.  See DESIGN.md for the data layout and rooflines.
+#include "render.cuh"
+#include "njf_internal.h"
+
+namespace njf {
+
+struct SlotScratch {
+  float dd[kRows];    // delta * sigma of the current tile
+  float cum[kRows];   // exclusive prefix sums (fp32) of dd
+  float wts[528];     // transmittance weights of the ray group (proposal: PDF input)
+  float cdf[544];     // PDF scratch
+};
+constexpr uint32_t kScratchSlotBytes = (sizeof(SlotScratch) + 15) & ~15u;
+constexpr uint32_t kSmemBytes = SmemMap::kScratch + kSlots * kScratchSlotBytes + 64 + 1024;
+
+__device__ __forceinline__ SlotScratch* slot_scratch(const CtaCtx& c, int slot) {
+  return reinterpret_cast<SlotScratch*>(c.smem + SmemMap::kScratch + slot * kScratchSlotBytes);
+}
+__device__ __forceinline__ uint32_t* cta_minmax(const CtaCtx& c) {
+  return reinterpret_cast<uint32_t*>(c.smem + SmemMap::kScratch + kSlots * kScratchSlotBytes);
+}
+
+// transmittance weights of this tile's rows (RaySamples.get_weights, ray_samplers.py:77-101):
+// stores dd, scans per ray (double accumulation), returns this row's weight.
+__device__ __forceinline__ float tile_weights(const EpiCtx& e, SlotScratch* sc, const PassGeom& g, int tile,
+                                              float dd, double& carry) {
+  const int wq = (threadIdx.x >> 5) & 3;
+  sc->dd[e.row] = dd;
+  named_bar_sync(1 + e.slot, kRows);
+  if (g.T == 1) {
+    for (int lr = wq; lr < g.G; lr += 4) {
+      double c0 = 0.0;
+      excl_scan_warp(sc->dd + lr * g.S, g.S, c0, sc->cum + lr * g.S);
+    }
+  } else if (wq == 0) {
+    const int n = min(kRows, g.S - tile * kRows);
+    excl_scan_warp(sc->dd, n, carry, sc->cum);
+  }
+  named_bar_sync(1 + e.slot, kRows);
+  const float tr = expf(-sc->cum[e.row]);
+  const float alpha = 1.f - expf(-dd);
+  return alpha * tr;
+}
+
+// ============================================================================= proposal pass
+struct ProposalParams {
+  Program prog;
+  const uint8_t* blob;
+  TrunkTab trunk;
+  PassGeom g;
+  int n_out;             // samples of the next level (PDF draws n_out+1 bin edges)
+  const float* u;        // [n_out+1] shared or per ray
+  int u_stride;
+  float anneal;
+  int sum_vec;
+  float* bins_out;       // [NR][n_out+1]
+  float* weights_out;    // optional [NR][S]
+  int32_t* inds_out;     // optional [NR][n_out+1]
+};
+
+__global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_constant__ ProposalParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  CtaCtx c = cta_setup(smem_raw);
+  const PassGeom& g = p.g;
+  const int warp = threadIdx.x >> 5;
+  const int nitems = (g.NG + 1) / 2;
+  int my_items = 0;
+  for (int it = blockIdx.x; it < nitems; it += gridDim.x) ++my_items;
+
+  if (warp == kLoaderWarp) {
+    if ((threadIdx.x & 31) == 0) loader_role(c, p.prog, p.blob, my_items * g.T);
+  } else if (warp == kIssuerWarp) {
+    if ((threadIdx.x & 31) == 0) {
+      const int NG = g.NG, T = g.T, bx = blockIdx.x, gx = gridDim.x;
+      issuer_role(c, p.prog, my_items * g.T, [=](int run) {
+        const int it = bx + (run / T) * gx;
+        return (2 * it + 1 < NG) ? 2 : 1;
+      });
+    }
+  } else {
+    EpiCtx e = epi_ctx(c);
+    SlotScratch* sc = slot_scratch(c, e.slot);
+    const int wq = warp & 3;
+    const int nb = p.n_out + 1;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+      const int group = 2 * it + e.slot;
+      if (group >= g.NG) continue;
+      double carry = 0.0;
+      for (int tile = 0; tile < g.T; ++tile) {
+        RowState rs;
+        row_setup(g, group, tile, e.row, rs);
+        write_posenc(e, rs.cam, rs.ray >= 0);
+        epi_publish(e);  // -> lin_in
+        gather_segment<128>(e, g, 0, rs.ix, rs.iy, rs.pixbase);
+        epi_wait_acc(e);
+        trunk_blocks_epilogue(e, g, p.trunk, 0, rs);
+        uint32_t r[16];
+        tmem_ld16(e.tmem + 128, r);
+        tmem_ld_wait();
+        // density = trunc_exp(x - 1) (density_decoder.py:64-66, activations.py:32-35)
+        const float sigma = expf(__fsub_rn(__uint_as_float(r[0]) + __ldg(p.trunk.b_out), 1.f));
+        const float dd = (rs.ray >= 0 && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
+        const float w = tile_weights(e, sc, g, tile, dd, carry);
+        if (rs.ray >= 0) {
+          sc->wts[g.T == 1 ? e.row : rs.s] = w;
+          if (p.weights_out) p.weights_out[static_cast<size_t>(rs.ray) * g.S + rs.s] = w;
+        }
+      }
+      named_bar_sync(1 + e.slot, kRows);
+      for (int lr = wq; lr < g.G; lr += 4) {
+        const int ray = group * g.G + lr;
+        if (ray >= g.NR) break;
+        pdf_resample_warp(sc->wts + lr * g.S, g.S, g.bins + static_cast<size_t>(ray) * g.bins_stride,
+                          p.u + static_cast<size_t>(ray) * p.u_stride, nb, p.anneal, p.sum_vec,
+                          sc->cdf + lr * (g.S + 1), p.bins_out + static_cast<size_t>(ray) * nb,
+                          p.inds_out ? p.inds_out + static_cast<size_t>(ray) * nb : nullptr);
+      }
+      named_bar_sync(1 + e.slot, kRows);
+    }
+  }
+  cta_teardown(c);
+}
+
+// ============================================================================= field pass
+struct FieldParams {
+  Program prog;
+  const uint8_t* blob;
+  TrunkTab dens, jac;
+  HeadTab head;
+  ColorTab color;
+  PassGeom g;
+  int head_kind;   // NJF_HEAD_*
+  int A;
+  // per-ray outputs
+  float* rgb; float* depth; float* jbar; float* p;
+  // per-sample outputs
+  float* steps; float* weights; float* sigma; float* jac_out; float* positions; float* rgb_samples;
+  uint32_t* minmax;  // [2] ordered-uint encoded min / max of steps
+};
+
+// LayerNorm(64) of x -> fp16 -> A-tile K-block 0
+__device__ __forceinline__ void ln64_to_a(const EpiCtx& e, const float (&x)[64], const float* __restrict__ gam,
+                                          const float* __restrict__ bet) {
+  float mean = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) mean += x[j];
+  mean *= (1.f / 64.f);
+  float var = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    const float d = x[j] - mean;
+    var = fmaf(d, d, var);
+  }
+  const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-5f);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = 32 * h + 2 * j;
+      const float y0 = fmaf((x[c] - mean) * rstd, __ldg(gam + c), __ldg(bet + c));
+      const float y1 = fmaf((x[c + 1] - mean) * rstd, __ldg(gam + c + 1), __ldg(bet + c + 1));
+      pk[j] = pack_f16x2(y0, y1);
+    }
+    a_store32(e, 32 * h, pk);
+  }
+}
+// load 64 accumulator columns (TMEM cols [128,192) of the slot)
+__device__ __forceinline__ void ld_acc64(const EpiCtx& e, float (&v)[64]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t r[32];
+    tmem_ld32(e.tmem + 128 + 32 * h, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[32 * h + j] = __uint_as_float(r[j]);
+  }
+}
+__device__ __forceinline__ void store64_to_a(const EpiCtx& e, const float (&v)[64]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[32 * h + 2 * j], v[32 * h + 2 * j + 1]);
+    a_store32(e, 32 * h, pk);
+  }
+}
+
+template <int A>
+__device__ __forceinline__ void softmax_heads(float (&lg)[64]) {
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    float m = -3.0e38f;
+#pragma unroll
+    for (int a = 0; a < A; ++a) m = fmaxf(m, lg[h * A + a]);
+    float s = 0.f;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      const float ev = expf(lg[h * A + a] - m);
+      lg[h * A + a] = ev;
+      s += ev;
+    }
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int a = 0; a < A; ++a) lg[h * A + a] *= inv;
+  }
+#pragma unroll
+  for (int j = 8 * A; j < 64; ++j) lg[j] = 0.f;
+}
+
+// Cross-attention Jacobian head (action_decoder_jacobian.py:418-446; transformer.py:63-135) with
+// the key/value projections folded into M1/M2 by njf_field_create.  Pre: accumulator wait for
+// (lin_in, q_enc) done; the 64 hoisted query channels are in the staging buffer.
+__device__ __forceinline__ void transformer_head(EpiCtx& e, const HeadTab& H, int A, const RowState& rs,
+                                                 float (&J)[32]) {
+  float x[64];
+  ld_acc64(e, x);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(e.tz + tz_offset(e.row, j));
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __half22float2(h[t]);
+      x[8 * j + 2 * t] += f.x;
+      x[8 * j + 2 * t + 1] += f.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    const float4 q = __ldg(H.q_e0 + j);
+    x[j] += fmaf(q.z, rs.cam[2], fmaf(q.y, rs.cam[1], fmaf(q.x, rs.cam[0], q.w)));
+  }
+#pragma unroll 1
+  for (int l = 0; l < 3; ++l) {
+    const XfLayerTab& L = H.layer[l];
+    ln64_to_a(e, x, L.ln1_g, L.ln1_b);
+    epi_publish(e);  // -> M1: scaled logits over (head, key)
+    epi_wait_acc(e);
+    {
+      float lg[64];
+      ld_acc64(e, lg);
+      // softmax over the A keys of each of the 8 heads; columns >= 8A are padding
+      switch (A) {
+        case 1: softmax_heads<1>(lg); break;
+        case 2: softmax_heads<2>(lg); break;
+        case 3: softmax_heads<3>(lg); break;
+        case 4: softmax_heads<4>(lg); break;
+        case 5: softmax_heads<5>(lg); break;
+        case 6: softmax_heads<6>(lg); break;
+        case 7: softmax_heads<7>(lg); break;
+        default: softmax_heads<8>(lg); break;
+      }
+      store64_to_a(e, lg);
+    }
+    epi_publish(e);  // -> M2: attention . (V W_out)
+    epi_wait_acc(e);
+    {
+      float t[64];
+      ld_acc64(e, t);
+#pragma unroll
+      for (int j = 0; j < 64; ++j) x[j] += t[j] + __ldg(L.b_o + j);
+    }
+    ln64_to_a(e, x, L.ln2_g, L.ln2_b);
+    epi_publish(e);  // -> W1
+    epi_wait_acc(e);
+    {
+      float t[64];
+      ld_acc64(e, t);
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const float v = t[j] + __ldg(L.b_1 + j);
+        t[j] = 0.5f * v * (1.f + erff(v * 0.70710678f));  // exact GELU (nn.GELU default)
+      }
+      store64_to_a(e, t);
+    }
+    epi_publish(e);  // -> W2
+    epi_wait_acc(e);
+    {
+      float t[64];
+      ld_acc64(e, t);
+#pragma unroll
+      for (int j = 0; j < 64; ++j) x[j] += t[j] + __ldg(L.b_2 + j);
+    }
+  }
+  store64_to_a(e, x);
+  epi_publish(e);  // -> jacobian_head Linear(64, 3A)
+  epi_wait_acc(e);
+  uint32_t r[32];
+  tmem_ld32(e.tmem + 128, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) J[j] = __uint_as_float(r[j]) + __ldg(H.b_head + j);
+}
+
+// SH degree 4 (tiny-cuda-nn convention) of the unit direction (action_decoder_jacobian.py:194-199)
+__device__ __forceinline__ void sh16(float dx, float dy, float dz, float (&o)[16]) {
+  // get_normalized_directions then tcnn's internal x*2-1
+  const float x = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(dx, 1.f), 0.5f), 2.f), 1.f);
+  const float y = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(dy, 1.f), 0.5f), 2.f), 1.f);
+  const float z = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(dz, 1.f), 0.5f), 2.f), 1.f);
+  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  o[0] = 0.28209479177387814f;
+  o[1] = -0.48860251190291987f * y;
+  o[2] = 0.48860251190291987f * z;
+  o[3] = -0.48860251190291987f * x;
+  o[4] = 1.0925484305920792f * xy;
+  o[5] = -1.0925484305920792f * yz;
+  o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  o[7] = -1.0925484305920792f * xz;
+  o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+  o[10] = 2.8906114426405538f * xy * z;
+  o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+  o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+  o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+  o[14] = 1.4453057213202769f * z * (x2 - y2);
+  o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constant__ FieldParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  CtaCtx c = cta_setup(smem_raw);
+  const PassGeom& g = p.g;
+  const int warp = threadIdx.x >> 5;
+  const int nitems = (g.NG + 1) / 2;
+  int my_items = 0;
+  for (int it = blockIdx.x; it < nitems; it += gridDim.x) ++my_items;
+  uint32_t* mm = cta_minmax(c);
+  if (threadIdx.x == 0) {
+    mm[0] = 0xffffffffu;
+    mm[1] = 0u;
+  }
+  __syncthreads();
+
+  if (warp == kLoaderWarp) {
+    if ((threadIdx.x & 31) == 0) loader_role(c, p.prog, p.blob, my_items * g.T);
+  } else if (warp == kIssuerWarp) {
+    if ((threadIdx.x & 31) == 0) {
+      const int NG = g.NG, T = g.T, bx = blockIdx.x, gx = gridDim.x;
+      issuer_role(c, p.prog, my_items * g.T, [=](int run) {
+        const int it = bx + (run / T) * gx;
+        return (2 * it + 1 < NG) ? 2 : 1;
+      });
+    }
+  } else {
+    EpiCtx e = epi_ctx(c);
+    SlotScratch* sc = slot_scratch(c, e.slot);
+    const int wq = warp & 3;
+    const int lane = threadIdx.x & 31;
+    const int A = p.A, A3 = 3 * p.A;
+    const int nch = 8 + A3;  // composite channels: rgb3, t, 1, pos3, J(3A)
+    // e.tz doubles as the composite staging buffer: [128 rows][64 fp32], 16 B chunks XOR-swizzled by row
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+      const int group = 2 * it + e.slot;
+      if (group >= g.NG) continue;
+      double carry = 0.0;
+      float cs0 = 0.f, cs1 = 0.f;  // column sums held by warp 0 across the tiles of a long ray
+      for (int tile = 0; tile < g.T; ++tile) {
+        RowState rs;
+        row_setup(g, group, tile, e.row, rs);
+        const bool valid = rs.ray >= 0;
+        float J[32];
+        write_posenc(e, rs.cam, valid);
+        epi_publish(e);  // -> lin_in (+ q_enc for the transformer head)
+        if (p.head_kind == NJF_HEAD_TRANSFORMER) {
+          gather_segment<64>(e, g, 384, rs.ix, rs.iy, rs.pixbase);
+          epi_wait_acc(e);
+          transformer_head(e, p.head, A, rs, J);
+        }
+        gather_segment<128>(e, g, 0, rs.ix, rs.iy, rs.pixbase);
+        if (p.head_kind != NJF_HEAD_TRANSFORMER) epi_wait_acc(e);
+        trunk_blocks_epilogue(e, g, p.dens, 0, rs);
+        // lin_out: 15 geometry features + density pre-activation (action_decoder_jacobian.py:106-112)
+        float geo[16];
+        {
+          uint32_t r[16];
+          tmem_ld16(e.tmem + 128, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) geo[j] = __uint_as_float(r[j]) + __ldg(p.dens.b_out + j);
+        }
+        const float sigma = expf(__fsub_rn(geo[15], 1.f));
+        // colour head input [geo15 | sh16 | 0...] (action_decoder_jacobian.py:208)
+        {
+          float sh[16];
+          const float* dp = g.dirs + static_cast<size_t>(valid ? rs.ray : 0) * 3;
+          sh16(__ldg(dp), __ldg(dp + 1), __ldg(dp + 2), sh);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) pk[j] = pack_f16x2(geo[2 * j], geo[2 * j + 1]);
+          pk[7] = pack_f16x2(geo[14], sh[0]);
+#pragma unroll
+          for (int j = 0; j < 7; ++j) pk[8 + j] = pack_f16x2(sh[1 + 2 * j], sh[2 + 2 * j]);
+          pk[15] = pack_f16x2(sh[15], 0.f);
+          a_store32(e, 0, pk);
+          a_zero32(e, 32);
+        }
+        epi_publish(e);  // -> color1
+        epi_wait_acc(e);
+        for (int c0 = 0; c0 < 64; c0 += 32) epi_relu_to_a(e, 128 + c0, c0, p.color.b1);
+        epi_publish(e);  // -> color2
+        epi_wait_acc(e);
+        float rgb[3];
+        {
+          float h2[64];
+          ld_acc64(e, h2);
+#pragma unroll
+          for (int j = 0; j < 64; ++j) h2[j] = fmaxf(h2[j] + __ldg(p.color.b2 + j), 0.f);
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            float a = __ldg(p.color.b3 + ch);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) a = fmaf(__ldg(p.color.w3 + ch * 64 + j), h2[j], a);
+            rgb[ch] = 1.f / (1.f + expf(-a));
+          }
+        }
+        if (p.head_kind == NJF_HEAD_MLP) {
+          // second ResnetFC on the same gathered point (action_decoder_jacobian.py:324-337)
+          write_posenc(e, rs.cam, valid);
+          epi_publish(e);  // -> lin_in (jacobian head)
+          gather_segment<128>(e, g, 384, rs.ix, rs.iy, rs.pixbase);
+          epi_wait_acc(e);
+          trunk_blocks_epilogue(e, g, p.jac, 384, rs);
+          uint32_t r[32];
+          tmem_ld32(e.tmem + 128, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) J[j] = __uint_as_float(r[j]) + __ldg(p.jac.b_out + j);
+        }
+        // ---- weights + compositing (model.py:351-367, 384-394)
+        const float dd = (valid && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
+        const float w = tile_weights(e, sc, g, tile, dd, carry);
+        if (valid) {
+          const size_t si = static_cast<size_t>(rs.ray) * g.S + rs.s;
+          if (p.steps) p.steps[si] = rs.tmid;
+          if (p.weights) p.weights[si] = w;
+          if (p.sigma) p.sigma[si] = sigma;
+          if (p.positions) {
+            p.positions[si * 3 + 0] = rs.pos[0];
+            p.positions[si * 3 + 1] = rs.pos[1];
+            p.positions[si * 3 + 2] = rs.pos[2];
+          }
+          if (p.rgb_samples) {
+            p.rgb_samples[si * 3 + 0] = rgb[0];
+            p.rgb_samples[si * 3 + 1] = rgb[1];
+            p.rgb_samples[si * 3 + 2] = rgb[2];
+          }
+          if (p.jac_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < A3) p.jac_out[si * A3 + j] = J[j];
+          }
+        }
+        {
+          // stage w * [rgb, t, 1, pos, J] for the per-ray column sums
+          float v[64];
+          v[0] = rgb[0]; v[1] = rgb[1]; v[2] = rgb[2]; v[3] = rs.tmid; v[4] = 1.f;
+          v[5] = rs.pos[0]; v[6] = rs.pos[1]; v[7] = rs.pos[2];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[8 + j] = (j < A3) ? J[j] : 0.f;
+#pragma unroll
+          for (int j = 40; j < 64; ++j) v[j] = 0.f;
+          const float ww = valid ? w : 0.f;
+          uint8_t* rowp = e.tz + e.row * 256;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            float4 o;
+            o.x = valid ? ww * v[4 * q + 0] : 0.f;
+            o.y = valid ? ww * v[4 * q + 1] : 0.f;
+            o.z = valid ? ww * v[4 * q + 2] : 0.f;
+            o.w = valid ? ww * v[4 * q + 3] : 0.f;
+            *reinterpret_cast<float4*>(rowp + ((q ^ (e.row & 7)) << 4)) = o;
+          }
+          // min / max of steps over valid samples (render_depth's clip range, model.py:277)
+          float tmn = valid ? rs.tmid : 3.0e38f, tmx = valid ? rs.tmid : -3.0e38f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            tmn = fminf(tmn, __shfl_xor_sync(0xffffffffu, tmn, o));
+            tmx = fmaxf(tmx, __shfl_xor_sync(0xffffffffu, tmx, o));
+          }
+          if (lane == 0 && tmn <= tmx) {
+            atomicMin(&mm[0], f2ord(tmn));
+            atomicMax(&mm[1], f2ord(tmx));
+          }
+        }
+        named_bar_sync(1 + e.slot, kRows);
+        auto colsum = [&](int r0, int n, float& s0, float& s1) {
+          for (int r = r0; r < r0 + n; ++r) {
+            const uint8_t* rp = e.tz + r * 256;
+            s0 += *reinterpret_cast<const float*>(rp + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+            if (nch > 32)
+              s1 += *reinterpret_cast<const float*>(rp + (((8 + (lane >> 2)) ^ (r & 7)) << 4) + (lane & 3) * 4);
+          }
+        };
+        auto emit = [&](int ray, float s0, float s1) {
+          // channel of this lane: s0 -> lane, s1 -> 32 + lane
+          const float num = __shfl_sync(0xffffffffu, s0, 3), den = __shfl_sync(0xffffffffu, s0, 4);
+          if (lane < 3 && p.rgb) p.rgb[static_cast<size_t>(ray) * 3 + lane] = s0;
+          if (lane == 3 && p.depth) p.depth[ray] = num / (den + 1e-10f);
+          if (lane >= 5 && lane < 8 && p.p) p.p[static_cast<size_t>(ray) * 3 + (lane - 5)] = s0;
+          if (p.jbar) {
+            if (lane >= 8 && lane - 8 < A3) p.jbar[static_cast<size_t>(ray) * A3 + (lane - 8)] = s0;
+            if (24 + lane < A3) p.jbar[static_cast<size_t>(ray) * A3 + 24 + lane] = s1;
+          }
+        };
+        if (g.T == 1) {
+          for (int lr = wq; lr < g.G; lr += 4) {
+            const int ray = group * g.G + lr;
+            if (ray >= g.NR) break;
+            float s0 = 0.f, s1 = 0.f;
+            colsum(lr * g.S, g.S, s0, s1);
+            emit(ray, s0, s1);
+          }
+        } else if (wq == 0) {
+          colsum(0, min(kRows, g.S - tile * kRows), cs0, cs1);
+          if (tile == g.T - 1 && group < g.NR) emit(group, cs0, cs1);
+        }
+        named_bar_sync(1 + e.slot, kRows);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && p.minmax) {
+    if (mm[0] != 0xffffffffu) atomicMin(&p.minmax[0], mm[0]);
+    if (mm[1] != 0u) atomicMax(&p.minmax[1], mm[1]);
+  }
+  cta_teardown(c);
+}
+
+// ============================================================================= small kernels
+__global__ void init_minmax_kernel(uint32_t* mm) {
+  mm[0] = 0xffffffffu;
+  mm[1] = 0u;
+}
+
+// depth clip + optical flow (model.py:271-279, 288-314; geometry.py:206-215)
+struct FinishParams {
+  int NR, R, A;
+  const float* action;    // [B][A]
+  const float* trgt_w2c;  // [B][16]
+  const float* trgt_k;    // [B][9] pixel units
+  const uint32_t* minmax;
+  float* depth;
+  const float* jbar;
+  const float* p;
+  float* pw;
+  float* flow;
+};
+__device__ __forceinline__ void project_uv(const float* W, const float* K, float x, float y, float z, float& u,
+                                           float& v) {
+  float c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c[i] = fmaf(W[4 * i + 2], z, fmaf(W[4 * i + 1], y, fmaf(W[4 * i], x, W[4 * i + 3])));
+  const float a = fmaf(K[2], c[2], fmaf(K[1], c[1], K[0] * c[0]));
+  const float b = fmaf(K[5], c[2], fmaf(K[4], c[1], K[3] * c[0]));
+  const float w = fmaf(K[8], c[2], fmaf(K[7], c[1], K[6] * c[0]));
+  const float zd = __fadd_rn(w, 1e-9f);
+  u = __fdiv_rn(a, zd);
+  v = __fdiv_rn(b, zd);
+}
+__global__ void finish_kernel(const FinishParams q) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= q.NR) return;
+  const int b = ray / q.R;
+  if (q.depth && q.minmax) {
+    const float lo = ord2f(q.minmax[0]), hi = ord2f(q.minmax[1]);
+    q.depth[ray] = fminf(fmaxf(q.depth[ray], lo), hi);
+  }
+  if (!q.p || !q.jbar) return;
+  const float px = q.p[ray * 3], py = q.p[ray * 3 + 1], pz = q.p[ray * 3 + 2];
+  float f[3] = {0.f, 0.f, 0.f};
+  for (int a = 0; a < q.A; ++a) {
+    const float ua = __ldg(q.action + b * q.A + a);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) f[d] = fmaf(q.jbar[static_cast<size_t>(ray) * 3 * q.A + a * 3 + d], ua, f[d]);
+  }
+  const float wx = px + f[0], wy = py + f[1], wz = pz + f[2];
+  if (q.pw) {
+    q.pw[ray * 3] = wx;
+    q.pw[ray * 3 + 1] = wy;
+    q.pw[ray * 3 + 2] = wz;
+  }
+  if (q.flow) {
+    float u0, v0, u1, v1;
+    project_uv(q.trgt_w2c + b * 16, q.trgt_k + b * 9, px, py, pz, u0, v0);
+    project_uv(q.trgt_w2c + b * 16, q.trgt_k + b * 9, wx, wy, wz, u1, v1);
+    q.flow[ray * 2] = u1 - u0;
+    q.flow[ray * 2 + 1] = v1 - v0;
+  }
+}
+
+// hoisted maps: out[b][px][n] = fp16( sum_c W[n][c] * feat[b][c][px] + bias[n] ), n in [n0, n0+CH)
+// classic 128x128x16 SIMT tile, 256 threads, 8x8 outputs per thread.
+__global__ void __launch_bounds__(256) hoist_kernel(const float* __restrict__ feat, const float* __restrict__ Wt,
+                                                    const float* __restrict__ bias, __half* __restrict__ out,
+                                                    int HW, int CH, int n0) {
+  __shared__ float sF[16][128 + 4];
+  __shared__ float sW[16][128 + 4];
+  const int b = blockIdx.z;
+  const int px0 = blockIdx.x * 128, nn0 = blockIdx.y * 128;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // tx: 8 px, ty: 8 n
+  const float* F = feat + static_cast<size_t>(b) * 512 * HW;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < 512; k0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 128; i += 256) {
+      const int kk = i >> 7, pp = i & 127;
+      const int px = px0 + pp;
+      sF[kk][pp] = (px < HW) ? F[static_cast<size_t>(k0 + kk) * HW + px] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 16 * 128; i += 256) {
+      const int nn = i >> 4, kk = i & 15;
+      const int n = nn0 + nn;
+      sW[kk][nn] = (n < CH) ? Wt[static_cast<size_t>(n0 + n) * 512 + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float fv[8], wv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) fv[i] = sF[kk][tx * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = sW[kk][ty * 8 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(fv[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int px = px0 + tx * 8 + i;
+    if (px >= HW) continue;
+    const int n = nn0 + ty * 8;
+    if (n >= CH) continue;  // CH is a multiple of 8
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      ow[j] = pack_f16x2(acc[i][2 * j] + __ldg(bias + n0 + n + 2 * j), acc[i][2 * j + 1] + __ldg(bias + n0 + n + 2 * j + 1));
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * HW + px) * CH + n) = o;
+  }
+}
+
+// standalone PDFSampler: one warp per ray
+__global__ void pdf_kernel(const float* weights, const float* bins_in, int bins_stride, const float* u, int u_stride,
+                           int n_rays, int S, int n_out, float anneal, int sum_vec, float* bins_out,
+                           int32_t* inds_out) {
+  extern __shared__ float sm[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * (blockDim.x >> 5) + wib;
+  float* w = sm + wib * (2 * S + 8);
+  float* cdf = w + S;
+  if (ray >= n_rays) return;
+  for (int j = lane; j < S; j += 32) w[j] = weights[static_cast<size_t>(ray) * S + j];
+  __syncwarp();
+  const int nb = n_out + 1;
+  pdf_resample_warp(w, S, bins_in + static_cast<size_t>(ray) * bins_stride, u + static_cast<size_t>(ray) * u_stride,
+                    nb, anneal, sum_vec, cdf, bins_out + static_cast<size_t>(ray) * nb,
+                    inds_out ? inds_out + static_cast<size_t>(ray) * nb : nullptr);
+}
+
+// standalone RaySamples.get_weights: one warp per ray
+__global__ void tw_kernel(const float* deltas, const float* sigma, int n_rays, int S, float* out) {
+  extern __shared__ float sm[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * (blockDim.x >> 5) + wib;
+  float* dd = sm + wib * 2 * S;
+  float* cum = dd + S;
+  if (ray >= n_rays) return;
+  for (int j = lane; j < S; j += 32) {
+    const float d = deltas[static_cast<size_t>(ray) * S + j];
+    dd[j] = d > 0.f ? __fmul_rn(d, sigma[static_cast<size_t>(ray) * S + j]) : 0.f;
+  }
+  __syncwarp();
+  double carry = 0.0;
+  excl_scan_warp(dd, S, carry, cum);
+  __syncwarp();
+  for (int j = lane; j < S; j += 32) out[static_cast<size_t>(ray) * S + j] = (1.f - expf(-dd[j])) * expf(-cum[j]);
+}
+
+}  // namespace njf
+
+// ============================================================================= host launchers
+using namespace njf;
+
+namespace {
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+int make_geom(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a, int S, const float* bins,
+              int bins_stride, const __half* map, int CH, PassGeom& g) {
+  if (S < 1 || S > 512) NJF_FAIL("samples per ray %d unsupported (1..512)", S);
+  g.NR = a->B * a->R;
+  g.R = a->R;
+  g.S = S;
+  g.G = S <= kRows ? kRows / S : 1;
+  g.T = S <= kRows ? 1 : (S + kRows - 1) / kRows;
+  g.NG = (g.NR + g.G - 1) / g.G;
+  g.origins = a->origins;
+  g.dirs = a->dirs;
+  g.z_near = a->z_near;
+  g.z_far = a->z_far;
+  g.bins = bins;
+  g.bins_stride = bins_stride;
+  g.ctxt_w2c = cams->ctxt_w2c;
+  g.ctxt_k = cams->ctxt_k;
+  g.map = map;
+  g.CH = CH;
+  g.Hf = a->Hf;
+  g.Wf = a->Wf;
+  (void)f;
+  return 0;
+}
+
+const __half* map_of(const NjfField* f, const NjfRenderArgs* a, int level /* -1 = main */) {
+  const size_t px = static_cast<size_t>(a->B) * a->Hf * a->Wf;
+  const __half* base = static_cast<const __half*>(a->maps);
+  if (level < 0) return base + px * f->ch_prop * f->desc.n_proposal;
+  return base + px * f->ch_prop * level;
+}
+
+int check_args(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a) {
+  if (!f || !cams || !a) NJF_FAIL("null argument");
+  if (a->B < 1 || a->R < 1) NJF_FAIL("B=%d R=%d: nothing to render", a->B, a->R);
+  if (a->n_levels != f->desc.n_proposal) NJF_FAIL("n_levels %d != field n_proposal %d", a->n_levels, f->desc.n_proposal);
+  if (!a->origins || !a->dirs || !a->z_near || !a->z_far || !a->maps) NJF_FAIL("missing ray / map input");
+  if (static_cast<size_t>(a->B) * a->Hf * a->Wf >= (1u << 30)) NJF_FAIL("feature map too large");
+  return 0;
+}
+
+template <class K>
+int set_smem(K kernel) {
+  static bool done = false;
+  if (!done) {
+    NJF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes)));
+    done = true;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t njf_hoisted_bytes(const NjfField* f, int B, int Hf, int Wf) {
+  return static_cast<size_t>(B) * Hf * Wf * f->ch_total * sizeof(__half);
+}
+
+extern "C" int njf_hoist_features(const NjfField* f, const float* feat_nchw, int B, int Hf, int Wf, void* maps_out,
+                                  void* stream_) {
+  if (!f || !feat_nchw || !maps_out) NJF_FAIL("njf_hoist_features: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int HW = Hf * Wf;
+  __half* out = static_cast<__half*>(maps_out);
+  int n0 = 0;
+  for (int m = 0; m <= f->desc.n_proposal; ++m) {
+    const int CH = (m < f->desc.n_proposal) ? f->ch_prop : f->ch_main;
+    dim3 grid((HW + 127) / 128, (CH + 127) / 128, B);
+    hoist_kernel<<<grid, 256, 0, stream>>>(feat_nchw, f->d_hoist_w, f->d_hoist_b, out, HW, CH, n0);
+    NJF_CUDA(cudaGetLastError());
+    out += static_cast<size_t>(B) * HW * CH;
+    n0 += CH;
+  }
+  return 0;
+}
+
+extern "C" int njf_proposal_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a, int level,
+                                 const float* bins_in, int bins_in_stride, void* stream_) {
+  if (check_args(f, cams, a)) return 1;
+  if (level < 0 || level >= a->n_levels) NJF_FAIL("level %d out of range", level);
+  if (!a->level_bins[level] || !a->u[level]) NJF_FAIL("level_bins[%d] / u[%d] required", level, level);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ProposalParams p{};
+  p.prog = f->prop_prog[level];
+  p.blob = f->prop_blob[level];
+  p.trunk = f->prop_trunk[level];
+  if (make_geom(f, cams, a, a->s_prop[level], bins_in, bins_in_stride, map_of(f, a, level), f->ch_prop, p.g)) return 1;
+  p.n_out = (level + 1 < a->n_levels) ? a->s_prop[level + 1] : a->s_nerf;
+  if (p.n_out < 1 || p.n_out > 512) NJF_FAIL("n_out %d unsupported", p.n_out);
+  p.u = a->u[level];
+  p.u_stride = a->u_stride[level];
+  p.anneal = a->anneal;
+  p.sum_vec = a->sum_vec_width;
+  p.bins_out = a->level_bins[level];
+  p.weights_out = a->prop_weights[level];
+  p.inds_out = a->level_inds[level];
+  if (set_smem(proposal_kernel)) return 1;
+  const int nitems = (p.g.NG + 1) / 2;
+  const int grid = nitems < num_sms() ? nitems : num_sms();
+  proposal_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  NJF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a, const float* bins,
+                              int bins_stride, void* stream_) {
+  if (check_args(f, cams, a)) return 1;
+  if (!a->minmax) NJF_FAIL("minmax workspace required");
+  if (!a->action) NJF_FAIL("action required");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FieldParams p{};
+  p.prog = f->field_prog;
+  p.blob = f->field_blob;
+  p.dens = f->dens_trunk;
+  p.jac = f->jac_trunk;
+  p.head = f->head;
+  p.color = f->color;
+  if (make_geom(f, cams, a, a->s_nerf, bins, bins_stride, map_of(f, a, -1), f->ch_main, p.g)) return 1;
+  p.head_kind = f->desc.head;
+  p.A = f->desc.action_dim;
+  p.rgb = a->rgb;
+  p.depth = a->depth;
+  p.jbar = a->jbar;
+  p.p = a->p;
+  p.steps = a->steps;
+  p.weights = a->weights;
+  p.sigma = a->sigma;
+  p.jac_out = a->jac;
+  p.positions = a->positions;
+  p.rgb_samples = a->rgb_samples;
+  p.minmax = reinterpret_cast<uint32_t*>(a->minmax);
+  init_minmax_kernel<<<1, 1, 0, stream>>>(p.minmax);
+  if (set_smem(field_kernel)) return 1;
+  const int nitems = (p.g.NG + 1) / 2;
+  const int grid = nitems < num_sms() ? nitems : num_sms();
+  field_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  NJF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int njf_finish_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a, void* stream_) {
+  if (check_args(f, cams, a)) return 1;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FinishParams q{};
+  q.NR = a->B * a->R;
+  q.R = a->R;
+  q.A = f->desc.action_dim;
+  q.action = a->action;
+  q.trgt_w2c = cams->trgt_w2c;
+  q.trgt_k = cams->trgt_k_px;
+  q.minmax = reinterpret_cast<const uint32_t*>(a->minmax);
+  q.depth = a->depth;
+  q.jbar = a->jbar;
+  q.p = a->p;
+  q.pw = a->pw;
+  q.flow = a->flow;
+  if ((q.flow || q.pw) && (!q.jbar || !q.p || !q.action || !q.trgt_w2c || !q.trgt_k))
+    NJF_FAIL("flow / pw outputs need jbar, p, action and the target camera");
+  finish_kernel<<<(q.NR + 255) / 256, 256, 0, stream>>>(q);
+  NJF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int njf_render_forward(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a, void* stream) {
+  if (check_args(f, cams, a)) return 1;
+  if (!a->bins0) NJF_FAIL("bins0 required");
+  const float* bins = a->bins0;
+  int stride = a->bins0_stride;
+  for (int l = 0; l < a->n_levels; ++l) {
+    if (njf_proposal_pass(f, cams, a, l, bins, stride, stream)) return 1;
+    bins = a->level_bins[l];
+    stride = ((l + 1 < a->n_levels) ? a->s_prop[l + 1] : a->s_nerf) + 1;
+  }
+  if (njf_field_pass(f, cams, a, bins, stride, stream)) return 1;
+  return njf_finish_pass(f, cams, a, stream);
+}
+
+extern "C" int njf_pdf_sample(const float* weights, const float* bins_in, int bins_in_stride, const float* u,
+                              int u_stride, int n_rays, int s_in, int n_out, float anneal, int sum_vec_width,
+                              float* bins_out, int32_t* inds_out, void* stream_) {
+  if (!weights || !bins_in || !u || !bins_out) NJF_FAIL("njf_pdf_sample: null argument");
+  if (s_in < 1 || s_in > 4096 || n_out < 1) NJF_FAIL("njf_pdf_sample: bad sizes");
+  if (n_rays == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int wpb = 4;
+  const size_t smem = static_cast<size_t>(wpb) * (2 * s_in + 8) * sizeof(float);
+  pdf_kernel<<<(n_rays + wpb - 1) / wpb, wpb * 32, smem, stream>>>(weights, bins_in, bins_in_stride, u, u_stride,
+                                                                 n_rays, s_in, n_out, anneal, sum_vec_width,
+                                                                 bins_out, inds_out);
+  NJF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int njf_transmittance_weights(const float* deltas, const float* sigma, int n_rays, int s,
+                                         float* weights_out, void* stream_) {
+  if (!deltas || !sigma || !weights_out) NJF_FAIL("njf_transmittance_weights: null argument");
+  if (s < 1 || s > 4096) NJF_FAIL("njf_transmittance_weights: bad sizes");
+  if (n_rays == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int wpb = 4;
+  tw_kernel<<<(n_rays + wpb - 1) / wpb, wpb * 32, static_cast<size_t>(wpb) * 2 * s * sizeof(float), stream>>>(
+      deltas, sigma, n_rays, s, weights_out);
+  NJF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int njf_flow_from_encoding(const float* jbar, const float* p, const float* action, const float* trgt_w2c,
+                                      const float* trgt_k_px, int n_rays, int rays_per_view, int action_dim,
+                                      float* flow, float* pw, void* stream_) {
+  if (!jbar || !p || !action || !trgt_w2c || !trgt_k_px) NJF_FAIL("njf_flow_from_encoding: null argument");
+  if (n_rays == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FinishParams q{};
+  q.NR = n_rays;
+  q.R = rays_per_view;
+  q.A = action_dim;
+  q.action = action;
+  q.trgt_w2c = trgt_w2c;
+  q.trgt_k = trgt_k_px;
+  q.jbar = jbar;
+  q.p = p;
+  q.pw = pw;
+  q.flow = flow;
+  finish_kernel<<<(n_rays + 255) / 256, 256, 0, stream>>>(q);
+  NJF_CUDA(cudaGetLastError());
+  return 0;
+}

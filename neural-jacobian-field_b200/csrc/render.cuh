@@ -1,0 +1,381 @@
+// Device-side building blocks of the render kernels: per-row ray/sample geometry, positional
+// encoding into the tcgen05 A tile, the warp-cooperative bilinear gather of hoisted feature
+// channels, the ResnetFC trunk driver, and the per-ray scan / PDF-resampling routines.
+#pragma once
+#include "field.h"
+
+namespace njf {
+
+// ----------------------------------------------------------------------------- pass geometry
+struct PassGeom {
+  int NR;   // total rays (B*R)
+  int R;    // rays per view
+  int S;    // samples per ray in this pass
+  int G;    // rays per 128-row tile (S <= 128) else 1
+  int T;    // tiles per ray group (ceil(S/128) when S > 128) else 1
+  int NG;   // ray groups = ceil(NR / G)
+  const float* origins;   // [NR][3]
+  const float* dirs;      // [NR][3]
+  const float* z_near;    // [B]
+  const float* z_far;     // [B]
+  const float* bins;      // spacing-domain bin edges, [S+1] shared or per ray
+  int bins_stride;        // 0 or S+1
+  const float* ctxt_w2c;  // [B][16]
+  const float* ctxt_k;    // [B][9]
+  const __half* map;      // hoisted map of this pass [B][Hf*Wf][CH]
+  int CH, Hf, Wf;
+};
+
+struct RowState {
+  float pos[3];   // world-space sample position (RaySamples.get_positions, ray_samplers.py:48-55)
+  float cam[3];   // context-camera coordinates (what the positional encoding sees)
+  float tmid;     // (start+end)/2
+  float delta;    // end-start
+  float ix, iy;   // border-clamped, un-normalised feature-map coordinates
+  int pixbase;    // view*Hf*Wf, or -1 for a padding row
+  int ray;        // global ray index or -1
+  int s;          // sample index along the ray
+};
+
+// All arithmetic that decides sample placement mirrors the reference op for op (explicit
+// round-to-nearest intrinsics so that nvcc cannot contract mul+add into fma).
+__device__ __forceinline__ void row_setup(const PassGeom& g, int group, int tile, int row, RowState& rs) {
+  int lr, s;
+  if (g.T == 1) {
+    lr = row / g.S;
+    s = row - lr * g.S;
+    if (lr >= g.G) lr = -1;
+  } else {
+    lr = 0;
+    s = tile * kRows + row;
+    if (s >= g.S) lr = -1;
+  }
+  const int ray = (lr < 0) ? -1 : group * g.G + lr;
+  rs.s = s;
+  if (ray < 0 || ray >= g.NR) {
+    rs.ray = -1;
+    rs.pixbase = -1;
+    rs.tmid = 0.f;
+    rs.delta = 0.f;
+    rs.ix = rs.iy = 0.f;
+    rs.pos[0] = rs.pos[1] = rs.pos[2] = 0.f;
+    rs.cam[0] = rs.cam[1] = rs.cam[2] = 0.f;
+    return;
+  }
+  rs.ray = ray;
+  const int b = ray / g.R;
+  const float* bp = g.bins + static_cast<size_t>(ray) * g.bins_stride;
+  const float b0 = __ldg(bp + s), b1 = __ldg(bp + s + 1);
+  const float nr = __ldg(g.z_near + b), fr = __ldg(g.z_far + b);
+  // spacing -> euclidean: x * s_far + (1 - x) * s_near  (ray_samplers.py:242-245)
+  const float st = __fadd_rn(__fmul_rn(b0, fr), __fmul_rn(__fsub_rn(1.f, b0), nr));
+  const float en = __fadd_rn(__fmul_rn(b1, fr), __fmul_rn(__fsub_rn(1.f, b1), nr));
+  const float se = __fadd_rn(st, en);
+  rs.tmid = __fmul_rn(se, 0.5f);
+  rs.delta = __fsub_rn(en, st);
+  const float* o = g.origins + static_cast<size_t>(ray) * 3;
+  const float* d = g.dirs + static_cast<size_t>(ray) * 3;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)  // origins + directions * (starts + ends) / 2
+    rs.pos[i] = __fadd_rn(__ldg(o + i), __fmul_rn(__fmul_rn(__ldg(d + i), se), 0.5f));
+  // world -> context camera (pixel_aligned_features.py:18-20, geometry.py:59-65)
+  const float* W = g.ctxt_w2c + b * 16;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    rs.cam[i] = fmaf(__ldg(W + 4 * i + 2), rs.pos[2],
+                     fmaf(__ldg(W + 4 * i + 1), rs.pos[1], fmaf(__ldg(W + 4 * i), rs.pos[0], __ldg(W + 4 * i + 3))));
+  // project with normalised intrinsics, z-divide with +1e-9 (geometry.py:137-154)
+  const float* K = g.ctxt_k + b * 9;
+  const float u = fmaf(__ldg(K + 2), rs.cam[2], fmaf(__ldg(K + 1), rs.cam[1], __ldg(K + 0) * rs.cam[0]));
+  const float v = fmaf(__ldg(K + 5), rs.cam[2], fmaf(__ldg(K + 4), rs.cam[1], __ldg(K + 3) * rs.cam[0]));
+  const float w = fmaf(__ldg(K + 8), rs.cam[2], fmaf(__ldg(K + 7), rs.cam[1], __ldg(K + 6) * rs.cam[0]));
+  const float zd = __fadd_rn(w, 1e-9f);
+  const float un = __fdiv_rn(u, zd), vn = __fdiv_rn(v, zd);
+  // grid = (uv - 0.5) * 2 ; align_corners=True: ((g + 1) / 2) * (size - 1) ; border clamp
+  const float gx = __fmul_rn(__fsub_rn(un, 0.5f), 2.f), gy = __fmul_rn(__fsub_rn(vn, 0.5f), 2.f);
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), static_cast<float>(g.Wf - 1));
+  float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), static_cast<float>(g.Hf - 1));
+  rs.ix = fminf(fmaxf(ix, 0.f), static_cast<float>(g.Wf - 1));
+  rs.iy = fminf(fmaxf(iy, 0.f), static_cast<float>(g.Hf - 1));
+  if (!(rs.ix == rs.ix)) rs.ix = 0.f;  // NaN guard (degenerate projection)
+  if (!(rs.iy == rs.iy)) rs.iy = 0.f;
+  rs.pixbase = b * g.Hf * g.Wf;
+}
+
+// NeRFEncoding(63) of the camera-space point into A-tile K-block 0 (columns 60..63 are zero: the
+// raw-xyz columns are applied in fp32 by the first epilogue).  Column order: sin block
+// (dim-major, freq-minor), cos block (= sin(t + pi/2)), like nerfstudio's torch implementation.
+__device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)[3], bool valid) {
+  float v[64];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float s0 = __fmul_rn(6.2831855f, cam[i]);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      const float t = s0 * static_cast<float>(1 << k);  // exact power-of-two scaling
+      v[i * 10 + k] = sinf(t);
+      v[30 + i * 10 + k] = sinf(__fadd_rn(t, 1.5707964f));
+    }
+  }
+  v[60] = v[61] = v[62] = v[63] = 0.f;
+  if (!valid) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = 0.f;
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[32 * h + 2 * j], v[32 * h + 2 * j + 1]);
+    a_store32(e, 32 * h, pk);
+  }
+}
+
+// ----------------------------------------------------------------------------- gather
+// Bilinear (align_corners=True, border) gather of NCH hoisted channels starting at channel ch0 for
+// the 32 rows owned by this warp; each tap is one contiguous NCH*2-byte read spread over the
+// lanes (8 B / lane).  Result (fp16) goes to the slot's staging buffer.
+template <int NCH>
+__device__ __forceinline__ void gather_segment(const EpiCtx& e, const PassGeom& g, int ch0, float ix, float iy,
+                                               int pixbase) {
+  static_assert(NCH == 128 || NCH == 64, "segment width");
+  const int lane = threadIdx.x & 31;
+  const int wrow0 = e.row & ~31;
+  const bool active = (NCH == 128) || lane < 16;
+  const uint2* mp = reinterpret_cast<const uint2*>(g.map + ch0) + lane;
+  const size_t pstride = static_cast<size_t>(g.CH) / 4;  // uint2 per pixel
+  constexpr int U = 4;
+#pragma unroll 1
+  for (int j0 = 0; j0 < 32; j0 += U) {
+    uint2 t[U][4];
+    float w[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float bx = __shfl_sync(0xffffffffu, ix, j0 + u);
+      const float by = __shfl_sync(0xffffffffu, iy, j0 + u);
+      const int pb = __shfl_sync(0xffffffffu, pixbase, j0 + u);
+      const float x0 = floorf(bx), y0 = floorf(by);
+      const float x1 = x0 + 1.f, y1 = y0 + 1.f;
+      w[u][0] = (x1 - bx) * (y1 - by);
+      w[u][1] = (bx - x0) * (y1 - by);
+      w[u][2] = (x1 - bx) * (by - y0);
+      w[u][3] = (bx - x0) * (by - y0);
+      const int xi = static_cast<int>(x0), yi = static_cast<int>(y0);
+      const int xj = min(xi + 1, g.Wf - 1), yj = min(yi + 1, g.Hf - 1);  // out-of-range taps have weight 0
+      if (pb >= 0 && active) {
+        const uint2* r0 = mp + static_cast<size_t>(pb + yi * g.Wf) * pstride;
+        const uint2* r1 = mp + static_cast<size_t>(pb + yj * g.Wf) * pstride;
+        t[u][0] = __ldg(r0 + xi * pstride);
+        t[u][1] = __ldg(r0 + xj * pstride);
+        t[u][2] = __ldg(r1 + xi * pstride);
+        t[u][3] = __ldg(r1 + xj * pstride);
+      } else {
+        t[u][0] = t[u][1] = t[u][2] = t[u][3] = make_uint2(0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&t[u][q].x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&t[u][q].y));
+        a0 = fmaf(lo.x, w[u][q], a0);
+        a1 = fmaf(lo.y, w[u][q], a1);
+        a2 = fmaf(hi.x, w[u][q], a2);
+        a3 = fmaf(hi.y, w[u][q], a3);
+      }
+      if (active) {
+        uint2 o;
+        o.x = pack_f16x2(a0, a1);
+        o.y = pack_f16x2(a2, a3);
+        *reinterpret_cast<uint2*>(e.tz + tz_offset(wrow0 + j0 + u, lane >> 1) + (lane & 1) * 8) = o;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// ----------------------------------------------------------------------------- trunk epilogues
+// x[c0..c0+32) += (W_in[:,60:63] . cam + b_in) + staged segment ; write back ; ReLU -> A tile
+__device__ __forceinline__ void epi_x_first(const EpiCtx& e, int c0, const float4* __restrict__ e0,
+                                            const float (&cam)[3]) {
+  uint32_t r[32];
+  tmem_ld32(e.tmem + c0, r);
+  tmem_ld_wait();
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float4 q = __ldg(e0 + c0 + j);
+    v[j] = __uint_as_float(r[j]) + fmaf(q.z, cam[2], fmaf(q.y, cam[1], fmaf(q.x, cam[0], q.w)));
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(e.tz + tz_offset(e.row, (c0 >> 3) + j));
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __half22float2(h[t]);
+      v[8 * j + 2 * t] += f.x;
+      v[8 * j + 2 * t + 1] += f.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
+  tmem_st32(e.tmem + c0, r);
+  uint32_t p[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    p[j] = pack_relu_f16x2(fminf(v[2 * j], kF16Max), fminf(v[2 * j + 1], kF16Max));
+  a_store32(e, c0, p);
+  tmem_st_wait();
+}
+
+// The 10 residual-block steps + lin_out of one ResnetFC trunk, epilogue side.  Pre-conditions:
+// lin_in's accumulator wait has completed (x = W_in[:, :60] . enc in TMEM) and segment 0 of this
+// trunk's hoisted channels is in the staging buffer.  Leaves the lin_out accumulator (bias NOT
+// yet added) in TMEM columns [128, 128+n_out).
+__device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom& g, const TrunkTab& tab, int seg_ch0,
+                                                      const RowState& rs) {
+  // E0: X_0 = lin_in + b_in + raw-xyz + tz_0
+  for (int c0 = 0; c0 < 128; c0 += 32) epi_x_first(e, c0, tab.e0, rs.cam);
+  epi_publish(e);  // -> fc_0 (block 0)
+#pragma unroll 1
+  for (int k = 0; k < 5; ++k) {
+    // overlap: gather the next hoisted segment while the tensor pipe runs fc_0
+    if (k < 2) gather_segment<128>(e, g, seg_ch0 + 128 * (k + 1), rs.ix, rs.iy, rs.pixbase);
+    epi_wait_acc(e);
+    for (int c0 = 0; c0 < 128; c0 += 32) epi_relu_to_a(e, 128 + c0, c0, tab.bias + (2 * k) * 128);
+    epi_publish(e);  // -> fc_1 (block k), accumulates onto x
+    epi_wait_acc(e);
+    const float* bn = tab.bias + (2 * k + 1) * 128;
+    if (k < 2) {
+      for (int c0 = 0; c0 < 128; c0 += 32) epi_x_update<true, false>(e, c0, bn, nullptr);
+    } else {
+      for (int c0 = 0; c0 < 128; c0 += 32) epi_x_update<false, false>(e, c0, bn, nullptr);
+    }
+    epi_publish(e);  // -> fc_0 (block k+1) or lin_out
+  }
+  epi_wait_acc(e);  // lin_out accumulator ready
+}
+
+// ----------------------------------------------------------------------------- per-ray scans (one warp)
+// exclusive prefix sums of dd[0..n) accumulated in double (like torch.cumsum on CPU), rounded to
+// fp32 per element; `carry` holds the running total across the tiles of a long ray.
+__device__ __forceinline__ void excl_scan_warp(const float* dd, int n, double& carry, float* cum) {
+  const int lane = threadIdx.x & 31;
+  const int C = (n + 31) >> 5;
+  const int j0 = min(lane * C, n), j1 = min(j0 + C, n);
+  double loc = 0.0;
+  for (int j = j0; j < j1; ++j) loc += static_cast<double>(dd[j]);
+  double inc = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  double run = carry + (inc - loc);
+  for (int j = j0; j < j1; ++j) {
+    cum[j] = static_cast<float>(run);
+    run += static_cast<double>(dd[j]);
+  }
+  carry += __shfl_sync(0xffffffffu, inc, 31);
+}
+
+// PDFSampler.generate_ray_samples (ray_samplers.py:351-451), eval or train (u supplied), for ONE
+// ray by ONE warp.  `w` (smem, S entries) holds the transmittance weights and is overwritten;
+// `cdf` is smem scratch of S+1 entries.
+__device__ __forceinline__ void pdf_resample_warp(float* w, int S, const float* __restrict__ bins_in,
+                                                  const float* __restrict__ u, int nb, float anneal, int sum_vec,
+                                                  float* cdf, float* __restrict__ bins_out,
+                                                  int32_t* __restrict__ inds_out) {
+  const int lane = threadIdx.x & 31;
+  const int C = (S + 31) >> 5;
+  const int j0 = min(lane * C, S), j1 = min(j0 + C, S);
+  for (int j = j0; j < j1; ++j) {
+    float x = w[j];
+    if (anneal != 1.0f) x = powf(x, anneal);
+    w[j] = __fadd_rn(x, 0.01f);  // histogram_padding
+  }
+  __syncwarp();
+  float wsum;
+  if (sum_vec == 8) {
+    // ATen's vectorised fp32 row sum on CPU: 8 lanes x 4 interleaved accumulators, then the lanes
+    // are added in order (SumKernel.cpp vectorized_inner_sum / row_sum); verified against
+    // torch.sum in tests/test_oracle_golden.py.
+    const int nvec = S >> 3, nilp = nvec >> 2;
+    float r = 0.f;
+    if (lane < 8) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int i = 0; i < nilp; ++i) {
+        a0 = __fadd_rn(a0, w[(4 * i + 0) * 8 + lane]);
+        a1 = __fadd_rn(a1, w[(4 * i + 1) * 8 + lane]);
+        a2 = __fadd_rn(a2, w[(4 * i + 2) * 8 + lane]);
+        a3 = __fadd_rn(a3, w[(4 * i + 3) * 8 + lane]);
+      }
+      for (int i = 4 * nilp; i < nvec; ++i) a0 = __fadd_rn(a0, w[i * 8 + lane]);
+      r = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+    }
+    float fin = 0.f;
+    for (int k = nvec * 8; k < S; ++k) fin = __fadd_rn(fin, w[k]);
+    for (int v = 0; v < 8; ++v) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, r, v));
+    wsum = fin;
+  } else {
+    double loc = 0.0;
+    for (int j = j0; j < j1; ++j) loc += static_cast<double>(w[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loc += __shfl_xor_sync(0xffffffffu, loc, o);
+    wsum = static_cast<float>(loc);
+  }
+  const float pad = fmaxf(__fsub_rn(1e-5f, wsum), 0.f);
+  const float padj = __fdiv_rn(pad, static_cast<float>(S));
+  wsum = __fadd_rn(wsum, pad);
+  // cdf = [0, min(1, cumsum(pdf))]
+  double loc = 0.0;
+  for (int j = j0; j < j1; ++j) {
+    const float pj = __fdiv_rn(__fadd_rn(w[j], padj), wsum);
+    w[j] = pj;
+    loc += static_cast<double>(pj);
+  }
+  double inc = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  double run = inc - loc;
+  for (int j = j0; j < j1; ++j) {
+    run += static_cast<double>(w[j]);
+    cdf[j + 1] = fminf(1.0f, static_cast<float>(run));
+  }
+  if (lane == 0) cdf[0] = 0.f;
+  __syncwarp();
+  for (int i = lane; i < nb; i += 32) {
+    const float uu = __ldg(u + i);
+    int lo = 0, hi = S + 1;  // searchsorted(cdf, u, right=True)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+    }
+    const int below = min(max(lo - 1, 0), S), above = min(max(lo, 0), S);
+    const float c0 = cdf[below], c1 = cdf[above];
+    const float b0 = __ldg(bins_in + below), b1 = __ldg(bins_in + above);
+    float t = __fdiv_rn(__fsub_rn(uu, c0), __fsub_rn(c1, c0));
+    if (t != t) t = 0.f;                       // nan_to_num(nan=0); +-inf are removed by the clip
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    bins_out[i] = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+    if (inds_out) inds_out[i] = lo;
+  }
+  __syncwarp();
+}
+
+// ordered-uint encoding of a float for atomicMin/atomicMax
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+}  // namespace njf

@@ -1,0 +1,368 @@
+"""``Model`` -- API-identical mirror of ``neural_jacobian_field.models.model.Model``
+(project/neural_jacobian_field/models/model.py:147-628) whose rendering arithmetic runs in
+``libnjf_b200.so``.
+
+Same constructor (``Model(cfg: ModelCfg)``), same input/output dataclasses, same state-dict keys
+(``encoder.model.*``, ``proposal_networks.N.density_head.*``, ``decoder.*``), same methods:
+``forward``, ``patch_render``, ``encode_image``, ``infer_optical_flow``, ``compute_pixel_encoding``,
+``step_before_iter`` / ``step_after_iter``.  Inputs may live on the host: they are copied to the
+model's CUDA device (that copy is what bench.py's ``e2e`` number includes).
+
+There is no CPU / PyTorch fallback: without a CUDA device or without the built extension every
+rendering call raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib, api
+from .modules import (ActionDecoderCfg, DensityDecoderCfg, EncoderCfg, get_action_decoder, get_density_decoder,
+                      get_encoder)
+from .render import RenderResult, render
+
+
+# ----------------------------------------------------------------------------- dataclasses (model.py:35-144)
+@dataclass
+class RenderingCfg:
+    num_proposal_samples: Tuple[int, ...]
+    num_nerf_samples: int
+    single_jitter: bool = False
+    proposal_warmup: int = 5000
+    proposal_update_every: int = 5
+    use_proposal_weight_anneal: bool = True
+    proposal_weights_anneal_max_num_iters: int = 1000
+    proposal_weights_anneal_slope: float = 10.0
+
+
+@dataclass
+class ModelCfg:
+    action_dim: int
+    rendering: RenderingCfg
+    encoder: EncoderCfg
+    density_decoder: DensityDecoderCfg
+    action_decoder: ActionDecoderCfg
+
+
+@dataclass
+class CameraInput:
+    input_image: Tensor       # (B,3,H,W)
+    ctxt_extrinsics: Tensor   # (B,4,4) camera-to-world, relative to the context camera
+    ctxt_intrinsics: Tensor   # (B,3,3) normalised
+    trgt_extrinsics: Tensor   # (B,4,4)
+    trgt_intrinsics: Tensor   # (B,3,3) pixel units
+
+
+@dataclass
+class RenderingInput:
+    origins: Tensor      # (B,R,3)
+    directions: Tensor   # (B,R,3)
+    z_near: Tensor       # (B,)
+    z_far: Tensor        # (B,)
+
+
+@dataclass
+class RobotInput:
+    robot_action: Tensor  # (B,A)
+
+
+@dataclass
+class ModelInput:
+    camera_input: CameraInput
+    rendering_input: RenderingInput
+    robot_input: RobotInput
+
+
+@dataclass
+class ModelStandardOutput:
+    rgb: Tensor
+    depth: Tensor
+    optical_flow: Tensor
+
+
+@dataclass
+class SampleBins:
+    """What the training losses read from the reference's RaySamples (spacing-domain bin edges)."""
+    spacing_starts: Tensor  # (B,R,S,1)
+    spacing_ends: Tensor    # (B,R,S,1)
+
+
+@dataclass
+class ModelTrainingOutput:
+    weights_list: List[Tensor]
+    ray_samples_list: List[SampleBins]
+
+
+@dataclass
+class ModelVisOutput:
+    action_features: Tensor
+    ray_positions: Tensor
+    ray_positions_warped: Tensor
+    weights: Tensor
+    steps: Tensor
+
+
+@dataclass
+class ModelOutput:
+    standard_output: ModelStandardOutput
+    training_output: Optional[ModelTrainingOutput]
+    vis_output: Optional[ModelVisOutput]
+
+
+@dataclass
+class ModelInferenceEncoding:
+    density: Tensor                # (B,R,S,1)
+    action_features: Tensor        # (B,R,S,3A)
+    weights: Tensor                # (B,R,S,1)
+    ray_samples_positions: Tensor  # (B,R,S,3)
+    # collapsed form used by infer_optical_flow (flow is linear in the action, so
+    # sum_s w (x + J u) = p + Jbar^T u): computed by the field kernel in the same pass
+    jbar: Optional[Tensor] = None  # (B,R,3A)
+    p: Optional[Tensor] = None     # (B,R,3)
+
+
+@dataclass
+class PixelEncoding:
+    features: Tensor
+    extrinsics: Tensor
+    intrinsics: Tensor
+    action: Tensor
+    hoisted: Optional[Tensor] = None  # njf_hoist_features output for ``features``
+
+
+@dataclass
+class RenderingOutput:
+    rgb: Tensor
+    depth_raw: Tensor
+    depth_rgb: Tensor
+    flow_raw: Tensor
+    flow_rgb: Tensor
+    ray_positions: Tensor
+    ray_positions_warped: Tensor
+    action_features: Tensor
+    steps: Tensor
+    weights: Tensor
+
+
+def apply_depth_colormap(depth: Tensor) -> Tensor:
+    """Visual-only stand-in for nerfstudio.utils.colormaps.apply_depth_colormap (model.py:607):
+    min-max normalised depth through a 5-knot turbo-like ramp."""
+    d = depth.float()
+    lo, hi = d.min(), d.max()
+    t = ((d - lo) / (hi - lo + 1e-10)).clamp(0, 1)
+    knots = torch.tensor([[0.19, 0.07, 0.23], [0.16, 0.57, 0.96], [0.48, 0.99, 0.35], [0.98, 0.70, 0.17],
+                          [0.48, 0.01, 0.01]], device=d.device)
+    x = t * 4.0
+    i = x.floor().clamp(max=3).long()
+    f = x - i
+    return knots[i[..., 0]] * (1 - f) + knots[i[..., 0] + 1] * f
+
+
+class _FlowFromEncoding(torch.autograd.Function):
+    """optical flow of the collapsed encoding; forward in libnjf_b200.so, analytic backward wrt the action."""
+
+    @staticmethod
+    def forward(ctx, action, jbar, p, w2c, kpx):
+        L = api._declare()
+        B, R = p.shape[:2]
+        A = action.shape[-1]
+        flow = torch.empty(B, R, 2, device=p.device, dtype=torch.float32)
+        pw = torch.empty(B, R, 3, device=p.device, dtype=torch.float32)
+        act = action.detach().contiguous().float()
+        _lib.check(L.njf_flow_from_encoding(api.dptr(jbar), api.dptr(p), api.dptr(act), api.dptr(w2c), api.dptr(kpx),
+                                            B * R, R, A, api.dptr(flow), api.dptr(pw), api.stream_ptr()))
+        ctx.save_for_backward(jbar, pw, w2c, kpx)
+        ctx.A = A
+        return flow
+
+    @staticmethod
+    def backward(ctx, g):
+        jbar, pw, w2c, kpx = ctx.saved_tensors
+        B, R = pw.shape[:2]
+        # uv = (K c)_{0,1} / ((K c)_2 + 1e-9), c = W[:3,:3] x + W[:3,3];  d uv / d x, then x = p + J^T u
+        c = torch.einsum("bij,brj->bri", w2c[:, :3, :3], pw) + w2c[:, None, :3, 3]
+        k = torch.einsum("bij,brj->bri", kpx, c)
+        z = k[..., 2:3] + 1e-9
+        dk = torch.zeros(B, R, 2, 3, device=pw.device)
+        dk[..., 0, 0] = 1.0 / z[..., 0]
+        dk[..., 1, 1] = 1.0 / z[..., 0]
+        dk[..., 0, 2] = -k[..., 0] / (z[..., 0] ** 2)
+        dk[..., 1, 2] = -k[..., 1] / (z[..., 0] ** 2)
+        dx = torch.einsum("brij,bjk,bkl->bril", dk, kpx, w2c[:, :3, :3])          # (B,R,2,3)
+        J = jbar.reshape(B, R, ctx.A, 3)
+        ga = torch.einsum("bri,bril,bral->ba", g, dx, J)
+        return ga, None, None, None, None
+
+
+class Model(nn.Module):
+    def __init__(self, cfg: ModelCfg):
+        super().__init__()
+        self.cfg = cfg
+        self.encoder = get_encoder(cfg.encoder)
+        self.decoder = get_action_decoder(cfg.action_decoder, action_dim=cfg.action_dim,
+                                          encoder_dim=self.encoder.get_output_dim())
+        n_prop = len(cfg.rendering.num_proposal_samples)
+        if not 1 <= n_prop <= api.NJF_MAX_LEVELS:
+            raise NotImplementedError(f"{n_prop} proposal levels (supported: 1..{api.NJF_MAX_LEVELS})")
+        self.proposal_networks = nn.ModuleList(
+            [get_density_decoder(cfg.density_decoder, encoder_dim=self.encoder.get_output_dim()) for _ in range(n_prop)])
+        self._anneal = 1.0
+        self._step = 0
+        self._steps_since_update = 0
+        self._field: Optional[api.Field] = None
+        self._field_key = None
+        self.sh_fp16_round = True  # tiny-cuda-nn's SH encoding returns fp16
+
+    # ------------------------------------------------------------------ training-schedule hooks (model.py:201-213)
+    def step_before_iter(self, step):
+        r = self.cfg.rendering
+        if r.use_proposal_weight_anneal:
+            n = r.proposal_weights_anneal_max_num_iters
+            train_frac = np.clip(step / n, 0, 1)
+            b = r.proposal_weights_anneal_slope
+            self._anneal = float((b * train_frac) / ((b - 1) * train_frac + 1))
+
+    def step_after_iter(self, step):
+        if self.cfg.rendering.use_proposal_weight_anneal:
+            self._step = step
+            self._steps_since_update += 1
+
+    # ------------------------------------------------------------------ packed-weight cache
+    def _hot_state(self) -> Dict[str, Tensor]:
+        sd = {}
+        for k, v in self.state_dict().items():
+            if k.startswith("decoder.") or k.startswith("proposal_networks."):
+                if "jacobian_head_arm" in k:
+                    continue
+                sd[k] = v
+        return sd
+
+    def field(self) -> api.Field:
+        """Packed weights for the kernels; re-packed whenever a hot-path parameter changed."""
+        dev = self._device()
+        params = [p for n, p in self.named_parameters() if not n.startswith("encoder.")]
+        key = (dev, tuple((p.data_ptr(), p._version) for p in params))
+        if self._field is None or self._field_key != key:
+            with torch.cuda.device(dev):
+                self._field = api.Field(self.cfg.action_decoder.name, self.cfg.action_dim, len(self.proposal_networks),
+                                        self._hot_state(), sh_fp16_round=self.sh_fp16_round)
+            self._field_key = key
+        return self._field
+
+    def _device(self) -> torch.device:
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.NjfError("njf_b200.Model renders on a CUDA device only (move the module with .cuda()); "
+                                "there is no CPU fallback")
+        return dev
+
+    def _check_mode(self):
+        if getattr(self.decoder, "mode", "regular") != "regular":
+            raise NotImplementedError("only decoder mode 'regular' is implemented")
+        if self.training:
+            raise NotImplementedError(
+                "njf_b200.Model: training-mode forward (stratified jitter + autograd through the render) is the "
+                "next row of the scope table (SURVEY.md section 8f); call model.eval() for inference")
+
+    # ------------------------------------------------------------------ encoding
+    def _encode(self, camera_input: CameraInput, robot_input: RobotInput) -> PixelEncoding:
+        dev = self._device()
+        img = camera_input.input_image.to(dev, non_blocking=True)
+        with torch.no_grad():
+            feats = self.encoder.forward(img).float().contiguous()
+            hoisted = self.field().hoist(feats)
+        return PixelEncoding(features=feats, extrinsics=camera_input.ctxt_extrinsics,
+                             intrinsics=camera_input.ctxt_intrinsics, action=robot_input.robot_action, hoisted=hoisted)
+
+    def compute_pixel_encoding(self, camera_input, rendering_input, robot_input) -> PixelEncoding:
+        return self._encode(camera_input, robot_input)
+
+    def _render(self, pe: PixelEncoding, camera_input: CameraInput, rendering_input: RenderingInput,
+                robot_input: RobotInput, **kw) -> RenderResult:
+        dev = self._device()
+        r = self.cfg.rendering
+        cams, keep = api.make_cameras(pe.extrinsics, pe.intrinsics, camera_input.trgt_extrinsics,
+                                      camera_input.trgt_intrinsics, dev)
+        mv = lambda t: t.detach().to(dev, torch.float32, non_blocking=True)
+        Hf, Wf = pe.features.shape[-2:]
+        with torch.cuda.device(dev):
+            res = render(self.field(), pe.hoisted, Hf, Wf, cams, mv(rendering_input.origins),
+                         mv(rendering_input.directions), mv(rendering_input.z_near), mv(rendering_input.z_far),
+                         mv(robot_input.robot_action), tuple(r.num_proposal_samples), r.num_nerf_samples,
+                         anneal=self._anneal, **kw)
+        res._cams = keep
+        return res
+
+    # ------------------------------------------------------------------ forward (model.py:316-396)
+    def forward(self, camera_input: CameraInput, rendering_input: RenderingInput, robot_input: RobotInput,
+                compute_vis_features: bool = False) -> ModelOutput:
+        self._check_mode()
+        out_dev = rendering_input.origins.device
+        pe = self._encode(camera_input, robot_input)
+        res = self._render(pe, camera_input, rendering_input, robot_input, vis=compute_vis_features)
+        back = (lambda t: t) if out_dev.type == "cuda" else (lambda t: t.to(out_dev))
+        out = ModelOutput(
+            standard_output=ModelStandardOutput(rgb=back(res.rgb), depth=back(res.depth), optical_flow=back(res.flow)),
+            training_output=None, vis_output=None)
+        if compute_vis_features:
+            out.vis_output = ModelVisOutput(action_features=back(res.jbar), steps=back(res.steps),
+                                            weights=back(res.weights), ray_positions=back(res.p),
+                                            ray_positions_warped=back(res.pw))
+        return out
+
+    # ------------------------------------------------------------------ inverse-dynamics helpers (model.py:458-525)
+    def encode_image(self, camera_input, rendering_input, robot_input) -> ModelInferenceEncoding:
+        self._check_mode()
+        pe = self._encode(camera_input, robot_input)
+        res = self._render(pe, camera_input, rendering_input, robot_input, vis=True, per_sample=True)
+        return ModelInferenceEncoding(density=res.sigma, action_features=res.jac, weights=res.weights[..., None],
+                                      ray_samples_positions=res.positions, jbar=res.jbar, p=res.p)
+
+    def infer_optical_flow(self, model_inference_encoding: ModelInferenceEncoding, camera_input: CameraInput,
+                           robot_input: RobotInput) -> Tensor:
+        assert "jacobian" in self.cfg.action_decoder.name
+        enc = model_inference_encoding
+        dev = enc.weights.device
+        if enc.jbar is None or enc.p is None:
+            raise _lib.NjfError("encoding lacks the collapsed (jbar, p) fields; produce it with Model.encode_image")
+        f = lambda t: t.detach().to("cpu", torch.float32)
+        w2c = torch.inverse(f(camera_input.trgt_extrinsics)).contiguous().to(dev)
+        kpx = f(camera_input.trgt_intrinsics).contiguous().to(dev)
+        action = robot_input.robot_action.to(dev)
+        return _FlowFromEncoding.apply(action, enc.jbar.contiguous(), enc.p.contiguous(), w2c, kpx)
+
+    # ------------------------------------------------------------------ patch_render (model.py:527-628)
+    @torch.no_grad()
+    def patch_render(self, camera_input: CameraInput, rendering_input: RenderingInput, robot_input: RobotInput,
+                     patch_size: int = 2048, render_height: int = 480, render_width: int = 640,
+                     verbose: bool = False) -> RenderingOutput:
+        """Same contract as the reference, including the per-patch depth clip range (model.py:277 couples
+        the rays of one forward call), but the image encoder and the hoisted maps are computed ONCE per
+        frame instead of once per patch.  ``patch_size=None`` renders the frame in one launch."""
+        from torchvision.utils import flow_to_image
+
+        self._check_mode()
+        pe = self._encode(camera_input, robot_input)
+        num_rays = rendering_input.origins.shape[1]
+        step = num_rays if patch_size is None else patch_size
+        keys = ["rgb", "depth_raw", "flow_raw", "action_features", "steps", "weights", "ray_positions",
+                "ray_positions_warped"]
+        acc = {k: [] for k in keys}
+        for s in range(0, num_rays, step):
+            ri = RenderingInput(origins=rendering_input.origins[:, s:s + step], directions=rendering_input.directions[:, s:s + step],
+                                z_near=rendering_input.z_near, z_far=rendering_input.z_far)
+            res = self._render(pe, camera_input, ri, robot_input, vis=True)
+            for k, v in zip(keys, (res.rgb, res.depth, res.flow, res.jbar, res.steps, res.weights, res.p, res.pw)):
+                acc[k].append(v)
+        out = {k: torch.cat(v, dim=1).reshape(v[0].shape[0], render_height, render_width, -1) for k, v in acc.items()}
+        out["depth_rgb"] = apply_depth_colormap(out["depth_raw"])
+        out["flow_rgb"] = flow_to_image(out["flow_raw"].permute(0, 3, 1, 2).contiguous()).permute(0, 2, 3, 1)
+        return RenderingOutput(**out)
+
+    def compute_density(self, world_space_xyz, pixel_encoding):
+        raise NotImplementedError("point-query API (model.py:416-456) is not built yet: next scope row")

@@ -1,0 +1,288 @@
+"""Parameter containers with the reference's state-dict names, plus the plugin registries.
+
+The reference's plugin surface for this path is Python: three name->class registries
+(``ENCODERS`` models/encoder/__init__.py:7-16; ``DENSITY_DECODERS`` / ``ACTION_DECODERS``
+models/decoder/__init__.py:11-19) and the config dataclasses that select them.  The classes below
+keep those names, constructor signatures and parameter names (the checkpoint contract,
+SURVEY.md section 8b), but hold NO arithmetic: rendering happens in libnjf_b200.so, which
+``njf_b200.model.Model`` drives.  Initial values follow the reference's init distributions.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Literal, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+# ----------------------------------------------------------------------------- config dataclasses
+@dataclass
+class MlpCfg:  # model_components/resnet_fc.py:11-17
+    n_blocks: int = 5
+    d_hidden: int = 128
+    combine_layer: int = 3
+    combine_type: Literal["mean"] = "mean"
+    beta: float = 0.0
+
+
+@dataclass
+class TransformerCfg:  # action_decoder_jacobian.py:33-39
+    attn_feat_dim: int = 64
+    attn_head_dim: int = 64
+    num_attn_heads: int = 8
+    attn_depth: int = 3
+    attn_mlp_dim: int = 64
+
+
+@dataclass
+class DensityDecoderMlpCfg:  # density_decoder.py:16-20
+    name: Literal["density_mlp"]
+    mlp: MlpCfg
+    num_frequencies: int = 10
+
+
+@dataclass
+class ActionDecoderJacobianMlpCfg:  # action_decoder_jacobian.py:42-49
+    name: Literal["jacobian_mlp"]
+    mlp: MlpCfg
+    num_frequencies: int = 10
+    geometry_feature_dim: int = 15
+    use_arm_model: bool = False
+    arm_action_dim: Optional[int] = None
+
+
+@dataclass
+class ActionDecoderJacobianTransformerCfg:  # action_decoder_jacobian.py:52-60
+    name: Literal["jacobian_transformer"]
+    mlp: MlpCfg
+    transformer: TransformerCfg
+    num_frequencies: int = 10
+    geometry_feature_dim: int = 15
+    use_arm_model: bool = False
+    arm_action_dim: Optional[int] = None
+
+
+@dataclass
+class EncoderResnetCfg:  # models/encoder/encoder_resnet.py:15-21
+    name: Literal["resnet"] = "resnet"
+    upsample_interp: Literal["bilinear"] = "bilinear"
+    num_layers: int = 4
+    use_first_pool: bool = True
+    norm_type: Literal["batch", "instance", "group", "none"] = "batch"
+
+
+def _check_mlp(cfg: MlpCfg, who: str) -> None:
+    if (cfg.n_blocks, cfg.d_hidden, cfg.combine_layer) != (5, 128, 3) or cfg.beta > 0:
+        raise NotImplementedError(
+            f"{who}: the sm_100a kernels are specialised for the shipped MLP shape "
+            f"(n_blocks=5, d_hidden=128, combine_layer=3, beta=0); got {cfg}")
+
+
+# ----------------------------------------------------------------------------- containers
+class ResnetBlockParams(nn.Module):
+    def __init__(self, d: int):
+        super().__init__()
+        self.fc_0 = nn.Linear(d, d)
+        self.fc_1 = nn.Linear(d, d)
+        nn.init.constant_(self.fc_0.bias, 0.0)
+        nn.init.kaiming_normal_(self.fc_0.weight, a=0, mode="fan_in")
+        nn.init.constant_(self.fc_1.bias, 0.0)
+        nn.init.zeros_(self.fc_1.weight)
+
+
+class ResnetFCParams(nn.Module):
+    """Parameters of the reference's ResnetFC (model_components/resnet_fc.py:82-128)."""
+
+    def __init__(self, cfg: MlpCfg, d_in: int, d_latent: int, d_out: int):
+        super().__init__()
+        self.lin_in = nn.Linear(d_in, cfg.d_hidden)
+        self.lin_out = nn.Linear(cfg.d_hidden, d_out)
+        self.blocks = nn.ModuleList([ResnetBlockParams(cfg.d_hidden) for _ in range(cfg.n_blocks)])
+        self.lin_z = nn.ModuleList([nn.Linear(d_latent, cfg.d_hidden) for _ in range(min(cfg.combine_layer, cfg.n_blocks))])
+        for lin in [self.lin_in, self.lin_out, *self.lin_z]:
+            nn.init.constant_(lin.bias, 0.0)
+            nn.init.kaiming_normal_(lin.weight, a=0, mode="fan_in")
+
+
+class _AttnParams(nn.Module):
+    def __init__(self, dim, heads, dim_head, kv_dim):
+        super().__init__()
+        inner = heads * dim_head
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_kv = nn.Linear(kv_dim, inner * 2, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(0.0))
+
+
+class _FFParams(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Dropout(0.0), nn.Linear(hidden, dim),
+                                 nn.Dropout(0.0))
+
+
+class _PreNormParams(nn.Module):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+
+class TransformerParams(nn.Module):
+    """model_components/transformer.py:85-117 (cross-attention: selfatt=False)."""
+
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim, kv_dim):
+        super().__init__()
+        self.layers = nn.ModuleList([
+            nn.ModuleList([_PreNormParams(dim, _AttnParams(dim, heads, dim_head, kv_dim)),
+                           _PreNormParams(dim, _FFParams(dim, mlp_dim))])
+            for _ in range(depth)])
+
+
+def _init_jacobian(m):  # action_decoder_jacobian.py:78-83
+    if type(m) == nn.Linear:
+        nn.init.normal_(m.weight, mean=0.0, std=1e-4)
+        if m.bias is not None:
+            nn.init.normal_(m.bias, mean=0.0, std=1e-4)
+
+
+def _color_head(geo: int) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(geo + 16, 64), nn.ReLU(), nn.Linear(64, 64), nn.ReLU(), nn.Linear(64, 3),
+                         nn.Sigmoid())
+
+
+class DensityDecoderMlp(nn.Module):
+    """Proposal-network density field (models/decoder/density_decoder.py:23-43)."""
+
+    def __init__(self, cfg: DensityDecoderMlpCfg, encoder_dim: int):
+        super().__init__()
+        _check_mlp(cfg.mlp, "density_mlp")
+        if cfg.num_frequencies != 10:
+            raise NotImplementedError("kernels are specialised for num_frequencies=10")
+        self.cfg = cfg
+        self.density_head = ResnetFCParams(cfg.mlp, 63, encoder_dim, 1)
+
+
+class ActionDecoderJacobian(nn.Module):
+    """Common surface of the two Jacobian decoders (action_decoder_jacobian.py:86-258)."""
+
+    spatial_dim: int = 3
+    action_param_glob_pattern = "jacobian"
+
+    def switch_mode(self, mode: Literal["regular", "arm"]):
+        if mode != "regular":
+            raise NotImplementedError("njf_b200: only mode='regular' has a fused kernel")
+        self.mode = mode
+
+    def freeze_non_action_parameters(self) -> int:
+        counts = 0
+        for name, param in self.named_parameters():
+            if self.action_param_glob_pattern not in name:
+                param.requires_grad = False
+                counts += 1
+        return counts
+
+    def _common(self, cfg, action_dim, encoder_dim):
+        _check_mlp(cfg.mlp, cfg.name)
+        if cfg.num_frequencies != 10 or cfg.geometry_feature_dim != 15:
+            raise NotImplementedError("kernels are specialised for num_frequencies=10, geometry_feature_dim=15")
+        self.cfg = cfg
+        self.action_dim = action_dim
+        self.mode = "regular"
+        self.density_head = ResnetFCParams(cfg.mlp, 63, encoder_dim, cfg.geometry_feature_dim + 1)
+
+
+class ActionDecoderJacobianMLP(ActionDecoderJacobian):  # action_decoder_jacobian.py:261-337
+    action_param_glob_pattern = "jacobian_head"
+
+    def __init__(self, cfg: ActionDecoderJacobianMlpCfg, action_dim: int, encoder_dim: int):
+        super().__init__()
+        self._common(cfg, action_dim, encoder_dim)
+        self.jacobian_head = ResnetFCParams(cfg.mlp, 63, encoder_dim, 3 * action_dim)
+        self.jacobian_head.apply(_init_jacobian)
+        if cfg.use_arm_model:
+            self.jacobian_head_arm = ResnetFCParams(cfg.mlp, 63, encoder_dim, 3 * cfg.arm_action_dim)
+            self.jacobian_head_arm.apply(_init_jacobian)
+        self.color_head = _color_head(cfg.geometry_feature_dim)
+
+
+class ActionDecoderJacobianTransformer(ActionDecoderJacobian):  # action_decoder_jacobian.py:340-446
+    action_param_glob_pattern = "jacobian"
+
+    def __init__(self, cfg: ActionDecoderJacobianTransformerCfg, action_dim: int, encoder_dim: int):
+        super().__init__()
+        self._common(cfg, action_dim, encoder_dim)
+        t = cfg.transformer
+        if (t.attn_feat_dim, t.attn_head_dim, t.num_attn_heads, t.attn_depth, t.attn_mlp_dim) != (64, 64, 8, 3, 64):
+            raise NotImplementedError(f"kernels are specialised for the shipped transformer (64/64/8/3/64); got {t}")
+        self.jacobian_index_embedding = nn.Parameter(torch.randn(1, action_dim, t.attn_feat_dim), requires_grad=True)
+        self.jacobian_query_mlp = nn.Linear(encoder_dim + 63, t.attn_feat_dim)
+        self.jacobian_attn_decoder = TransformerParams(t.attn_feat_dim, t.attn_depth, t.num_attn_heads,
+                                                       t.attn_head_dim, t.attn_mlp_dim, t.attn_feat_dim)
+        self.jacobian_head = nn.Linear(t.attn_feat_dim, 3 * action_dim)
+        self.jacobian_head.apply(_init_jacobian)
+        if cfg.use_arm_model:
+            self.jacobian_head_arm = ResnetFCParams(cfg.mlp, 63, encoder_dim, 3 * cfg.arm_action_dim)
+            self.jacobian_head_arm.apply(_init_jacobian)
+        self.color_head = _color_head(cfg.geometry_feature_dim)
+
+
+class EncoderResnet(nn.Module):
+    """PixelNeRF image encoder (models/encoder/encoder_resnet.py:24-89): torchvision resnet34 trunk
+    (conv1..layer3), bilinear upsampling to the conv1 resolution, channel concat (512 ch at H/2 x W/2).
+    Runs once per image on cuDNN -- outside the hot path; its NCHW fp32
+    output is the input contract of njf_hoist_features."""
+
+    def __init__(self, cfg: EncoderResnetCfg):
+        super().__init__()
+        import torchvision
+
+        if cfg.norm_type != "batch" or cfg.num_layers != 4 or not cfg.use_first_pool:
+            raise NotImplementedError(f"encoder config {cfg} not supported (shipped: batch norm, 4 layers, first pool)")
+        self.cfg = cfg
+        self.model = torchvision.models.resnet34(weights=None)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, (nn.BatchNorm2d, nn.GroupNorm)):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    def forward(self, rgb: torch.Tensor) -> torch.Tensor:
+        m = self.model
+        x = m.relu(m.bn1(m.conv1(rgb)))
+        lat = [x]
+        x = m.layer1(m.maxpool(x)); lat.append(x)
+        x = m.layer2(x); lat.append(x)
+        x = m.layer3(x); lat.append(x)
+        sz = lat[0].shape[-2:]
+        return torch.cat([F.interpolate(t, sz, mode=self.cfg.upsample_interp, align_corners=False) for t in lat], 1)
+
+    def get_output_dim(self) -> int:
+        return 512
+
+
+# ----------------------------------------------------------------------------- registries
+ENCODERS = {"resnet": EncoderResnet}
+DENSITY_DECODERS = {"density_mlp": DensityDecoderMlp}
+ACTION_DECODERS = {"jacobian_mlp": ActionDecoderJacobianMLP, "jacobian_transformer": ActionDecoderJacobianTransformer}
+# "flow_mlp" (ablation decoder, models/decoder/action_decoder_flow.py) is out of scope: no shipped config selects it.
+
+EncoderCfg = EncoderResnetCfg
+DensityDecoderCfg = DensityDecoderMlpCfg
+ActionDecoderCfg = ActionDecoderJacobianMlpCfg | ActionDecoderJacobianTransformerCfg
+
+
+def get_encoder(cfg):
+    return ENCODERS[cfg.name](cfg)
+
+
+def get_density_decoder(cfg, encoder_dim: int):
+    return DENSITY_DECODERS[cfg.name](cfg=cfg, encoder_dim=encoder_dim)
+
+
+def get_action_decoder(cfg, action_dim: int, encoder_dim: int):
+    if cfg.name not in ACTION_DECODERS:
+        raise NotImplementedError(f"action decoder '{cfg.name}' has no B200 kernel (supported: {sorted(ACTION_DECODERS)})")
+    return ACTION_DECODERS[cfg.name](cfg=cfg, action_dim=action_dim, encoder_dim=encoder_dim)

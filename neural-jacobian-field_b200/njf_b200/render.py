@@ -1,0 +1,118 @@
+"""Typed Python entry to the fused render path (njf_render_forward and its stage entry points)."""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field as dc_field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib, api
+
+
+@dataclass
+class RenderResult:
+    rgb: Optional[torch.Tensor] = None            # (B,R,3)
+    depth: Optional[torch.Tensor] = None          # (B,R,1)
+    flow: Optional[torch.Tensor] = None           # (B,R,2)
+    jbar: Optional[torch.Tensor] = None           # (B,R,3A)
+    p: Optional[torch.Tensor] = None              # (B,R,3)
+    pw: Optional[torch.Tensor] = None             # (B,R,3)
+    steps: Optional[torch.Tensor] = None          # (B,R,S)
+    weights: Optional[torch.Tensor] = None        # (B,R,S)
+    sigma: Optional[torch.Tensor] = None          # (B,R,S,1)
+    jac: Optional[torch.Tensor] = None            # (B,R,S,3A)
+    positions: Optional[torch.Tensor] = None      # (B,R,S,3)
+    rgb_samples: Optional[torch.Tensor] = None    # (B,R,S,3)
+    prop_weights: List[torch.Tensor] = dc_field(default_factory=list)   # per level (B,R,S_l)
+    level_bins: List[torch.Tensor] = dc_field(default_factory=list)     # per level (B,R,n_l+1) spacing bins
+    level_inds: List[torch.Tensor] = dc_field(default_factory=list)     # per level (B,R,n_l+1) int32
+    bins0: Optional[torch.Tensor] = None
+
+
+def render(fld: api.Field, maps: torch.Tensor, Hf: int, Wf: int, cams: api.NjfCameras, origins: torch.Tensor,
+           dirs: torch.Tensor, z_near: torch.Tensor, z_far: torch.Tensor, action: torch.Tensor,
+           s_prop: Sequence[int], s_nerf: int, *, vis: bool = True, per_sample: bool = False,
+           sampler_outputs: bool = False, bins0: Optional[torch.Tensor] = None,
+           us: Optional[Sequence[torch.Tensor]] = None, anneal: float = 1.0,
+           sum_vec_width: Optional[int] = None, final_bins: Optional[torch.Tensor] = None) -> RenderResult:
+    """One fused render of B x R rays.  All tensors live on the field's CUDA device.
+
+    ``final_bins`` (B,R,s_nerf+1): skip the proposal levels and render the field at the given
+    spacing-domain bins (stage-wise parity tests / externally supplied samples)."""
+    L = api._declare()
+    dev = origins.device
+    B, R = origins.shape[:2]
+    A = fld.action_dim
+    f32 = dict(device=dev, dtype=torch.float32)
+    origins, dirs = origins.contiguous().float(), dirs.contiguous().float()
+    z_near, z_far = z_near.contiguous().float(), z_far.contiguous().float()
+    action = action.contiguous().float()
+    if len(s_prop) != fld.n_proposal:
+        raise _lib.NjfError(f"{len(s_prop)} proposal levels requested, field has {fld.n_proposal}")
+    tab_bins0, tab_us = api.eval_tables(s_prop, s_nerf, dev)
+    bins0 = tab_bins0 if bins0 is None else bins0.contiguous().float()
+    us = tab_us if us is None else [u.contiguous().float() for u in us]
+
+    res = RenderResult(bins0=bins0)
+    a = api.NjfRenderArgs()
+    a.B, a.R, a.n_levels, a.s_nerf = B, R, len(s_prop), int(s_nerf)
+    for i, s in enumerate(s_prop):
+        a.s_prop[i] = int(s)
+    a.origins, a.dirs = api.dptr(origins), api.dptr(dirs)
+    a.z_near, a.z_far, a.action = api.dptr(z_near), api.dptr(z_far), api.dptr(action)
+    a.bins0 = api.dptr(bins0)
+    a.bins0_stride = 0 if bins0.dim() == 1 else bins0.shape[-1]
+    a.anneal = float(anneal)
+    a.sum_vec_width = api.default_sum_vec_width() if sum_vec_width is None else int(sum_vec_width)
+    a.maps, a.Hf, a.Wf = api.dptr(maps), int(Hf), int(Wf)
+    keep = [origins, dirs, z_near, z_far, action, bins0, maps] + list(us)
+    for lvl in range(len(s_prop)):
+        n = s_prop[lvl + 1] if lvl + 1 < len(s_prop) else s_nerf
+        u = us[lvl]
+        a.u[lvl] = api.dptr(u)
+        a.u_stride[lvl] = 0 if u.dim() == 1 else n + 1
+        lb = torch.empty(B, R, n + 1, **f32)
+        res.level_bins.append(lb)
+        a.level_bins[lvl] = api.dptr(lb)
+        if sampler_outputs:
+            pw = torch.empty(B, R, s_prop[lvl], **f32)
+            li = torch.empty(B, R, n + 1, device=dev, dtype=torch.int32)
+            res.prop_weights.append(pw)
+            res.level_inds.append(li)
+            a.prop_weights[lvl] = api.dptr(pw)
+            a.level_inds[lvl] = api.dptr(li)
+    minmax = torch.empty(2, **f32)
+    a.minmax = api.dptr(minmax)
+    keep.append(minmax)
+    res.rgb = torch.empty(B, R, 3, **f32)
+    res.depth = torch.empty(B, R, 1, **f32)
+    res.flow = torch.empty(B, R, 2, **f32)
+    res.jbar = torch.empty(B, R, 3 * A, **f32)
+    res.p = torch.empty(B, R, 3, **f32)
+    res.pw = torch.empty(B, R, 3, **f32)
+    a.rgb, a.depth, a.flow = api.dptr(res.rgb), api.dptr(res.depth), api.dptr(res.flow)
+    a.jbar, a.p, a.pw = api.dptr(res.jbar), api.dptr(res.p), api.dptr(res.pw)
+    if vis or per_sample:
+        res.steps = torch.empty(B, R, s_nerf, **f32)
+        res.weights = torch.empty(B, R, s_nerf, **f32)
+        a.steps, a.weights = api.dptr(res.steps), api.dptr(res.weights)
+    if per_sample:
+        res.sigma = torch.empty(B, R, s_nerf, 1, **f32)
+        res.jac = torch.empty(B, R, s_nerf, 3 * A, **f32)
+        res.positions = torch.empty(B, R, s_nerf, 3, **f32)
+        res.rgb_samples = torch.empty(B, R, s_nerf, 3, **f32)
+        a.sigma, a.jac = api.dptr(res.sigma), api.dptr(res.jac)
+        a.positions, a.rgb_samples = api.dptr(res.positions), api.dptr(res.rgb_samples)
+    st = api.stream_ptr()
+    h = fld.handle
+    if final_bins is None:
+        _lib.check(L.njf_render_forward(h, ctypes.byref(cams), ctypes.byref(a), st))
+    else:
+        fb = final_bins.contiguous().float()
+        keep.append(fb)
+        stride = 0 if fb.dim() == 1 else fb.shape[-1]
+        _lib.check(L.njf_field_pass(h, ctypes.byref(cams), ctypes.byref(a), api.dptr(fb), stride, st))
+        _lib.check(L.njf_finish_pass(h, ctypes.byref(cams), ctypes.byref(a), st))
+    res._keep = keep  # inputs stay alive until the caller is done with the (async) result
+    return res

@@ -1,0 +1,191 @@
+"""GPU parity of the CUDA render path (through the C-ABI) against
+ (a) the golden vectors produced by the unmodified reference (tests/golden) and
+ (b) the CPU oracle (oracle/njf_oracle.py) on fresh seeded inputs at larger sizes.
+
+Tolerances (fp16 tensor-core operands, fp32 accumulate, vs the fp32 CPU reference):
+  sample indexing      : bit-exact given identical weights (PDF sampler alone)
+  sigma (per sample)   : <= 2e-2 relative (of max(|sigma|, 0.05))
+  rgb (per sample/ray) : <= 4e-3 / 2e-3 absolute
+  Jacobian             : <= 2e-2 of the per-tensor max
+  depth                : <= 1e-3 * (far - near);  optical flow: <= 2e-2 of max + 0.05 px
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, O, RENDER_FIXTURES, load_fixture, oracle_render, synth
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _field_and_maps(head, A, s_prop, weights, feat):
+    from njf_b200 import api
+
+    fld = api.Field(head, A, len(s_prop), weights)
+    maps = fld.hoist(feat.to(DEV))
+    return fld, maps
+
+
+def _run(fx_tuple, **kw):
+    from njf_b200 import api
+    from njf_b200.render import render
+
+    fx, t, head, A, s_prop, s_nerf, w = fx_tuple
+    fld, maps = _field_and_maps(head, A, s_prop, w, t("feat"))
+    cams, keep = api.make_cameras(t("ctxt_c2w"), t("ctxt_k"), t("trgt_c2w"), t("trgt_k_px"), DEV)
+    Hf, Wf = fx["feat"].shape[-2:]
+    g = lambda k: t(k).to(DEV)
+    res = render(fld, maps, Hf, Wf, cams, g("origins"), g("dirs"), g("z_near"), g("z_far"), g("action"),
+                 s_prop, s_nerf, vis=True, per_sample=True, sampler_outputs=True, **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def _rel(a, b, floor):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def _check_samples(res, ref, near_far):
+    sig, sig_ref = res.sigma.cpu().numpy(), ref["sigma"]
+    assert _rel(sig, sig_ref, 0.05) < 2e-2, "sigma"
+    np.testing.assert_allclose(res.rgb_samples.cpu().numpy(), ref["rgb_samples"], atol=4e-3, rtol=0)
+    jm = max(float(np.abs(ref["jacobian"]).max()), 1e-6)
+    np.testing.assert_allclose(res.jac.cpu().numpy(), ref["jacobian"], atol=2e-2 * jm, rtol=0)
+    np.testing.assert_allclose(res.positions.cpu().numpy(), ref["positions"], atol=2e-5, rtol=1e-5)
+
+
+def _check_composites(res, ref, near_far, loose=1.0):
+    np.testing.assert_allclose(res.rgb.cpu().numpy(), ref["rgb"], atol=2e-3 * loose, rtol=0)
+    np.testing.assert_allclose(res.depth.cpu().numpy(), ref["depth"], atol=1e-3 * near_far * loose, rtol=0)
+    np.testing.assert_allclose(res.weights.cpu().numpy(), ref["weights"], atol=2e-3 * loose, rtol=0)
+    np.testing.assert_allclose(res.steps.cpu().numpy(), ref["steps"], atol=2e-3 * loose, rtol=0)
+    jm = max(float(np.abs(ref["action_features"]).max()), 1e-6)
+    np.testing.assert_allclose(res.jbar.cpu().numpy(), ref["action_features"], atol=2e-2 * jm * loose, rtol=0)
+    np.testing.assert_allclose(res.p.cpu().numpy(), ref["ray_positions"], atol=3e-3 * loose, rtol=0)
+    np.testing.assert_allclose(res.pw.cpu().numpy(), ref["ray_positions_warped"], atol=3e-3 * loose, rtol=0)
+    fm = float(np.abs(ref["optical_flow"]).max())
+    np.testing.assert_allclose(res.flow.cpu().numpy(), ref["optical_flow"], atol=(2e-2 * fm + 0.05) * loose, rtol=0)
+
+
+@pytest.mark.parametrize("tag", ["16_24", "64_64", "128_128", "256_256", "48_32"])
+def test_pdf_sampler_bit_exact_vs_reference(tag):
+    from njf_b200 import api
+
+    z = np.load(os.path.join(GOLDEN, "pdf_sampler.npz"))
+    s_out = int(tag.split("_")[1])
+    w = torch.from_numpy(z[f"w_{tag}"]).to(DEV)
+    bins_in = torch.from_numpy(z[f"bins_in_{tag}"]).to(DEV)
+    _, us = api.eval_tables([w.shape[1]], s_out, DEV)
+    bins, inds = api.pdf_sample(w, bins_in, us[0], s_out)
+    assert np.array_equal(inds.cpu().numpy(), z[f"inds_{tag}"].astype(np.int32))
+    assert np.array_equal(bins.cpu().numpy(), z[f"bins_out_{tag}"])
+    tw = api.transmittance_weights(torch.from_numpy(z[f"deltas_{tag}"]).to(DEV), w * 20.0)
+    np.testing.assert_allclose(tw.cpu().numpy(), z[f"tw_{tag}"], atol=1e-6, rtol=1e-5)
+
+
+def test_hoisted_maps_match_linear():
+    from njf_b200 import api
+
+    fx, t, head, A, s_prop, s_nerf, w = load_fixture("render_transformer")
+    feat = t("feat")
+    fld, maps = _field_and_maps(head, A, s_prop, w, feat)
+    B, C, Hf, Wf = feat.shape
+    m = maps.view(torch.float16).cpu().float()
+    px = feat.permute(0, 2, 3, 1).reshape(B * Hf * Wf, C)
+    off = 0
+    for prefix, nch in (("proposal_networks.0.density_head", 384), ("decoder.density_head", 384)):
+        ch = 384 if prefix.startswith("proposal") else 448
+        blk = m[off: off + B * Hf * Wf * ch].reshape(B * Hf * Wf, ch)
+        for k in range(3):
+            ref = torch.nn.functional.linear(px, w[f"{prefix}.lin_z.{k}.weight"], w[f"{prefix}.lin_z.{k}.bias"])
+            np.testing.assert_allclose(blk[:, 128 * k: 128 * (k + 1)].numpy(), ref.numpy(), atol=4e-3, rtol=2e-3)
+        if ch == 448:
+            ref = torch.nn.functional.linear(px, w["decoder.jacobian_query_mlp.weight"][:, 63:])
+            np.testing.assert_allclose(blk[:, 384:].numpy(), ref.numpy(), atol=4e-3, rtol=2e-3)
+        off += B * Hf * Wf * ch
+
+
+@pytest.mark.parametrize("name", RENDER_FIXTURES)
+def test_field_pass_given_reference_bins(name):
+    """Main pass alone at the reference's own final sample bins: per-sample and composite parity."""
+    fxt = load_fixture(name)
+    fx, t = fxt[0], fxt[1]
+    res = _run(fxt, final_bins=t("final_bins").to(DEV))
+    nf = float(fx["z_far"].max() - fx["z_near"].min())
+    if name.endswith("initlike"):
+        # white-spectrum weights: only the well-conditioned quantities are compared tightly
+        np.testing.assert_allclose(res.positions.cpu().numpy(), fx["positions"], atol=2e-5, rtol=1e-5)
+        assert _rel(res.sigma.cpu().numpy(), fx["sigma"], 0.05) < 5e-2
+        np.testing.assert_allclose(res.rgb.cpu().numpy(), fx["rgb"], atol=5e-3, rtol=0)
+        return
+    _check_samples(res, fx, nf)
+    _check_composites(res, fx, nf)
+
+
+@pytest.mark.parametrize("name", RENDER_FIXTURES[:3])
+def test_full_render_vs_reference(name):
+    fxt = load_fixture(name)
+    fx = fxt[0]
+    res = _run(fxt)
+    nf = float(fx["z_far"].max() - fx["z_near"].min())
+    nl = len(fxt[4])
+    for lvl in range(nl):
+        inds = res.level_inds[lvl].cpu().numpy()
+        ref = fx[f"inds_{lvl + 1}"]
+        mism = float(np.mean(inds != ref))
+        print(f"{name}: level {lvl} searchsorted mismatch rate {mism:.4f}")
+        assert mism < 0.03
+    np.testing.assert_allclose(res.level_bins[-1].cpu().numpy(), fx["final_bins"], atol=2e-3, rtol=0)
+    np.testing.assert_allclose(res.prop_weights[-1].cpu().numpy(), fx["proposal_weights"], atol=2e-3, rtol=0)
+    _check_composites(res, fx, nf, loose=2.0)
+
+
+@pytest.mark.parametrize("head,A,s_prop,s_nerf,R,B", [
+    ("jacobian_transformer", 8, (128,), 128, 300, 1),
+    ("jacobian_transformer", 8, (64,), 64, 257, 2),
+    ("jacobian_mlp", 6, (256,), 256, 70, 1),
+    ("jacobian_transformer", 5, (48,), 40, 130, 1),
+    ("jacobian_transformer", 8, (32, 24), 200, 64, 1),
+])
+def test_render_vs_oracle_seeded(head, A, s_prop, s_nerf, R, B):
+    """Larger seeded cases against the CPU oracle: stage-wise (field pass at the oracle's bins) and
+    end-to-end composites."""
+    from njf_b200 import api
+    from njf_b200.render import render
+
+    g = torch.Generator().manual_seed(1000 + R)
+    w = synth.synth_state_dict(synth.field_shapes(head, A, n_proposal=len(s_prop)), 77 + A)
+    feat = torch.randn(B, 512, 20, 28, generator=g).abs() * 0.7
+    K = synth.normalized_intrinsics(**synth.ALLEGRO_INTRINSICS_PX)[None].repeat(B, 1, 1)
+    kpx = K.clone(); kpx[:, 0] *= 640; kpx[:, 1] *= 480
+    ctxt = torch.eye(4)[None].repeat(B, 1, 1)
+    trgt = torch.stack([synth.relative_target_pose(1 + b) for b in range(B)])
+    coords = torch.rand(R, 2, generator=g)
+    rays = [synth.world_rays(coords, K[b], trgt[b]) for b in range(B)]
+    o = torch.stack([r[0] for r in rays]); d = torch.stack([r[1] for r in rays])
+    zn = torch.full((B,), 0.5); zf = torch.full((B,), 3.2)
+    act = 0.1 * torch.randn(B, A, generator=g)
+    spec = O.FieldSpec(head=head, action_dim=A)
+    with torch.no_grad():
+        ref = O.render_forward(w, spec, feat, ctxt, K, trgt, kpx, o, d, zn, zf, act, s_prop, s_nerf)
+    ref = {k: v.numpy() for k, v in ref.items()}
+    fld, maps = _field_and_maps(head, A, s_prop, w, feat)
+    cams, keep = api.make_cameras(ctxt, K, trgt, kpx, DEV)
+    args = (fld, maps, 20, 28, cams, o.to(DEV), d.to(DEV), zn.to(DEV), zf.to(DEV), act.to(DEV), s_prop, s_nerf)
+    st = render(*args, per_sample=True, final_bins=torch.from_numpy(ref["final_bins"]).to(DEV))
+    torch.cuda.synchronize()
+    ref2 = dict(ref, action_features=ref["action_features"])
+    _check_samples(st, ref, 2.7)
+    _check_composites(st, ref2, 2.7)
+    full = render(*args, vis=True, sampler_outputs=True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(full.level_bins[-1].cpu().numpy(), ref["final_bins"], atol=3e-3, rtol=0)
+    _check_composites(full, ref2, 2.7, loose=2.5)
+    mse = float(np.mean((full.rgb.cpu().numpy() - ref["rgb"]) ** 2))
+    psnr = 10 * np.log10(1.0 / max(mse, 1e-12))
+    print(f"{head} A={A} S={s_prop}->{s_nerf}: PSNR vs oracle {psnr:.1f} dB")
+    assert psnr > 50.0

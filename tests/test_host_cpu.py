@@ -1,0 +1,86 @@
+"""CPU-only checks of the host-side mirror and the C-ABI library (no compute calls)."""
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import ROOT, synth
+
+
+def _cfg(head="jacobian_transformer", A=8, s_prop=(16,), s_nerf=24):
+    from njf_b200 import model as M, modules as mod
+
+    mlp = mod.MlpCfg()
+    if head == "jacobian_transformer":
+        dec = mod.ActionDecoderJacobianTransformerCfg(name=head, mlp=mlp, transformer=mod.TransformerCfg())
+    else:
+        dec = mod.ActionDecoderJacobianMlpCfg(name=head, mlp=mlp)
+    return M.ModelCfg(action_dim=A, rendering=M.RenderingCfg(tuple(s_prop), s_nerf), encoder=mod.EncoderResnetCfg(),
+                      density_decoder=mod.DensityDecoderMlpCfg("density_mlp", mlp), action_decoder=dec)
+
+
+def test_library_exports_every_declared_symbol():
+    from njf_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "njf_b200.h")).read()
+    names = set(re.findall(r"\b(njf_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 14
+    L = _lib.lib()
+    for n in sorted(names):
+        assert hasattr(L, n), f"libnjf_b200.so does not export {n}"
+    assert L.njf_version() >= 100
+
+
+@pytest.mark.parametrize("head,A", [("jacobian_transformer", 8), ("jacobian_mlp", 6)])
+def test_state_dict_keys_are_the_reference_contract(head, A):
+    from njf_b200.model import Model
+
+    m = Model(_cfg(head, A))
+    sd = m.state_dict()
+    hot = {k: tuple(v.shape) for k, v in sd.items() if not k.startswith("encoder.")}
+    assert hot == synth.field_shapes(head, A)
+    assert "encoder.model.conv1.weight" in sd and "encoder.model.layer3.5.bn2.running_var" in sd
+    if os.path.isdir("/root/reference/project"):  # build container only: compare with the real thing
+        import sys
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_shim
+
+        ref = ref_shim.reference_modules().Model(ref_shim.build_reference_cfg(A, head, (16,), 24))
+        rsd = ref.state_dict()
+        assert {k: tuple(v.shape) for k, v in rsd.items()} == {k: tuple(v.shape) for k, v in sd.items()}
+        m.load_state_dict(rsd, strict=True)
+
+
+def test_freeze_and_schedule_hooks():
+    from njf_b200.model import Model
+
+    m = Model(_cfg())
+    n = m.decoder.freeze_non_action_parameters()
+    assert n > 0
+    assert all(p.requires_grad == ("jacobian" in k) for k, p in m.decoder.named_parameters())
+    m.step_before_iter(500)
+    b, f = 10.0, 0.5
+    assert abs(m._anneal - (b * f) / ((b - 1) * f + 1)) < 1e-9
+    m.step_after_iter(500)
+    assert m._step == 500
+
+
+def test_no_cpu_fallback():
+    from njf_b200 import _lib
+    from njf_b200.model import CameraInput, Model, RenderingInput, RobotInput
+
+    m = Model(_cfg()).eval()
+    cam = CameraInput(torch.rand(1, 3, 16, 24), torch.eye(4)[None], torch.eye(3)[None], torch.eye(4)[None], torch.eye(3)[None])
+    with pytest.raises(_lib.NjfError):
+        m.forward(cam, RenderingInput(torch.zeros(1, 4, 3), torch.ones(1, 4, 3), torch.tensor([0.5]), torch.tensor([2.0])),
+                  RobotInput(torch.zeros(1, 8)))
+
+
+def test_unsupported_configs_fail_loudly():
+    from njf_b200 import modules as mod
+
+    with pytest.raises(NotImplementedError):
+        mod.DensityDecoderMlp(mod.DensityDecoderMlpCfg("density_mlp", mod.MlpCfg(n_blocks=4)), 512)
+    with pytest.raises(NotImplementedError):
+        mod.get_action_decoder(type("C", (), {"name": "flow_mlp"})(), 8, 512)
