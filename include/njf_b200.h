@@ -120,7 +120,8 @@ typedef struct NjfRenderArgs {
   float* prop_weights[NJF_MAX_LEVELS]; /* [B][R][s_prop[l]] */
   float* level_bins[NJF_MAX_LEVELS];   /* REQUIRED workspace: [B][R][n_l+1], bins produced by level l's PDF step */
   int32_t* level_inds[NJF_MAX_LEVELS]; /* [B][R][n_l+1] searchsorted results */
-  float* minmax;                  /* REQUIRED workspace: 2 floats */
+  float* minmax;                  /* REQUIRED workspace: 2 floats; after njf_field_pass = (min, max) of steps over the call
+                                     (all-reduce it across ranks before njf_finish_pass when one call is ray-sharded) */
 } NjfRenderArgs;
 
 int njf_render_forward(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* args, void* stream);

@@ -541,6 +541,12 @@ __global__ void init_minmax_kernel(uint32_t* mm) {
   mm[0] = 0xffffffffu;
   mm[1] = 0u;
 }
+// ordered-uint -> plain fp32 in place, so that ranks can all-reduce (min, max) between the passes
+__global__ void decode_minmax_kernel(uint32_t* mm) {
+  const float lo = ord2f(mm[0]), hi = ord2f(mm[1]);
+  reinterpret_cast<float*>(mm)[0] = lo;
+  reinterpret_cast<float*>(mm)[1] = hi;
+}
 
 // depth clip + optical flow (model.py:271-279, 288-314; geometry.py:206-215)
 struct FinishParams {
@@ -548,7 +554,7 @@ struct FinishParams {
   const float* action;    // [B][A]
   const float* trgt_w2c;  // [B][16]
   const float* trgt_k;    // [B][9] pixel units
-  const uint32_t* minmax;
+  const float* minmax;   // [2] call-global (min, max) of steps
   float* depth;
   const float* jbar;
   const float* p;
@@ -572,7 +578,7 @@ __global__ void finish_kernel(const FinishParams q) {
   if (ray >= q.NR) return;
   const int b = ray / q.R;
   if (q.depth && q.minmax) {
-    const float lo = ord2f(q.minmax[0]), hi = ord2f(q.minmax[1]);
+    const float lo = q.minmax[0], hi = q.minmax[1];
     q.depth[ray] = fminf(fmaxf(q.depth[ray], lo), hi);
   }
   if (!q.p || !q.jbar) return;
@@ -845,6 +851,7 @@ extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const N
   const int nitems = (p.g.NG + 1) / 2;
   const int grid = nitems < num_sms() ? nitems : num_sms();
   field_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  decode_minmax_kernel<<<1, 1, 0, stream>>>(p.minmax);
   NJF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -859,7 +866,7 @@ extern "C" int njf_finish_pass(const NjfField* f, const NjfCameras* cams, const 
   q.action = a->action;
   q.trgt_w2c = cams->trgt_w2c;
   q.trgt_k = cams->trgt_k_px;
-  q.minmax = reinterpret_cast<const uint32_t*>(a->minmax);
+  q.minmax = a->minmax;
   q.depth = a->depth;
   q.jbar = a->jbar;
   q.p = a->p;
