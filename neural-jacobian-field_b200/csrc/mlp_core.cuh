@@ -230,12 +230,12 @@ __device__ __forceinline__ void epi_relu_to_a(const EpiCtx& e, int tcol, int c0,
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
-    const float v0 = fminf(__uint_as_float(r[4 * j + 0]) + b.x, kF16Max);
-    const float v1 = fminf(__uint_as_float(r[4 * j + 1]) + b.y, kF16Max);
-    const float v2 = fminf(__uint_as_float(r[4 * j + 2]) + b.z, kF16Max);
-    const float v3 = fminf(__uint_as_float(r[4 * j + 3]) + b.w, kF16Max);
-    p[2 * j] = pack_relu_f16x2(v0, v1);
-    p[2 * j + 1] = pack_relu_f16x2(v2, v3);
+    const float2 s0 = fadd2(make_float2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])),
+                            make_float2(b.x, b.y));
+    const float2 s1 = fadd2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])),
+                            make_float2(b.z, b.w));
+    p[2 * j] = pack_relu_f16x2(fminf(s0.x, kF16Max), fminf(s0.y, kF16Max));
+    p[2 * j + 1] = pack_relu_f16x2(fminf(s1.x, kF16Max), fminf(s1.y, kF16Max));
   }
   a_store32(e, c0, p);
 }
@@ -254,10 +254,11 @@ __device__ __forceinline__ void epi_x_update(const EpiCtx& e, int c0,
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
-    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+    const float2 s0 = fadd2(make_float2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])),
+                            make_float2(b.x, b.y));
+    const float2 s1 = fadd2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])),
+                            make_float2(b.z, b.w));
+    v[4 * j + 0] = s0.x; v[4 * j + 1] = s0.y; v[4 * j + 2] = s1.x; v[4 * j + 3] = s1.y;
   }
   if (kHasTz) {
 #pragma unroll
@@ -266,9 +267,9 @@ __device__ __forceinline__ void epi_x_update(const EpiCtx& e, int c0,
       const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(h[t]);
-        v[8 * j + 2 * t] += f.x;
-        v[8 * j + 2 * t + 1] += f.y;
+        const float2 s = fadd2(make_float2(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]), __half22float2(h[t]));
+        v[8 * j + 2 * t] = s.x;
+        v[8 * j + 2 * t + 1] = s.y;
       }
     }
   }

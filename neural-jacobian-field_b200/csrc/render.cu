@@ -8,6 +8,7 @@
 // plus the standalone sampler kernels.  See DESIGN.md for the data layout and rooflines.
 #include "render.cuh"
 #include "njf_internal.h"
+#include <cstdlib>
 
 namespace njf {
 
@@ -16,6 +17,7 @@ struct SlotScratch {
   float cum[kRows];   // exclusive prefix sums (fp32) of dd
   float wts[528];     // transmittance weights of the ray group (proposal: PDF input)
   float cdf[544];     // PDF scratch
+  TapEntry taps[kRows];  // bilinear taps of the current tile
 };
 constexpr uint32_t kScratchSlotBytes = (sizeof(SlotScratch) + 15) & ~15u;
 constexpr uint32_t kSmemBytes = SmemMap::kScratch + kSlots * kScratchSlotBytes + 64 + 1024;
@@ -96,11 +98,13 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
       for (int tile = 0; tile < g.T; ++tile) {
         RowState rs;
         row_setup(g, group, tile, e.row, rs);
-        write_posenc(e, rs.cam, rs.ray >= 0);
+        write_taps(sc->taps, e.row, rs, g.Hf, g.Wf);
+        write_posenc(e, rs.cam, rs.ray >= 0, g.debug);
         epi_publish(e);  // -> lin_in
-        gather_segment<128>(e, g, 0, rs.ix, rs.iy, rs.pixbase);
+        __syncwarp();
+        gather_segment<128>(e, g, sc->taps, 0);
         epi_wait_acc(e);
-        trunk_blocks_epilogue(e, g, p.trunk, 0, rs);
+        trunk_blocks_epilogue(e, g, p.trunk, 0, rs, sc->taps);
         uint32_t r[16];
         tmem_ld16(e.tmem + 128, r);
         tmem_ld_wait();
@@ -368,16 +372,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         row_setup(g, group, tile, e.row, rs);
         const bool valid = rs.ray >= 0;
         float J[32];
-        write_posenc(e, rs.cam, valid);
+        write_taps(sc->taps, e.row, rs, g.Hf, g.Wf);
+        write_posenc(e, rs.cam, valid, g.debug);
         epi_publish(e);  // -> lin_in (+ q_enc for the transformer head)
+        __syncwarp();
         if (p.head_kind == NJF_HEAD_TRANSFORMER) {
-          gather_segment<64>(e, g, 384, rs.ix, rs.iy, rs.pixbase);
+          gather_segment<64>(e, g, sc->taps, 384);
           epi_wait_acc(e);
           transformer_head(e, p.head, A, rs, J);
         }
-        gather_segment<128>(e, g, 0, rs.ix, rs.iy, rs.pixbase);
+        gather_segment<128>(e, g, sc->taps, 0);
         if (p.head_kind != NJF_HEAD_TRANSFORMER) epi_wait_acc(e);
-        trunk_blocks_epilogue(e, g, p.dens, 0, rs);
+        trunk_blocks_epilogue(e, g, p.dens, 0, rs, sc->taps);
         // lin_out: 15 geometry features + density pre-activation (action_decoder_jacobian.py:106-112)
         float geo[16];
         {
@@ -424,11 +430,11 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         }
         if (p.head_kind == NJF_HEAD_MLP) {
           // second ResnetFC on the same gathered point (action_decoder_jacobian.py:324-337)
-          write_posenc(e, rs.cam, valid);
+          write_posenc(e, rs.cam, valid, g.debug);
           epi_publish(e);  // -> lin_in (jacobian head)
-          gather_segment<128>(e, g, 384, rs.ix, rs.iy, rs.pixbase);
+          gather_segment<128>(e, g, sc->taps, 384);
           epi_wait_acc(e);
-          trunk_blocks_epilogue(e, g, p.jac, 384, rs);
+          trunk_blocks_epilogue(e, g, p.jac, 384, rs, sc->taps);
           uint32_t r[32];
           tmem_ld32(e.tmem + 128, r);
           tmem_ld_wait();
@@ -737,6 +743,8 @@ int make_geom(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a,
   g.CH = CH;
   g.Hf = a->Hf;
   g.Wf = a->Wf;
+  const char* dbg = getenv("NJF_DEBUG_SKIP");
+  g.debug = dbg ? atoi(dbg) : 0;
   (void)f;
   return 0;
 }

@@ -24,6 +24,7 @@ struct PassGeom {
   const float* ctxt_k;    // [B][9]
   const __half* map;      // hoisted map of this pass [B][Hf*Wf][CH]
   int CH, Hf, Wf;
+  int debug;              // NJF_DEBUG_SKIP bits (timing attribution only): 1 skip gather, 2 skip posenc
 };
 
 struct RowState {
@@ -102,19 +103,33 @@ __device__ __forceinline__ void row_setup(const PassGeom& g, int group, int tile
   rs.pixbase = b * g.Hf * g.Wf;
 }
 
+// sin(t) for |t| up to ~1e5: 3-term Cody-Waite reduction by 2*pi (FMA, constants with short
+// mantissas so n*C1 is exact), then the SFU sine on [-pi, pi] (abs error ~4e-7 incl. reduction;
+// checked against float64 in DESIGN.md section 5).  The argument is the SAME fp32 number the
+// reference feeds to torch.sin, so its large-argument rounding behaviour is reproduced.
+__device__ __forceinline__ float sin_cw(float t) {
+  const float n = rintf(t * 0.15915494f);
+  float r = fmaf(n, -6.28125f, t);
+  r = fmaf(n, -1.9350052e-3f, r);
+  r = fmaf(n, -3.019916e-7f, r);
+  return __sinf(r);
+}
+
 // NeRFEncoding(63) of the camera-space point into A-tile K-block 0 (columns 60..63 are zero: the
 // raw-xyz columns are applied in fp32 by the first epilogue).  Column order: sin block
 // (dim-major, freq-minor), cos block (= sin(t + pi/2)), like nerfstudio's torch implementation.
-__device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)[3], bool valid) {
+__device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)[3], bool valid,
+                                             int debug = 0) {
   float v[64];
+  if (debug & 2) valid = false;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const float s0 = __fmul_rn(6.2831855f, cam[i]);
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
       const float t = s0 * static_cast<float>(1 << k);  // exact power-of-two scaling
-      v[i * 10 + k] = sinf(t);
-      v[30 + i * 10 + k] = sinf(__fadd_rn(t, 1.5707964f));
+      v[i * 10 + k] = sin_cw(t);
+      v[30 + i * 10 + k] = sin_cw(__fadd_rn(t, 1.5707964f));
     }
   }
   v[60] = v[61] = v[62] = v[63] = 0.f;
@@ -132,13 +147,40 @@ __device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)
 }
 
 // ----------------------------------------------------------------------------- gather
-// Bilinear (align_corners=True, border) gather of NCH hoisted channels starting at channel ch0 for
-// the 32 rows owned by this warp; each tap is one contiguous NCH*2-byte read spread over the
-// lanes (8 B / lane).  Result (fp16) goes to the slot's staging buffer.
+// Per-row bilinear taps (F.grid_sample align_corners=True, padding_mode="border"): computed ONCE per
+// row by the row's own thread, then broadcast-read by the gathering warp for every channel segment.
+struct TapEntry {
+  int pix[4];   // global pixel index (view*Hf*Wf + y*Wf + x) of the nw, ne, sw, se taps
+  float w[4];   // their weights (all zero for padding rows)
+};
+__device__ __forceinline__ void write_taps(TapEntry* tab, int row, const RowState& rs, int Hf, int Wf) {
+  int4 px = make_int4(0, 0, 0, 0);
+  float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rs.pixbase >= 0) {
+    const float x0 = floorf(rs.ix), y0 = floorf(rs.iy);
+    const float x1 = x0 + 1.f, y1 = y0 + 1.f;
+    w.x = (x1 - rs.ix) * (y1 - rs.iy);
+    w.y = (rs.ix - x0) * (y1 - rs.iy);
+    w.z = (x1 - rs.ix) * (rs.iy - y0);
+    w.w = (rs.ix - x0) * (rs.iy - y0);
+    const int xi = static_cast<int>(x0), yi = static_cast<int>(y0);
+    const int xj = min(xi + 1, Wf - 1), yj = min(yi + 1, Hf - 1);  // out-of-range taps have weight 0
+    px.x = rs.pixbase + yi * Wf + xi;
+    px.y = rs.pixbase + yi * Wf + xj;
+    px.z = rs.pixbase + yj * Wf + xi;
+    px.w = rs.pixbase + yj * Wf + xj;
+  }
+  *reinterpret_cast<int4*>(tab[row].pix) = px;
+  *reinterpret_cast<float4*>(tab[row].w) = w;
+}
+
+// Gather of NCH hoisted channels starting at channel ch0 for the 32 rows owned by this warp; each
+// tap is one contiguous NCH*2-byte read spread over the lanes (8 B / lane), interpolation in
+// packed fp32 (FFMA2).  Result (fp16) goes to the slot's staging buffer.
 template <int NCH>
-__device__ __forceinline__ void gather_segment(const EpiCtx& e, const PassGeom& g, int ch0, float ix, float iy,
-                                               int pixbase) {
+__device__ __forceinline__ void gather_segment(const EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0) {
   static_assert(NCH == 128 || NCH == 64, "segment width");
+  if (g.debug & 1) return;
   const int lane = threadIdx.x & 31;
   const int wrow0 = e.row & ~31;
   const bool active = (NCH == 128) || lane < 16;
@@ -148,47 +190,35 @@ __device__ __forceinline__ void gather_segment(const EpiCtx& e, const PassGeom& 
 #pragma unroll 1
   for (int j0 = 0; j0 < 32; j0 += U) {
     uint2 t[U][4];
-    float w[U][4];
+    float4 w[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const float bx = __shfl_sync(0xffffffffu, ix, j0 + u);
-      const float by = __shfl_sync(0xffffffffu, iy, j0 + u);
-      const int pb = __shfl_sync(0xffffffffu, pixbase, j0 + u);
-      const float x0 = floorf(bx), y0 = floorf(by);
-      const float x1 = x0 + 1.f, y1 = y0 + 1.f;
-      w[u][0] = (x1 - bx) * (y1 - by);
-      w[u][1] = (bx - x0) * (y1 - by);
-      w[u][2] = (x1 - bx) * (by - y0);
-      w[u][3] = (bx - x0) * (by - y0);
-      const int xi = static_cast<int>(x0), yi = static_cast<int>(y0);
-      const int xj = min(xi + 1, g.Wf - 1), yj = min(yi + 1, g.Hf - 1);  // out-of-range taps have weight 0
-      if (pb >= 0 && active) {
-        const uint2* r0 = mp + static_cast<size_t>(pb + yi * g.Wf) * pstride;
-        const uint2* r1 = mp + static_cast<size_t>(pb + yj * g.Wf) * pstride;
-        t[u][0] = __ldg(r0 + xi * pstride);
-        t[u][1] = __ldg(r0 + xj * pstride);
-        t[u][2] = __ldg(r1 + xi * pstride);
-        t[u][3] = __ldg(r1 + xj * pstride);
+      const TapEntry* te = taps + wrow0 + j0 + u;
+      const int4 px = *reinterpret_cast<const int4*>(te->pix);
+      w[u] = *reinterpret_cast<const float4*>(te->w);
+      if (active) {
+        t[u][0] = __ldg(mp + static_cast<size_t>(px.x) * pstride);
+        t[u][1] = __ldg(mp + static_cast<size_t>(px.y) * pstride);
+        t[u][2] = __ldg(mp + static_cast<size_t>(px.z) * pstride);
+        t[u][3] = __ldg(mp + static_cast<size_t>(px.w) * pstride);
       } else {
         t[u][0] = t[u][1] = t[u][2] = t[u][3] = make_uint2(0u, 0u);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float wq[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+      float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&t[u][q].x));
-        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&t[u][q].y));
-        a0 = fmaf(lo.x, w[u][q], a0);
-        a1 = fmaf(lo.y, w[u][q], a1);
-        a2 = fmaf(hi.x, w[u][q], a2);
-        a3 = fmaf(hi.y, w[u][q], a3);
+        const float2 ww = make_float2(wq[q], wq[q]);
+        lo = ffma2(__half22float2(*reinterpret_cast<const __half2*>(&t[u][q].x)), ww, lo);
+        hi = ffma2(__half22float2(*reinterpret_cast<const __half2*>(&t[u][q].y)), ww, hi);
       }
       if (active) {
         uint2 o;
-        o.x = pack_f16x2(a0, a1);
-        o.y = pack_f16x2(a2, a3);
+        o.x = pack_f16x2(lo.x, lo.y);
+        o.y = pack_f16x2(hi.x, hi.y);
         *reinterpret_cast<uint2*>(e.tz + tz_offset(wrow0 + j0 + u, lane >> 1) + (lane & 1) * 8) = o;
       }
     }
@@ -204,10 +234,16 @@ __device__ __forceinline__ void epi_x_first(const EpiCtx& e, int c0, const float
   tmem_ld32(e.tmem + c0, r);
   tmem_ld_wait();
   float v[32];
+  const float2 cx = make_float2(cam[0], cam[0]), cy = make_float2(cam[1], cam[1]), cz = make_float2(cam[2], cam[2]);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float4 q = __ldg(e0 + c0 + j);
-    v[j] = __uint_as_float(r[j]) + fmaf(q.z, cam[2], fmaf(q.y, cam[1], fmaf(q.x, cam[0], q.w)));
+  for (int j = 0; j < 32; j += 2) {
+    const float4 q0 = __ldg(e0 + c0 + j), q1 = __ldg(e0 + c0 + j + 1);
+    float2 t = ffma2(make_float2(q0.x, q1.x), cx, make_float2(q0.w, q1.w));
+    t = ffma2(make_float2(q0.y, q1.y), cy, t);
+    t = ffma2(make_float2(q0.z, q1.z), cz, t);
+    t = fadd2(t, make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+    v[j] = t.x;
+    v[j + 1] = t.y;
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -215,9 +251,9 @@ __device__ __forceinline__ void epi_x_first(const EpiCtx& e, int c0, const float
     const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const float2 f = __half22float2(h[t]);
-      v[8 * j + 2 * t] += f.x;
-      v[8 * j + 2 * t + 1] += f.y;
+      const float2 s2 = fadd2(make_float2(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]), __half22float2(h[t]));
+      v[8 * j + 2 * t] = s2.x;
+      v[8 * j + 2 * t + 1] = s2.y;
     }
   }
 #pragma unroll
@@ -236,14 +272,14 @@ __device__ __forceinline__ void epi_x_first(const EpiCtx& e, int c0, const float
 // trunk's hoisted channels is in the staging buffer.  Leaves the lin_out accumulator (bias NOT
 // yet added) in TMEM columns [128, 128+n_out).
 __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom& g, const TrunkTab& tab, int seg_ch0,
-                                                      const RowState& rs) {
+                                                      const RowState& rs, const TapEntry* taps) {
   // E0: X_0 = lin_in + b_in + raw-xyz + tz_0
   for (int c0 = 0; c0 < 128; c0 += 32) epi_x_first(e, c0, tab.e0, rs.cam);
   epi_publish(e);  // -> fc_0 (block 0)
 #pragma unroll 1
   for (int k = 0; k < 5; ++k) {
     // overlap: gather the next hoisted segment while the tensor pipe runs fc_0
-    if (k < 2) gather_segment<128>(e, g, seg_ch0 + 128 * (k + 1), rs.ix, rs.iy, rs.pixbase);
+    if (k < 2) gather_segment<128>(e, g, taps, seg_ch0 + 128 * (k + 1));
     epi_wait_acc(e);
     for (int c0 = 0; c0 < 128; c0 += 32) epi_relu_to_a(e, 128 + c0, c0, tab.bias + (2 * k) * 128);
     epi_publish(e);  // -> fc_1 (block k), accumulates onto x
