@@ -201,7 +201,7 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
         const double scale = 1.0 / std::sqrt(64.0);
         for (int h = 0; h < 8; ++h)
           for (int a = 0; a < A; ++a) {
-            const int n = h * A + a;  // logit / attention column
+            const int n = h * 8 + a;  // logit / attention column (heads padded to 8 keys)
             for (int k = 0; k < 64; ++k) {
               double s = 0;
               for (int d = 0; d < 64; ++d) s += static_cast<double>(wq_[(h * 64 + d) * 64 + k]) * K[a * 512 + h * 64 + d];

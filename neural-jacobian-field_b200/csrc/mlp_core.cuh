@@ -1,12 +1,13 @@
 // Warp-specialised tcgen05 "layer chain" machinery shared by the render kernels
 // and the self-test.
 //
-// One CTA = 320 threads:
-//   warps 0-3  : epilogue warpgroup of tile slot 0 (thread = one sample point = one TMEM lane)
-//   warps 4-7  : epilogue warpgroup of tile slot 1
-//   warp  8    : MMA issuer (one elected thread issues every tcgen05.mma / commit)
-//   warp  9    : weight loader (one elected thread streams packed layer images with
-//                cp.async.bulk into a 2-stage shared-memory ring)
+// One CTA = 576 threads:
+//   warps 0-7   : epilogue group of tile slot 0 -- TWO threads per sample point (TMEM lane):
+//                 warp = 4*h + q handles rows 32q..32q+31, column half h (64 of every 128 columns)
+//   warps 8-15  : epilogue group of tile slot 1
+//   warp  16    : MMA issuer (one elected thread issues every tcgen05.mma / commit)
+//   warp  17    : weight loader (one elected thread streams packed layer images with
+//                 cp.async.bulk into a 2-stage shared-memory ring)
 // Both slots run the SAME step program, so one weight stage feeds two 128-row tiles
 // and the tensor pipe works on one slot while the other slot's warpgroup runs its
 // epilogue (ping-pong).
@@ -19,10 +20,10 @@ namespace njf {
 
 constexpr int kRows = 128;
 constexpr int kSlots = 2;
-constexpr int kEpiThreads = 256;
-constexpr int kIssuerWarp = 8;
-constexpr int kLoaderWarp = 9;
-constexpr int kThreads = 320;
+constexpr int kSlotThreads = 256;   // epilogue threads per slot (2 per row)
+constexpr int kIssuerWarp = 16;
+constexpr int kLoaderWarp = 17;
+constexpr int kThreads = 576;
 constexpr int kStages = 2;
 constexpr uint32_t kStageBytes = 32768;  // up to N=128 x K=128 fp16
 constexpr uint32_t kATileBytes = 32768;  // 128 rows x 128 cols fp16 (2 K-blocks of 16 KB)
@@ -58,7 +59,7 @@ struct SmemMap {
   static constexpr uint32_t kScratch = kMisc + kMiscBytes;          // kernel-specific
 };
 struct Barriers {
-  uint64_t a_ready[kSlots];    // 128 arrivals: slot's A tile written (+ TMEM reads drained)
+  uint64_t a_ready[kSlots];    // 256 arrivals: slot's A tile written (+ TMEM reads drained)
   uint64_t acc_ready[kSlots];  // tcgen05.commit: slot's accumulator complete
   uint64_t w_full[kStages];    // bulk-copy transaction bytes landed
   uint64_t w_empty[kStages];   // tcgen05.commit: both slots' MMAs done with the stage
@@ -80,7 +81,7 @@ __device__ __forceinline__ CtaCtx cta_setup(uint8_t* smem_raw) {
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSlots; ++s) {
-      mbar_init(&c.bars->a_ready[s], kRows);
+      mbar_init(&c.bars->a_ready[s], kSlotThreads);
       mbar_init(&c.bars->acc_ready[s], 1);
     }
     for (int s = 0; s < kStages; ++s) {
@@ -171,12 +172,22 @@ struct EpiCtx {
   uint32_t acc_par;
   int row;            // 0..127 (== TMEM lane)
   int slot;
+  int half;           // 0/1: which 64 of every 128 columns this thread handles
+  int col0;           // 64 * half
+  int q;              // row quarter (warp % 4)
 };
+// named barrier ids: 0 = __syncthreads, 1..2 = slot groups (256 threads),
+// 3..10 = the two warps (64 threads) that share a row quarter of a slot
+__device__ __forceinline__ void slot_bar(const EpiCtx& e) { named_bar_sync(1 + e.slot, kSlotThreads); }
+__device__ __forceinline__ void pair_bar(const EpiCtx& e) { named_bar_sync(3 + e.slot * 4 + e.q, 64); }
 __device__ __forceinline__ EpiCtx epi_ctx(const CtaCtx& c) {
   EpiCtx e;
   const int warp = threadIdx.x >> 5;
-  e.slot = warp >> 2;
-  e.row = threadIdx.x & 127;
+  e.slot = warp >> 3;
+  e.half = (warp >> 2) & 1;
+  e.col0 = e.half * 64;
+  e.q = warp & 3;
+  e.row = e.q * 32 + (threadIdx.x & 31);
   e.a_tile = c.smem + SmemMap::kA + e.slot * kATileBytes;
   e.tz = c.smem + SmemMap::kTz + e.slot * kTzBytes;
   e.a_ready = &c.bars->a_ready[e.slot];

@@ -13,14 +13,18 @@
 namespace njf {
 
 struct SlotScratch {
-  float dd[kRows];    // delta * sigma of the current tile
-  float cum[kRows];   // exclusive prefix sums (fp32) of dd
-  float wts[528];     // transmittance weights of the ray group (proposal: PDF input)
-  float cdf[544];     // PDF scratch
+  float dd[kRows];       // delta * sigma of the current tile
+  float cum[kRows];      // exclusive prefix sums (fp32) of dd
+  float wrow[kRows];     // transmittance weight of each row (shared between the row's two threads)
+  float wts[528];        // transmittance weights of the ray group (proposal: PDF input)
+  float cdf[544];        // PDF scratch
   TapEntry taps[kRows];  // bilinear taps of the current tile
+  float2 xch[kRows][2];  // per-row exchange between the two column-half threads (LayerNorm sums)
+  float4 rgbp[kRows];    // colour-head partial dot products of the upper column half
 };
 constexpr uint32_t kScratchSlotBytes = (sizeof(SlotScratch) + 15) & ~15u;
 constexpr uint32_t kSmemBytes = SmemMap::kScratch + kSlots * kScratchSlotBytes + 64 + 1024;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 __device__ __forceinline__ SlotScratch* slot_scratch(const CtaCtx& c, int slot) {
   return reinterpret_cast<SlotScratch*>(c.smem + SmemMap::kScratch + slot * kScratchSlotBytes);
@@ -30,25 +34,30 @@ __device__ __forceinline__ uint32_t* cta_minmax(const CtaCtx& c) {
 }
 
 // transmittance weights of this tile's rows (RaySamples.get_weights, ray_samplers.py:77-101):
-// stores dd, scans per ray (double accumulation), returns this row's weight.
+// the h=0 thread of each row stores dd, one warp per ray scans (double accumulation), every
+// thread of the row gets the row's weight back.
 __device__ __forceinline__ float tile_weights(const EpiCtx& e, SlotScratch* sc, const PassGeom& g, int tile,
                                               float dd, double& carry) {
-  const int wq = (threadIdx.x >> 5) & 3;
-  sc->dd[e.row] = dd;
-  named_bar_sync(1 + e.slot, kRows);
+  const int w8 = (threadIdx.x >> 5) & 7;
+  if (e.half == 0) sc->dd[e.row] = dd;
+  slot_bar(e);
   if (g.T == 1) {
-    for (int lr = wq; lr < g.G; lr += 4) {
+    for (int lr = w8; lr < g.G; lr += 8) {
       double c0 = 0.0;
       excl_scan_warp(sc->dd + lr * g.S, g.S, c0, sc->cum + lr * g.S);
     }
-  } else if (wq == 0) {
+  } else if (w8 == 0) {
     const int n = min(kRows, g.S - tile * kRows);
     excl_scan_warp(sc->dd, n, carry, sc->cum);
   }
-  named_bar_sync(1 + e.slot, kRows);
-  const float tr = expf(-sc->cum[e.row]);
-  const float alpha = 1.f - expf(-dd);
-  return alpha * tr;
+  slot_bar(e);
+  if (e.half == 0) {
+    const float tr = expf(-sc->cum[e.row]);
+    const float alpha = 1.f - expf(-dd);
+    sc->wrow[e.row] = alpha * tr;
+  }
+  slot_bar(e);
+  return sc->wrow[e.row];
 }
 
 // ============================================================================= proposal pass
@@ -89,7 +98,8 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
   } else {
     EpiCtx e = epi_ctx(c);
     SlotScratch* sc = slot_scratch(c, e.slot);
-    const int wq = warp & 3;
+    const int w8 = warp & 7;
+    const int lane = threadIdx.x & 31;
     const int nb = p.n_out + 1;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
       const int group = 2 * it + e.slot;
@@ -98,27 +108,30 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
       for (int tile = 0; tile < g.T; ++tile) {
         RowState rs;
         row_setup(g, group, tile, e.row, rs);
-        write_taps(sc->taps, e.row, rs, g.Hf, g.Wf);
+        if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf);
         write_posenc(e, rs.cam, rs.ray >= 0, g.debug);
         epi_publish(e);  // -> lin_in
         __syncwarp();
         gather_segment<128>(e, g, sc->taps, 0);
         epi_wait_acc(e);
         trunk_blocks_epilogue(e, g, p.trunk, 0, rs, sc->taps);
-        uint32_t r[16];
-        tmem_ld16(e.tmem + 128, r);
-        tmem_ld_wait();
-        // density = trunc_exp(x - 1) (density_decoder.py:64-66, activations.py:32-35)
-        const float sigma = expf(__fsub_rn(__uint_as_float(r[0]) + __ldg(p.trunk.b_out), 1.f));
-        const float dd = (rs.ray >= 0 && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
+        float dd = 0.f;
+        if (e.half == 0) {
+          uint32_t r[16];
+          tmem_ld16(e.tmem + 128, r);
+          tmem_ld_wait();
+          // density = trunc_exp(x - 1) (density_decoder.py:64-66, activations.py:32-35)
+          const float sigma = expf(__fsub_rn(__uint_as_float(r[0]) + __ldg(p.trunk.b_out), 1.f));
+          dd = (rs.ray >= 0 && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
+        }
         const float w = tile_weights(e, sc, g, tile, dd, carry);
-        if (rs.ray >= 0) {
+        if (e.half == 0 && rs.ray >= 0) {
           sc->wts[g.T == 1 ? e.row : rs.s] = w;
           if (p.weights_out) p.weights_out[static_cast<size_t>(rs.ray) * g.S + rs.s] = w;
         }
       }
-      named_bar_sync(1 + e.slot, kRows);
-      for (int lr = wq; lr < g.G; lr += 4) {
+      slot_bar(e);
+      for (int lr = w8; lr < g.G; lr += 8) {
         const int ray = group * g.G + lr;
         if (ray >= g.NR) break;
         pdf_resample_warp(sc->wts + lr * g.S, g.S, g.bins + static_cast<size_t>(ray) * g.bins_stride,
@@ -126,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
                           sc->cdf + lr * (g.S + 1), p.bins_out + static_cast<size_t>(ray) * nb,
                           p.inds_out ? p.inds_out + static_cast<size_t>(ray) * nb : nullptr);
       }
-      named_bar_sync(1 + e.slot, kRows);
+      slot_bar(e);
     }
   }
   cta_teardown(c);
@@ -149,86 +162,110 @@ struct FieldParams {
   uint32_t* minmax;  // [2] ordered-uint encoded min / max of steps
 };
 
-// LayerNorm(64) of x -> fp16 -> A-tile K-block 0
-__device__ __forceinline__ void ln64_to_a(const EpiCtx& e, const float (&x)[64], const float* __restrict__ gam,
-                                          const float* __restrict__ bet) {
-  float mean = 0.f;
+// ---- helpers on this thread's 32 of the 64 transformer / colour columns (columns 32h .. 32h+31)
+__device__ __forceinline__ void ld_acc32(const EpiCtx& e, float (&v)[32]) {
+  uint32_t r[32];
+  tmem_ld32(e.tmem + 128 + 32 * e.half, r);
+  tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < 64; ++j) mean += x[j];
-  mean *= (1.f / 64.f);
-  float var = 0.f;
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void store32_to_a(const EpiCtx& e, const float (&v)[32]) {
+  uint32_t pk[16];
 #pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    const float d = x[j] - mean;
-    var = fmaf(d, d, var);
-  }
-  const float rstd = rsqrtf(var * (1.f / 64.f) + 1e-5f);
+  for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
+  a_store32(e, 32 * e.half, pk);
+}
+// v[j] += tab[32h + j] (fp32 vector loads)
+__device__ __forceinline__ void add_vec32(const EpiCtx& e, float (&v)[32], const float* __restrict__ tab) {
+  const float4* t4 = reinterpret_cast<const float4*>(tab + 32 * e.half);
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint32_t pk[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int c = 32 * h + 2 * j;
-      const float y0 = fmaf((x[c] - mean) * rstd, __ldg(gam + c), __ldg(bet + c));
-      const float y1 = fmaf((x[c + 1] - mean) * rstd, __ldg(gam + c + 1), __ldg(bet + c + 1));
-      pk[j] = pack_f16x2(y0, y1);
-    }
-    a_store32(e, 32 * h, pk);
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = __ldg(t4 + j);
+    const float2 s0 = fadd2(make_float2(v[4 * j], v[4 * j + 1]), make_float2(b.x, b.y));
+    const float2 s1 = fadd2(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(b.z, b.w));
+    v[4 * j] = s0.x; v[4 * j + 1] = s0.y; v[4 * j + 2] = s1.x; v[4 * j + 3] = s1.y;
   }
 }
-// load 64 accumulator columns (TMEM cols [128,192) of the slot)
-__device__ __forceinline__ void ld_acc64(const EpiCtx& e, float (&v)[64]) {
+// LayerNorm over the row's 64 values (32 here, 32 in the partner thread) -> fp16 -> A tile
+__device__ __forceinline__ void ln64_to_a(const EpiCtx& e, SlotScratch* sc, const float (&x)[32],
+                                          const float* __restrict__ gam, const float* __restrict__ bet) {
+  float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint32_t r[32];
-    tmem_ld32(e.tmem + 128 + 32 * h, r);
-    tmem_ld_wait();
+  for (int j = 0; j < 32; j += 2) acc = fadd2(acc, make_float2(x[j], x[j + 1]));
+  sc->xch[e.row][e.half].x = acc.x + acc.y;
+  pair_bar(e);
+  const float mean = (sc->xch[e.row][0].x + sc->xch[e.row][1].x) * (1.f / 64.f);
+  float2 sq = make_float2(0.f, 0.f);
+  const float2 nm = make_float2(-mean, -mean);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[32 * h + j] = __uint_as_float(r[j]);
+  for (int j = 0; j < 32; j += 2) {
+    const float2 d = fadd2(make_float2(x[j], x[j + 1]), nm);
+    sq = ffma2(d, d, sq);
   }
-}
-__device__ __forceinline__ void store64_to_a(const EpiCtx& e, const float (&v)[64]) {
+  sc->xch[e.row][e.half].y = sq.x + sq.y;
+  pair_bar(e);
+  const float var = (sc->xch[e.row][0].y + sc->xch[e.row][1].y) * (1.f / 64.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float4* g4 = reinterpret_cast<const float4*>(gam + 32 * e.half);
+  const float4* b4 = reinterpret_cast<const float4*>(bet + 32 * e.half);
+  uint32_t pk[16];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint32_t pk[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[32 * h + 2 * j], v[32 * h + 2 * j + 1]);
-    a_store32(e, 32 * h, pk);
+  for (int j = 0; j < 8; ++j) {
+    const float4 gg = __ldg(g4 + j), bb = __ldg(b4 + j);
+    const float y0 = fmaf((x[4 * j + 0] - mean) * rstd, gg.x, bb.x);
+    const float y1 = fmaf((x[4 * j + 1] - mean) * rstd, gg.y, bb.y);
+    const float y2 = fmaf((x[4 * j + 2] - mean) * rstd, gg.z, bb.z);
+    const float y3 = fmaf((x[4 * j + 3] - mean) * rstd, gg.w, bb.w);
+    pk[2 * j] = pack_f16x2(y0, y1);
+    pk[2 * j + 1] = pack_f16x2(y2, y3);
   }
+  a_store32(e, 32 * e.half, pk);
 }
-
+// softmax over the A real keys of each of this thread's 4 heads (heads are padded to 8 columns)
 template <int A>
-__device__ __forceinline__ void softmax_heads(float (&lg)[64]) {
+__device__ __forceinline__ void softmax_heads(float (&lg)[32]) {
 #pragma unroll
-  for (int h = 0; h < 8; ++h) {
+  for (int h = 0; h < 4; ++h) {
     float m = -3.0e38f;
 #pragma unroll
-    for (int a = 0; a < A; ++a) m = fmaxf(m, lg[h * A + a]);
+    for (int a = 0; a < A; ++a) m = fmaxf(m, lg[h * 8 + a]);
     float s = 0.f;
 #pragma unroll
     for (int a = 0; a < A; ++a) {
-      const float ev = expf(lg[h * A + a] - m);
-      lg[h * A + a] = ev;
+      const float ev = __expf(lg[h * 8 + a] - m);
+      lg[h * 8 + a] = ev;
       s += ev;
     }
-    const float inv = 1.f / s;
+    const float inv = __fdividef(1.f, s);
 #pragma unroll
-    for (int a = 0; a < A; ++a) lg[h * A + a] *= inv;
+    for (int a = 0; a < 8; ++a) lg[h * 8 + a] = (a < A) ? lg[h * 8 + a] * inv : 0.f;
   }
-#pragma unroll
-  for (int j = 8 * A; j < 64; ++j) lg[j] = 0.f;
+}
+// exact-erf GELU (nn.GELU default): erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7)
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float z = fabsf(v) * 0.70710678f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfa = 1.f - poly * t * __expf(-z * z);
+  const float erfv = copysignf(erfa, v);
+  return 0.5f * v * (1.f + erfv);
 }
 
 // Cross-attention Jacobian head (action_decoder_jacobian.py:418-446; transformer.py:63-135) with
 // the key/value projections folded into M1/M2 by njf_field_create.  Pre: accumulator wait for
-// (lin_in, q_enc) done; the 64 hoisted query channels are in the staging buffer.
-__device__ __forceinline__ void transformer_head(EpiCtx& e, const HeadTab& H, int A, const RowState& rs,
-                                                 float (&J)[32]) {
-  float x[64];
-  ld_acc64(e, x);
+// (lin_in, q_enc) done; the 64 hoisted query channels are in the staging buffer.  Each thread
+// carries 32 of the row's 64 stream values and produces 16 of the 32 (padded) Jacobian columns.
+__device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, const HeadTab& H, int A,
+                                                 const RowState& rs, float (&J)[16]) {
+  float x[32];
+  ld_acc32(e, x);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint4 q = *reinterpret_cast<const uint4*>(e.tz + tz_offset(e.row, j));
+  for (int j = 0; j < 4; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(e.tz + tz_offset(e.row, 4 * e.half + j));
     const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -238,20 +275,19 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, const HeadTab& H, in
     }
   }
 #pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    const float4 q = __ldg(H.q_e0 + j);
+  for (int j = 0; j < 32; ++j) {
+    const float4 q = __ldg(H.q_e0 + 32 * e.half + j);
     x[j] += fmaf(q.z, rs.cam[2], fmaf(q.y, rs.cam[1], fmaf(q.x, rs.cam[0], q.w)));
   }
 #pragma unroll 1
   for (int l = 0; l < 3; ++l) {
     const XfLayerTab& L = H.layer[l];
-    ln64_to_a(e, x, L.ln1_g, L.ln1_b);
+    ln64_to_a(e, sc, x, L.ln1_g, L.ln1_b);
     epi_publish(e);  // -> M1: scaled logits over (head, key)
     epi_wait_acc(e);
     {
-      float lg[64];
-      ld_acc64(e, lg);
-      // softmax over the A keys of each of the 8 heads; columns >= 8A are padding
+      float lg[32];
+      ld_acc32(e, lg);
       switch (A) {
         case 1: softmax_heads<1>(lg); break;
         case 2: softmax_heads<2>(lg); break;
@@ -262,46 +298,53 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, const HeadTab& H, in
         case 7: softmax_heads<7>(lg); break;
         default: softmax_heads<8>(lg); break;
       }
-      store64_to_a(e, lg);
+      store32_to_a(e, lg);
     }
     epi_publish(e);  // -> M2: attention . (V W_out)
     epi_wait_acc(e);
     {
-      float t[64];
-      ld_acc64(e, t);
+      float t[32];
+      ld_acc32(e, t);
+      add_vec32(e, t, L.b_o);
 #pragma unroll
-      for (int j = 0; j < 64; ++j) x[j] += t[j] + __ldg(L.b_o + j);
+      for (int j = 0; j < 32; ++j) x[j] += t[j];
     }
-    ln64_to_a(e, x, L.ln2_g, L.ln2_b);
+    ln64_to_a(e, sc, x, L.ln2_g, L.ln2_b);
     epi_publish(e);  // -> W1
     epi_wait_acc(e);
     {
-      float t[64];
-      ld_acc64(e, t);
+      float t[32];
+      ld_acc32(e, t);
+      add_vec32(e, t, L.b_1);
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const float v = t[j] + __ldg(L.b_1 + j);
-        t[j] = 0.5f * v * (1.f + erff(v * 0.70710678f));  // exact GELU (nn.GELU default)
-      }
-      store64_to_a(e, t);
+      for (int j = 0; j < 32; ++j) t[j] = gelu_erf(t[j]);
+      store32_to_a(e, t);
     }
     epi_publish(e);  // -> W2
     epi_wait_acc(e);
     {
-      float t[64];
-      ld_acc64(e, t);
+      float t[32];
+      ld_acc32(e, t);
+      add_vec32(e, t, L.b_2);
 #pragma unroll
-      for (int j = 0; j < 64; ++j) x[j] += t[j] + __ldg(L.b_2 + j);
+      for (int j = 0; j < 32; ++j) x[j] += t[j];
     }
   }
-  store64_to_a(e, x);
+  store32_to_a(e, x);
   epi_publish(e);  // -> jacobian_head Linear(64, 3A)
   epi_wait_acc(e);
-  uint32_t r[32];
-  tmem_ld32(e.tmem + 128, r);
+  uint32_t r[16];
+  tmem_ld16(e.tmem + 128 + 16 * e.half, r);
   tmem_ld_wait();
+  const float4* b4 = reinterpret_cast<const float4*>(H.b_head + 16 * e.half);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) J[j] = __uint_as_float(r[j]) + __ldg(H.b_head + j);
+  for (int j = 0; j < 4; ++j) {
+    const float4 b = __ldg(b4 + j);
+    J[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
+    J[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
+    J[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
+    J[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+  }
 }
 
 // SH degree 4 (tiny-cuda-nn convention) of the unit direction (action_decoder_jacobian.py:194-199)
@@ -357,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
   } else {
     EpiCtx e = epi_ctx(c);
     SlotScratch* sc = slot_scratch(c, e.slot);
-    const int wq = warp & 3;
+    const int w8 = warp & 7;
     const int lane = threadIdx.x & 31;
     const int A = p.A, A3 = 3 * p.A;
     const int nch = 8 + A3;  // composite channels: rgb3, t, 1, pos3, J(3A)
@@ -366,36 +409,35 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
       const int group = 2 * it + e.slot;
       if (group >= g.NG) continue;
       double carry = 0.0;
-      float cs0 = 0.f, cs1 = 0.f;  // column sums held by warp 0 across the tiles of a long ray
+      float cs0 = 0.f, cs1 = 0.f;  // column sums held by warp 0 of the slot across the tiles of a long ray
       for (int tile = 0; tile < g.T; ++tile) {
         RowState rs;
         row_setup(g, group, tile, e.row, rs);
         const bool valid = rs.ray >= 0;
-        float J[32];
-        write_taps(sc->taps, e.row, rs, g.Hf, g.Wf);
+        float J[16];  // this thread's 16 of the 32 (padded) Jacobian columns: 16h .. 16h+15
+        if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf);
         write_posenc(e, rs.cam, valid, g.debug);
         epi_publish(e);  // -> lin_in (+ q_enc for the transformer head)
         __syncwarp();
         if (p.head_kind == NJF_HEAD_TRANSFORMER) {
           gather_segment<64>(e, g, sc->taps, 384);
           epi_wait_acc(e);
-          transformer_head(e, p.head, A, rs, J);
+          transformer_head(e, sc, p.head, A, rs, J);
         }
         gather_segment<128>(e, g, sc->taps, 0);
         if (p.head_kind != NJF_HEAD_TRANSFORMER) epi_wait_acc(e);
         trunk_blocks_epilogue(e, g, p.dens, 0, rs, sc->taps);
         // lin_out: 15 geometry features + density pre-activation (action_decoder_jacobian.py:106-112)
-        float geo[16];
-        {
+        float sigma = 0.f;
+        if (e.half == 0) {
+          float geo[16];
           uint32_t r[16];
           tmem_ld16(e.tmem + 128, r);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) geo[j] = __uint_as_float(r[j]) + __ldg(p.dens.b_out + j);
-        }
-        const float sigma = expf(__fsub_rn(geo[15], 1.f));
-        // colour head input [geo15 | sh16 | 0...] (action_decoder_jacobian.py:208)
-        {
+          sigma = expf(__fsub_rn(geo[15], 1.f));
+          // colour head input [geo15 | sh16 | 0...] (action_decoder_jacobian.py:208)
           float sh[16];
           const float* dp = g.dirs + static_cast<size_t>(valid ? rs.ray : 0) * 3;
           sh16(__ldg(dp), __ldg(dp + 1), __ldg(dp + 2), sh);
@@ -407,25 +449,41 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           for (int j = 0; j < 7; ++j) pk[8 + j] = pack_f16x2(sh[1 + 2 * j], sh[2 + 2 * j]);
           pk[15] = pack_f16x2(sh[15], 0.f);
           a_store32(e, 0, pk);
+        } else {
           a_zero32(e, 32);
         }
         epi_publish(e);  // -> color1
         epi_wait_acc(e);
-        for (int c0 = 0; c0 < 64; c0 += 32) epi_relu_to_a(e, 128 + c0, c0, p.color.b1);
+        epi_relu_to_a(e, 128 + 32 * e.half, 32 * e.half, p.color.b1);
         epi_publish(e);  // -> color2
         epi_wait_acc(e);
-        float rgb[3];
+        float rgb[3] = {0.f, 0.f, 0.f};
         {
-          float h2[64];
-          ld_acc64(e, h2);
-#pragma unroll
-          for (int j = 0; j < 64; ++j) h2[j] = fmaxf(h2[j] + __ldg(p.color.b2 + j), 0.f);
+          float h2[32];
+          ld_acc32(e, h2);
+          add_vec32(e, h2, p.color.b2);
+          float part[3];
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
-            float a = __ldg(p.color.b3 + ch);
+            const float4* w4 = reinterpret_cast<const float4*>(p.color.w3 + ch * 64 + 32 * e.half);
+            float a = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) a = fmaf(__ldg(p.color.w3 + ch * 64 + j), h2[j], a);
-            rgb[ch] = 1.f / (1.f + expf(-a));
+            for (int j = 0; j < 8; ++j) {
+              const float4 ww = __ldg(w4 + j);
+              a = fmaf(ww.x, fmaxf(h2[4 * j + 0], 0.f), a);
+              a = fmaf(ww.y, fmaxf(h2[4 * j + 1], 0.f), a);
+              a = fmaf(ww.z, fmaxf(h2[4 * j + 2], 0.f), a);
+              a = fmaf(ww.w, fmaxf(h2[4 * j + 3], 0.f), a);
+            }
+            part[ch] = a;
+          }
+          if (e.half == 1) sc->rgbp[e.row] = make_float4(part[0], part[1], part[2], 0.f);
+          pair_bar(e);
+          if (e.half == 0) {
+            const float4 o = sc->rgbp[e.row];
+            rgb[0] = 1.f / (1.f + expf(-(part[0] + o.x + __ldg(p.color.b3 + 0))));
+            rgb[1] = 1.f / (1.f + expf(-(part[1] + o.y + __ldg(p.color.b3 + 1))));
+            rgb[2] = 1.f / (1.f + expf(-(part[2] + o.z + __ldg(p.color.b3 + 2))));
           }
         }
         if (p.head_kind == NJF_HEAD_MLP) {
@@ -435,49 +493,42 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           gather_segment<128>(e, g, sc->taps, 384);
           epi_wait_acc(e);
           trunk_blocks_epilogue(e, g, p.jac, 384, rs, sc->taps);
-          uint32_t r[32];
-          tmem_ld32(e.tmem + 128, r);
+          uint32_t r[16];
+          tmem_ld16(e.tmem + 128 + 16 * e.half, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) J[j] = __uint_as_float(r[j]) + __ldg(p.jac.b_out + j);
+          for (int j = 0; j < 16; ++j) J[j] = __uint_as_float(r[j]) + __ldg(p.jac.b_out + 16 * e.half + j);
         }
         // ---- weights + compositing (model.py:351-367, 384-394)
         const float dd = (valid && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
         const float w = tile_weights(e, sc, g, tile, dd, carry);
-        if (valid) {
-          const size_t si = static_cast<size_t>(rs.ray) * g.S + rs.s;
-          if (p.steps) p.steps[si] = rs.tmid;
-          if (p.weights) p.weights[si] = w;
-          if (p.sigma) p.sigma[si] = sigma;
-          if (p.positions) {
-            p.positions[si * 3 + 0] = rs.pos[0];
-            p.positions[si * 3 + 1] = rs.pos[1];
-            p.positions[si * 3 + 2] = rs.pos[2];
+        const float ww = valid ? w : 0.f;
+        uint8_t* rowp = e.tz + e.row * 256;
+        if (e.half == 0) {
+          if (valid) {
+            const size_t si = static_cast<size_t>(rs.ray) * g.S + rs.s;
+            if (p.steps) p.steps[si] = rs.tmid;
+            if (p.weights) p.weights[si] = w;
+            if (p.sigma) p.sigma[si] = sigma;
+            if (p.positions) {
+              p.positions[si * 3 + 0] = rs.pos[0];
+              p.positions[si * 3 + 1] = rs.pos[1];
+              p.positions[si * 3 + 2] = rs.pos[2];
+            }
+            if (p.rgb_samples) {
+              p.rgb_samples[si * 3 + 0] = rgb[0];
+              p.rgb_samples[si * 3 + 1] = rgb[1];
+              p.rgb_samples[si * 3 + 2] = rgb[2];
+            }
           }
-          if (p.rgb_samples) {
-            p.rgb_samples[si * 3 + 0] = rgb[0];
-            p.rgb_samples[si * 3 + 1] = rgb[1];
-            p.rgb_samples[si * 3 + 2] = rgb[2];
-          }
-          if (p.jac_out) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < A3) p.jac_out[si * A3 + j] = J[j];
-          }
-        }
-        {
-          // stage w * [rgb, t, 1, pos, J] for the per-ray column sums
-          float v[64];
+          // stage w * [rgb, t, 1, pos, J0..15] : composite columns 0..23
+          float v[24];
           v[0] = rgb[0]; v[1] = rgb[1]; v[2] = rgb[2]; v[3] = rs.tmid; v[4] = 1.f;
           v[5] = rs.pos[0]; v[6] = rs.pos[1]; v[7] = rs.pos[2];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[8 + j] = (j < A3) ? J[j] : 0.f;
+          for (int j = 0; j < 16; ++j) v[8 + j] = (j < A3) ? J[j] : 0.f;
 #pragma unroll
-          for (int j = 40; j < 64; ++j) v[j] = 0.f;
-          const float ww = valid ? w : 0.f;
-          uint8_t* rowp = e.tz + e.row * 256;
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
+          for (int q = 0; q < 6; ++q) {
             float4 o;
             o.x = valid ? ww * v[4 * q + 0] : 0.f;
             o.y = valid ? ww * v[4 * q + 1] : 0.f;
@@ -496,8 +547,25 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
             atomicMin(&mm[0], f2ord(tmn));
             atomicMax(&mm[1], f2ord(tmx));
           }
+        } else {
+          // J16..31 : composite columns 24..39
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 o;
+            o.x = (valid && 16 + 4 * q + 0 < A3) ? ww * J[4 * q + 0] : 0.f;
+            o.y = (valid && 16 + 4 * q + 1 < A3) ? ww * J[4 * q + 1] : 0.f;
+            o.z = (valid && 16 + 4 * q + 2 < A3) ? ww * J[4 * q + 2] : 0.f;
+            o.w = (valid && 16 + 4 * q + 3 < A3) ? ww * J[4 * q + 3] : 0.f;
+            *reinterpret_cast<float4*>(rowp + (((6 + q) ^ (e.row & 7)) << 4)) = o;
+          }
         }
-        named_bar_sync(1 + e.slot, kRows);
+        if (valid && p.jac_out) {
+          const size_t si = static_cast<size_t>(rs.ray) * g.S + rs.s;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (16 * e.half + j < A3) p.jac_out[si * A3 + 16 * e.half + j] = J[j];
+        }
+        slot_bar(e);
         auto colsum = [&](int r0, int n, float& s0, float& s1) {
           for (int r = r0; r < r0 + n; ++r) {
             const uint8_t* rp = e.tz + r * 256;
@@ -518,18 +586,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           }
         };
         if (g.T == 1) {
-          for (int lr = wq; lr < g.G; lr += 4) {
+          for (int lr = w8; lr < g.G; lr += 8) {
             const int ray = group * g.G + lr;
             if (ray >= g.NR) break;
             float s0 = 0.f, s1 = 0.f;
             colsum(lr * g.S, g.S, s0, s1);
             emit(ray, s0, s1);
           }
-        } else if (wq == 0) {
+        } else if (w8 == 0) {
           colsum(0, min(kRows, g.S - tile * kRows), cs0, cs1);
           if (tile == g.T - 1 && group < g.NR) emit(group, cs0, cs1);
         }
-        named_bar_sync(1 + e.slot, kRows);
+        slot_bar(e);
       }
     }
   }

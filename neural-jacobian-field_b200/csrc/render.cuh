@@ -118,32 +118,25 @@ __device__ __forceinline__ float sin_cw(float t) {
 // NeRFEncoding(63) of the camera-space point into A-tile K-block 0 (columns 60..63 are zero: the
 // raw-xyz columns are applied in fp32 by the first epilogue).  Column order: sin block
 // (dim-major, freq-minor), cos block (= sin(t + pi/2)), like nerfstudio's torch implementation.
+// Each of the row's two threads writes its 32 columns.
 __device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)[3], bool valid,
                                              int debug = 0) {
-  float v[64];
   if (debug & 2) valid = false;
+  float v[32];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const float s0 = __fmul_rn(6.2831855f, cam[i]);
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-      const float t = s0 * static_cast<float>(1 << k);  // exact power-of-two scaling
-      v[i * 10 + k] = sin_cw(t);
-      v[30 + i * 10 + k] = sin_cw(__fadd_rn(t, 1.5707964f));
-    }
+  for (int j = 0; j < 32; ++j) {
+    const int c = 32 * e.half + j;           // 0..63
+    const int cc = c < 30 ? c : c - 30;      // index inside the sin / cos block
+    const int i = cc / 10, k = cc - 10 * i;
+    const float x = i == 0 ? cam[0] : (i == 1 ? cam[1] : cam[2]);
+    float t = __fmul_rn(6.2831855f, x) * static_cast<float>(1 << k);  // exact power-of-two scaling
+    if (c >= 30) t = __fadd_rn(t, 1.5707964f);
+    v[j] = (valid && c < 60) ? sin_cw(t) : 0.f;
   }
-  v[60] = v[61] = v[62] = v[63] = 0.f;
-  if (!valid) {
+  uint32_t pk[16];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = 0.f;
-  }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint32_t pk[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[32 * h + 2 * j], v[32 * h + 2 * j + 1]);
-    a_store32(e, 32 * h, pk);
-  }
+  for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
+  a_store32(e, 32 * e.half, pk);
 }
 
 // ----------------------------------------------------------------------------- gather
@@ -174,21 +167,23 @@ __device__ __forceinline__ void write_taps(TapEntry* tab, int row, const RowStat
   *reinterpret_cast<float4*>(tab[row].w) = w;
 }
 
-// Gather of NCH hoisted channels starting at channel ch0 for the 32 rows owned by this warp; each
-// tap is one contiguous NCH*2-byte read spread over the lanes (8 B / lane), interpolation in
-// packed fp32 (FFMA2).  Result (fp16) goes to the slot's staging buffer.
+// Gather of NCH hoisted channels starting at channel ch0 for the 16 rows owned by this warp
+// (rows 32q + 16h ..); each tap is one contiguous NCH*2-byte read spread over the lanes
+// (8 B / lane), interpolation in packed fp32 (FFMA2).  Result (fp16) goes to the slot's staging
+// buffer, which the row's two epilogue threads read: pair barriers fence both directions.
 template <int NCH>
 __device__ __forceinline__ void gather_segment(const EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0) {
   static_assert(NCH == 128 || NCH == 64, "segment width");
-  if (g.debug & 1) return;
+  pair_bar(e);  // the partner warp has finished reading the previous segment
+  if (g.debug & 1) { pair_bar(e); return; }
   const int lane = threadIdx.x & 31;
-  const int wrow0 = e.row & ~31;
+  const int wrow0 = e.q * 32 + e.half * 16;
   const bool active = (NCH == 128) || lane < 16;
   const uint2* mp = reinterpret_cast<const uint2*>(g.map + ch0) + lane;
   const size_t pstride = static_cast<size_t>(g.CH) / 4;  // uint2 per pixel
   constexpr int U = 4;
 #pragma unroll 1
-  for (int j0 = 0; j0 < 32; j0 += U) {
+  for (int j0 = 0; j0 < 16; j0 += U) {
     uint2 t[U][4];
     float4 w[U];
 #pragma unroll
@@ -223,7 +218,7 @@ __device__ __forceinline__ void gather_segment(const EpiCtx& e, const PassGeom& 
       }
     }
   }
-  __syncwarp();
+  pair_bar(e);
 }
 
 // ----------------------------------------------------------------------------- trunk epilogues
@@ -274,21 +269,21 @@ __device__ __forceinline__ void epi_x_first(const EpiCtx& e, int c0, const float
 __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom& g, const TrunkTab& tab, int seg_ch0,
                                                       const RowState& rs, const TapEntry* taps) {
   // E0: X_0 = lin_in + b_in + raw-xyz + tz_0
-  for (int c0 = 0; c0 < 128; c0 += 32) epi_x_first(e, c0, tab.e0, rs.cam);
+  for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_first(e, c0, tab.e0, rs.cam);
   epi_publish(e);  // -> fc_0 (block 0)
 #pragma unroll 1
   for (int k = 0; k < 5; ++k) {
     // overlap: gather the next hoisted segment while the tensor pipe runs fc_0
     if (k < 2) gather_segment<128>(e, g, taps, seg_ch0 + 128 * (k + 1));
     epi_wait_acc(e);
-    for (int c0 = 0; c0 < 128; c0 += 32) epi_relu_to_a(e, 128 + c0, c0, tab.bias + (2 * k) * 128);
+    for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_relu_to_a(e, 128 + c0, c0, tab.bias + (2 * k) * 128);
     epi_publish(e);  // -> fc_1 (block k), accumulates onto x
     epi_wait_acc(e);
     const float* bn = tab.bias + (2 * k + 1) * 128;
     if (k < 2) {
-      for (int c0 = 0; c0 < 128; c0 += 32) epi_x_update<true, false>(e, c0, bn, nullptr);
+      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<true, false>(e, c0, bn, nullptr);
     } else {
-      for (int c0 = 0; c0 < 128; c0 += 32) epi_x_update<false, false>(e, c0, bn, nullptr);
+      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<false, false>(e, c0, bn, nullptr);
     }
     epi_publish(e);  // -> fc_0 (block k+1) or lin_out
   }

@@ -45,38 +45,36 @@ __global__ void __launch_bounds__(kThreads, 1) selftest_kernel(const __grid_cons
       const int tile = 2 * it + e.slot;
       if (tile >= p.ntiles) continue;  // whole warpgroup idles; issuer skips this slot
       const size_t grow = static_cast<size_t>(tile) * kRows + e.row;
-      // A tile K-block 0 <- fp16(a_in row)
+      // A tile K-block 0 <- fp16(a_in row): each of the row's two threads writes 32 columns
       {
-        const float* src = p.a_in + grow * 64;
+        const float* src = p.a_in + grow * 64 + 32 * e.half;
+        uint32_t pk[16];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(src[32 * h + 2 * j], src[32 * h + 2 * j + 1]);
-          a_store32(e, 32 * h, pk);
-        }
+        for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(src[2 * j], src[2 * j + 1]);
+        a_store32(e, 32 * e.half, pk);
       }
       epi_publish(e);  // step 0: x = a * W0^T
-      // stage the "gathered" term the way the gather warps do: lane = 4 channels of one row
+      // stage the "gathered" term the way the gather warps do: lane = 4 channels of one row,
+      // warp (h, q) covers rows 32q + 16h .. + 16
       {
-        const int lane = threadIdx.x & 31, wrow0 = (e.row & ~31);
-        for (int r = 0; r < 32; ++r) {
+        const int lane = threadIdx.x & 31, wrow0 = e.q * 32 + 16 * e.half;
+        for (int r = 0; r < 16; ++r) {
           const float* src = p.tz_in + (static_cast<size_t>(tile) * kRows + wrow0 + r) * 128 + 4 * lane;
           uint2 v;
           v.x = pack_f16x2(src[0], src[1]);
           v.y = pack_f16x2(src[2], src[3]);
           *reinterpret_cast<uint2*>(e.tz + tz_offset(wrow0 + r, lane >> 1) + (lane & 1) * 8) = v;
         }
-        __syncwarp();
+        pair_bar(e);
       }
       epi_wait_acc(e);
-      for (int c0 = 0; c0 < 128; c0 += 32) epi_x_update<true, false>(e, c0, p.bias, nullptr);
+      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<true, false>(e, c0, p.bias, nullptr);
       epi_publish(e);  // step 1: net = relu(x) * W1^T
       epi_wait_acc(e);
-      for (int c0 = 0; c0 < 128; c0 += 32) epi_relu_to_a(e, 128 + c0, c0, p.bias + 128);
+      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_relu_to_a(e, 128 + c0, c0, p.bias + 128);
       epi_publish(e);  // step 2: x += relu(net) * W2^T
       epi_wait_acc(e);
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(e.tmem + c0, r);
         tmem_ld_wait();
@@ -84,10 +82,10 @@ __global__ void __launch_bounds__(kThreads, 1) selftest_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r[j]);
       }
-      for (int c0 = 0; c0 < 128; c0 += 32) epi_relu_to_a(e, c0, c0, p.bias + 256);
+      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_relu_to_a(e, c0, c0, p.bias + 256);
       epi_publish(e);  // step 3: y = relu(x) * W3^T (N=16)
       epi_wait_acc(e);
-      {
+      if (e.half == 0) {
         uint32_t r[16];
         tmem_ld16(e.tmem + 128, r);
         tmem_ld_wait();
@@ -95,6 +93,7 @@ __global__ void __launch_bounds__(kThreads, 1) selftest_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 16; ++j) dst[j] = __uint_as_float(r[j]);
       }
+      pair_bar(e);  // staging rows are rewritten by the partner warp in the next item
     }
   }
   cta_teardown(c);
