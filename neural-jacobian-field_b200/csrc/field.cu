@@ -21,7 +21,6 @@ namespace {
 struct Builder {
   std::map<std::string, std::pair<const float*, int64_t>> t;
   std::vector<uint8_t> blob;
-  std::vector<float> tab;
   std::vector<float> hoist_w, hoist_b;  // rows of [512]
   std::string err;
 
@@ -54,31 +53,16 @@ struct Builder {
     if (w) pack_sw128_f16(w, n_real, k_real, ld, n_pad, k_pad, blob.data() + st.w_off);
     p.steps[p.nsteps++] = st;
   }
-  size_t tab_alloc(size_t n) {
-    // 16-byte aligned sub-allocations (float4 tables)
-    while (tab.size() % 4) tab.push_back(0.f);
-    const size_t off = tab.size();
-    tab.resize(off + n, 0.f);
-    return off;
-  }
 };
-
-struct TrunkOff { size_t e0, bias, b_out; };
 
 // lin_in step + hoisted lin_z rows; the block steps are appended separately (program order differs
 // between heads).
-void trunk_lin_in(Builder& b, Program& prog, const std::string& p, TrunkOff& off, int flags = 0) {
+void trunk_lin_in(Builder& b, Program& prog, const std::string& p, TrunkTab& tab, int flags = 0) {
   const float* w = b.get(p + ".lin_in.weight", 128 * 63);
   const float* bi = b.get(p + ".lin_in.bias", 128);
   b.step(prog, w, 128, 60, 63, 128, 64, /*d_col=*/0, /*acc=*/0, flags);
-  off.e0 = b.tab_alloc(128 * 4);
   if (w && bi)
-    for (int c = 0; c < 128; ++c) {
-      b.tab[off.e0 + 4 * c + 0] = w[c * 63 + 60];
-      b.tab[off.e0 + 4 * c + 1] = w[c * 63 + 61];
-      b.tab[off.e0 + 4 * c + 2] = w[c * 63 + 62];
-      b.tab[off.e0 + 4 * c + 3] = bi[c];
-    }
+    for (int c = 0; c < 128; ++c) tab.e0[c] = make_float4(w[c * 63 + 60], w[c * 63 + 61], w[c * 63 + 62], bi[c]);
   for (int k = 0; k < 3; ++k) {
     const float* wz = b.get(p + ".lin_z." + std::to_string(k) + ".weight", 128 * 512);
     const float* bz = b.get(p + ".lin_z." + std::to_string(k) + ".bias", 128);
@@ -88,9 +72,7 @@ void trunk_lin_in(Builder& b, Program& prog, const std::string& p, TrunkOff& off
     }
   }
 }
-void trunk_blocks(Builder& b, Program& prog, const std::string& p, int d_out, int n_out_pad, TrunkOff& off) {
-  off.bias = b.tab_alloc(10 * 128);
-  off.b_out = b.tab_alloc(32);
+void trunk_blocks(Builder& b, Program& prog, const std::string& p, int d_out, int n_out_pad, TrunkTab& tab) {
   const float* b1[5] = {};
   for (int k = 0; k < 5; ++k) {
     const std::string q = p + ".blocks." + std::to_string(k);
@@ -100,10 +82,10 @@ void trunk_blocks(Builder& b, Program& prog, const std::string& p, int d_out, in
     b1[k] = b.get(q + ".fc_1.bias", 128);
     b.step(prog, w0, 128, 128, 128, 128, 128, /*d_col=*/128, 0);
     b.step(prog, w1, 128, 128, 128, 128, 128, /*d_col=*/0, 1);
-    if (b0) std::memcpy(&b.tab[off.bias + (2 * k) * 128], b0, 128 * sizeof(float));
+    if (b0) std::memcpy(&tab.bias[(2 * k) * 128], b0, 128 * sizeof(float));
   }
   if (b1[0] && b1[1] && b1[2] && b1[3] && b1[4]) {
-    float* T = &b.tab[off.bias];
+    float* T = tab.bias;
     for (int c = 0; c < 128; ++c) {
       T[1 * 128 + c] = b1[0][c];                         // added (with tz_1) before block 1
       T[3 * 128 + c] = b1[1][c];                         // added (with tz_2) before block 2
@@ -115,7 +97,7 @@ void trunk_blocks(Builder& b, Program& prog, const std::string& p, int d_out, in
   const float* wo = b.get(p + ".lin_out.weight", static_cast<int64_t>(d_out) * 128);
   const float* bo = b.get(p + ".lin_out.bias", d_out);
   b.step(prog, wo, d_out, 128, 128, n_out_pad, 128, /*d_col=*/128, 0);
-  if (bo) std::memcpy(&b.tab[off.b_out], bo, d_out * sizeof(float));
+  if (bo) std::memcpy(tab.b_out, bo, d_out * sizeof(float));
 }
 
 }  // namespace
@@ -136,20 +118,18 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
   Builder b;
   for (int i = 0; i < n_tensors; ++i) b.t[tensors[i].name] = {tensors[i].data, tensors[i].numel};
 
-  auto* f = new NjfField();
+  auto* f = new NjfField();   // value-initialised: all tables start at zero
   f->desc = *desc;
-  TrunkOff prop_off[NJF_MAX_LEVELS], dens_off{}, jac_off{};
   // hoist channel order: proposal nets (384 each), then the main map (dens 384 + head part)
   for (int i = 0; i < desc->n_proposal; ++i) {
     const std::string p = "proposal_networks." + std::to_string(i) + ".density_head";
-    trunk_lin_in(b, f->prop_prog[i], p, prop_off[i]);
-    trunk_blocks(b, f->prop_prog[i], p, 1, 16, prop_off[i]);
+    trunk_lin_in(b, f->prop_prog[i], p, f->prop_trunk[i]);
+    trunk_blocks(b, f->prop_prog[i], p, 1, 16, f->prop_trunk[i]);
   }
-  size_t q_e0 = 0, xf_off[3] = {}, bh_off = 0, col_off = 0;
   Program& fp = f->field_prog;
   // transformer head: lin_in and q_enc read the same A tile (the positional encoding) and are
   // covered by ONE accumulator commit (two arrivals on one mbarrier phase would be unsafe)
-  trunk_lin_in(b, fp, "decoder.density_head", dens_off,
+  trunk_lin_in(b, fp, "decoder.density_head", f->dens_trunk,
                desc->head == NJF_HEAD_TRANSFORMER ? kStepNoCommit : 0);
   if (desc->head == NJF_HEAD_TRANSFORMER) {
     f->ch_main = 448;
@@ -157,14 +137,9 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
     const float* bq = b.get("decoder.jacobian_query_mlp.bias", 64);
     const float* emb = b.get("decoder.jacobian_index_embedding", static_cast<int64_t>(A) * 64);
     b.step(fp, wq, 64, 60, 575, 64, 64, /*d_col=*/128, 0, kStepReuseA);
-    q_e0 = b.tab_alloc(64 * 4);
     if (wq && bq) {
-      for (int c = 0; c < 64; ++c) {
-        b.tab[q_e0 + 4 * c + 0] = wq[c * 575 + 60];
-        b.tab[q_e0 + 4 * c + 1] = wq[c * 575 + 61];
-        b.tab[q_e0 + 4 * c + 2] = wq[c * 575 + 62];
-        b.tab[q_e0 + 4 * c + 3] = bq[c];
-      }
+      for (int c = 0; c < 64; ++c)
+        f->head.q_e0[c] = make_float4(wq[c * 575 + 60], wq[c * 575 + 61], wq[c * 575 + 62], bq[c]);
       // hoisted query channels: the 512 feature columns of jacobian_query_mlp (bias lives in q_e0)
       for (int c = 0; c < 64; ++c) b.hoist_w.insert(b.hoist_w.end(), wq + c * 575 + 63, wq + c * 575 + 575);
       b.hoist_b.insert(b.hoist_b.end(), 64, 0.f);
@@ -218,18 +193,18 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
       b.step(fp, m2.data(), 64, 64, 64, 64, 64, 128, 0);
       b.step(fp, w1, 64, 64, 64, 64, 64, 128, 0);
       b.step(fp, w2, 64, 64, 64, 64, 64, 128, 0);
-      xf_off[l] = b.tab_alloc(7 * 64);
       const float* src[7] = {g1, be1, bo, g2, be2, bb1, bb2};
+      XfLayerTab& T = f->head.layer[l];
+      float* dst[7] = {T.ln1_g, T.ln1_b, T.b_o, T.ln2_g, T.ln2_b, T.b_1, T.b_2};
       for (int i = 0; i < 7; ++i)
-        if (src[i]) std::memcpy(&b.tab[xf_off[l] + i * 64], src[i], 64 * sizeof(float));
+        if (src[i]) std::memcpy(dst[i], src[i], 64 * sizeof(float));
     }
     const float* wh = b.get("decoder.jacobian_head.weight", static_cast<int64_t>(3 * A) * 64);
     const float* bh = b.get("decoder.jacobian_head.bias", 3 * A);
     b.step(fp, wh, 3 * A, 64, 64, 32, 64, 128, 0);
-    bh_off = b.tab_alloc(32);
-    if (bh) std::memcpy(&b.tab[bh_off], bh, 3 * A * sizeof(float));
+    if (bh) std::memcpy(f->head.b_head, bh, 3 * A * sizeof(float));
   }
-  trunk_blocks(b, fp, "decoder.density_head", 16, 16, dens_off);
+  trunk_blocks(b, fp, "decoder.density_head", 16, 16, f->dens_trunk);
   {
     const float* w1 = b.get("decoder.color_head.0.weight", 64 * 31);
     const float* b1 = b.get("decoder.color_head.0.bias", 64);
@@ -239,18 +214,17 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
     const float* b3 = b.get("decoder.color_head.4.bias", 3);
     b.step(fp, w1, 64, 31, 31, 64, 64, 128, 0);
     b.step(fp, w2, 64, 64, 64, 64, 64, 128, 0);
-    col_off = b.tab_alloc(64 + 64 + 192 + 4);
     if (b1 && b2 && w3 && b3) {
-      std::memcpy(&b.tab[col_off], b1, 64 * 4);
-      std::memcpy(&b.tab[col_off + 64], b2, 64 * 4);
-      std::memcpy(&b.tab[col_off + 128], w3, 192 * 4);
-      std::memcpy(&b.tab[col_off + 320], b3, 3 * 4);
+      std::memcpy(f->color.b1, b1, 64 * 4);
+      std::memcpy(f->color.b2, b2, 64 * 4);
+      std::memcpy(f->color.w3, w3, 192 * 4);
+      std::memcpy(f->color.b3, b3, 3 * 4);
     }
   }
   if (desc->head == NJF_HEAD_MLP) {
     f->ch_main = 768;
-    trunk_lin_in(b, fp, "decoder.jacobian_head", jac_off);
-    trunk_blocks(b, fp, "decoder.jacobian_head", 3 * A, 32, jac_off);
+    trunk_lin_in(b, fp, "decoder.jacobian_head", f->jac_trunk);
+    trunk_blocks(b, fp, "decoder.jacobian_head", 3 * A, 32, f->jac_trunk);
   }
   if (!b.err.empty()) {
     delete f;
@@ -262,36 +236,13 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
     NJF_FAIL("internal: hoist rows %zu != %d", b.hoist_b.size(), f->ch_total);
   }
   NJF_CUDA(cudaMalloc(&f->d_blob, b.blob.size()));
-  NJF_CUDA(cudaMalloc(&f->d_tab, b.tab.size() * sizeof(float)));
   NJF_CUDA(cudaMalloc(&f->d_hoist_w, b.hoist_w.size() * sizeof(float)));
   NJF_CUDA(cudaMalloc(&f->d_hoist_b, b.hoist_b.size() * sizeof(float)));
   NJF_CUDA(cudaMemcpy(f->d_blob, b.blob.data(), b.blob.size(), cudaMemcpyHostToDevice));
-  NJF_CUDA(cudaMemcpy(f->d_tab, b.tab.data(), b.tab.size() * sizeof(float), cudaMemcpyHostToDevice));
   NJF_CUDA(cudaMemcpy(f->d_hoist_w, b.hoist_w.data(), b.hoist_w.size() * sizeof(float), cudaMemcpyHostToDevice));
   NJF_CUDA(cudaMemcpy(f->d_hoist_b, b.hoist_b.data(), b.hoist_b.size() * sizeof(float), cudaMemcpyHostToDevice));
-  auto trunk_tab = [&](const TrunkOff& o) {
-    TrunkTab t;
-    t.e0 = reinterpret_cast<const float4*>(f->d_tab + o.e0);
-    t.bias = f->d_tab + o.bias;
-    t.b_out = f->d_tab + o.b_out;
-    return t;
-  };
-  for (int i = 0; i < desc->n_proposal; ++i) {
-    f->prop_trunk[i] = trunk_tab(prop_off[i]);
-    f->prop_blob[i] = f->d_blob;
-  }
+  for (int i = 0; i < desc->n_proposal; ++i) f->prop_blob[i] = f->d_blob;
   f->field_blob = f->d_blob;
-  f->dens_trunk = trunk_tab(dens_off);
-  if (desc->head == NJF_HEAD_MLP) f->jac_trunk = trunk_tab(jac_off);
-  if (desc->head == NJF_HEAD_TRANSFORMER) {
-    f->head.q_e0 = reinterpret_cast<const float4*>(f->d_tab + q_e0);
-    for (int l = 0; l < 3; ++l) {
-      const float* base = f->d_tab + xf_off[l];
-      f->head.layer[l] = XfLayerTab{base, base + 64, base + 128, base + 192, base + 256, base + 320, base + 384};
-    }
-    f->head.b_head = f->d_tab + bh_off;
-  }
-  f->color = ColorTab{f->d_tab + col_off, f->d_tab + col_off + 64, f->d_tab + col_off + 128, f->d_tab + col_off + 320};
   *out = f;
   return 0;
 }
@@ -299,7 +250,6 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
 extern "C" void njf_field_destroy(NjfField* f) {
   if (!f) return;
   cudaFree(f->d_blob);
-  cudaFree(f->d_tab);
   cudaFree(f->d_hoist_w);
   cudaFree(f->d_hoist_b);
   delete f;

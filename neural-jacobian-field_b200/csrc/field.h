@@ -5,27 +5,24 @@
 
 namespace njf {
 
-// fp32 side tables of one ResnetFC trunk (device pointers)
+// fp32 side tables.  They travel BY VALUE inside the kernel parameter structs (constant bank:
+// every epilogue access is warp-uniform, so it is a broadcast constant-cache read instead of an
+// L1-thrashed global load).
 struct TrunkTab {
-  const float4* e0;   // [128] (W_in[:,60], W_in[:,61], W_in[:,62], b_in): raw-xyz columns kept in fp32
-  const float* bias;  // [10][128]: b0_0, b1_0, b0_1, b1_1, b0_2, c3, b0_3, c4, b0_4, c5 (c* cumulative fc_1 biases)
-  const float* b_out; // [32] lin_out bias (zero padded)
+  float4 e0[128];       // (W_in[:,60], W_in[:,61], W_in[:,62], b_in): raw-xyz columns kept in fp32
+  float bias[10 * 128]; // b0_0, b1_0, b0_1, b1_1, b0_2, c3, b0_3, c4, b0_4, c5 (c* cumulative fc_1 biases)
+  float b_out[32];      // lin_out bias (zero padded)
 };
-
 struct XfLayerTab {
-  const float* ln1_g; const float* ln1_b; const float* b_o;
-  const float* ln2_g; const float* ln2_b; const float* b_1; const float* b_2;  // each [64]
+  float ln1_g[64], ln1_b[64], b_o[64], ln2_g[64], ln2_b[64], b_1[64], b_2[64];
 };
 struct HeadTab {
-  const float4* q_e0;   // [64] (Wq[:,60..62], bq)
+  float4 q_e0[64];      // (Wq[:,60..62], bq)
   XfLayerTab layer[3];
-  const float* b_head;  // [32]
+  float b_head[32];
 };
 struct ColorTab {
-  const float* b1;  // [64]
-  const float* b2;  // [64]
-  const float* w3;  // [3][64]
-  const float* b3;  // [4]
+  float b1[64], b2[64], w3[3 * 64], b3[4];
 };
 
 }  // namespace njf
@@ -33,7 +30,6 @@ struct ColorTab {
 struct NjfField {
   NjfFieldDesc desc;
   uint8_t* d_blob = nullptr;   // all layer images
-  float* d_tab = nullptr;      // all fp32 tables
   float* d_hoist_w = nullptr;  // [ch_total][512] rows of the hoisted linear maps
   float* d_hoist_b = nullptr;  // [ch_total]
   int ch_prop = 384;           // channels of each proposal map

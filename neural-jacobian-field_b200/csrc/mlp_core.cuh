@@ -75,8 +75,9 @@ struct CtaCtx {
 // all 320 threads
 __device__ __forceinline__ CtaCtx cta_setup(uint8_t* smem_raw) {
   CtaCtx c;
-  c.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                      ~static_cast<uintptr_t>(1023));
+  // align inside the shared window with pointer arithmetic only (keeps the shared address space
+  // visible to the compiler: LDS/STS instead of generic LD/ST)
+  c.smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   c.bars = reinterpret_cast<Barriers*>(c.smem + SmemMap::kMisc);
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
@@ -111,7 +112,7 @@ __device__ __forceinline__ void loader_role(const CtaCtx& c, const Program& prog
   for (int run = 0; run < nrun; ++run) {
     for (int s = 0; s < prog.nsteps; ++s, ++cnt) {
       const uint32_t stage = cnt % kStages, par = (cnt / kStages) & 1u;
-      mbar_wait(&c.bars->w_empty[stage], par ^ 1u);
+      mbar_wait_backoff(&c.bars->w_empty[stage], par ^ 1u);
       const uint32_t bytes = prog.steps[s].w_bytes;
       mbar_arrive_expect_tx(&c.bars->w_full[stage], bytes);
       bulk_g2s(c.smem + SmemMap::kW + stage * kStageBytes, blob + prog.steps[s].w_off, bytes,
@@ -162,8 +163,28 @@ __device__ __forceinline__ void issuer_role(const CtaCtx& c, const Program& prog
   }
 }
 
+// ----------------------------------------------------------------------------- optional phase profiler
+// -DNJF_PROFILE: lane 0 of every epilogue warp attributes SM-clock cycles to phases; summed per
+// phase into g_prof (read with njf_prof_read).  Zero cost in the normal build.
+enum ProfPhase { kPSetup = 0, kPGather, kPWaitAcc, kPEpi, kPWeights, kPPdf, kPHead, kPColor, kPComposite, kPBar, kPOther, kPCount };
+#ifdef NJF_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF(e, ph)                                   \
+  do {                                                \
+    const long long now_ = clock64();                 \
+    (e).prof[ph] += static_cast<unsigned>(now_ - (e).pt); \
+    (e).pt = now_;                                    \
+  } while (0)
+#else
+#define PROF(e, ph) do { } while (0)
+#endif
+
 // ----------------------------------------------------------------------------- epilogue-side helpers
 struct EpiCtx {
+#ifdef NJF_PROFILE
+  long long pt;
+  unsigned prof[kPCount];
+#endif
   uint8_t* a_tile;    // this slot's A tile (generic pointer)
   uint8_t* tz;        // this slot's 32 KB staging buffer
   uint64_t* a_ready;
@@ -194,7 +215,19 @@ __device__ __forceinline__ EpiCtx epi_ctx(const CtaCtx& c) {
   e.acc_ready = &c.bars->acc_ready[e.slot];
   e.tmem = c.tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + e.slot * kSlotCols;
   e.acc_par = 0;
+#ifdef NJF_PROFILE
+  e.pt = clock64();
+  for (int i = 0; i < kPCount; ++i) e.prof[i] = 0;
+#endif
   return e;
+}
+__device__ __forceinline__ void prof_flush(EpiCtx& e) {
+#ifdef NJF_PROFILE
+  if ((threadIdx.x & 31) == 0)
+    for (int i = 0; i < kPCount; ++i) atomicAdd(&g_prof[i], static_cast<unsigned long long>(e.prof[i]));
+#else
+  (void)e;
+#endif
 }
 // A tile fully written (generic proxy) and all of this thread's TMEM accesses retired
 __device__ __forceinline__ void epi_publish(EpiCtx& e) {
@@ -203,9 +236,11 @@ __device__ __forceinline__ void epi_publish(EpiCtx& e) {
   mbar_arrive(e.a_ready);
 }
 __device__ __forceinline__ void epi_wait_acc(EpiCtx& e) {
-  mbar_wait(e.acc_ready, e.acc_par);
+  PROF(e, kPOther);
+  mbar_wait_backoff(e.acc_ready, e.acc_par);
   e.acc_par ^= 1u;
   tc_fence_after();
+  PROF(e, kPWaitAcc);
 }
 // 32 packed fp16x2 words (64 columns? no: 16 words = 32 columns) -> A tile columns [c0, c0+32)
 __device__ __forceinline__ void a_store32(const EpiCtx& e, int c0, const uint32_t (&p)[16]) {
@@ -239,14 +274,10 @@ __device__ __forceinline__ void epi_relu_to_a(const EpiCtx& e, int tcol, int c0,
   tmem_ld_wait();
   uint32_t p[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
-    const float2 s0 = fadd2(make_float2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])),
-                            make_float2(b.x, b.y));
-    const float2 s1 = fadd2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])),
-                            make_float2(b.z, b.w));
-    p[2 * j] = pack_relu_f16x2(fminf(s0.x, kF16Max), fminf(s0.y, kF16Max));
-    p[2 * j + 1] = pack_relu_f16x2(fminf(s1.x, kF16Max), fminf(s1.y, kF16Max));
+  for (int j = 0; j < 16; ++j) {
+    const float2 s0 = fadd2(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])),
+                            make_float2(bias[c0 + 2 * j], bias[c0 + 2 * j + 1]));
+    p[j] = pack_relu_f16x2(s0.x, s0.y);
   }
   a_store32(e, c0, p);
 }
@@ -263,13 +294,11 @@ __device__ __forceinline__ void epi_x_update(const EpiCtx& e, int c0,
   tmem_ld_wait();
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
-    const float2 s0 = fadd2(make_float2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])),
-                            make_float2(b.x, b.y));
-    const float2 s1 = fadd2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])),
-                            make_float2(b.z, b.w));
-    v[4 * j + 0] = s0.x; v[4 * j + 1] = s0.y; v[4 * j + 2] = s1.x; v[4 * j + 3] = s1.y;
+  for (int j = 0; j < 16; ++j) {
+    const float2 s0 = fadd2(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])),
+                            make_float2(bias[c0 + 2 * j], bias[c0 + 2 * j + 1]));
+    v[2 * j] = s0.x;
+    v[2 * j + 1] = s0.y;
   }
   if (kHasTz) {
 #pragma unroll
@@ -296,7 +325,7 @@ __device__ __forceinline__ void epi_x_update(const EpiCtx& e, int c0,
   uint32_t p[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j)
-    p[j] = pack_relu_f16x2(fminf(v[2 * j], kF16Max), fminf(v[2 * j + 1], kF16Max));
+    p[j] = pack_relu_f16x2(v[2 * j], v[2 * j + 1]);
   a_store32(e, c0, p);
   if (kHasTz || kHasExtra) tmem_st_wait();
 }

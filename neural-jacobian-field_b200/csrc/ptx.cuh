@@ -44,6 +44,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for the many epilogue threads: back off between polls so that waiting warps do not eat the
+// issue slots of the warps that still have work
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
 
 // ----------------------------------------------------------------------------- bulk copy (TMA engine)
 // global -> shared, completion signalled as transaction bytes on an mbarrier.
@@ -167,15 +172,15 @@ __device__ __forceinline__ void tmem_st_wait() {
 }
 
 // ----------------------------------------------------------------------------- misc
-// pack two fp32 -> fp16x2 with ReLU (negative and NaN -> +0) in ONE cvt; lo in low half
+// pack two fp32 -> fp16x2 with ReLU and saturation to the finite fp16 range in ONE F2FP; lo in low half
 __device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 constexpr float kF16Max = 65504.0f;

@@ -36,9 +36,10 @@ __device__ __forceinline__ uint32_t* cta_minmax(const CtaCtx& c) {
 // transmittance weights of this tile's rows (RaySamples.get_weights, ray_samplers.py:77-101):
 // the h=0 thread of each row stores dd, one warp per ray scans (double accumulation), every
 // thread of the row gets the row's weight back.
-__device__ __forceinline__ float tile_weights(const EpiCtx& e, SlotScratch* sc, const PassGeom& g, int tile,
+__device__ __forceinline__ float tile_weights(EpiCtx& e, SlotScratch* sc, const PassGeom& g, int tile,
                                               float dd, double& carry) {
   const int w8 = (threadIdx.x >> 5) & 7;
+  PROF(e, kPOther);
   if (e.half == 0) sc->dd[e.row] = dd;
   slot_bar(e);
   if (g.T == 1) {
@@ -57,6 +58,7 @@ __device__ __forceinline__ float tile_weights(const EpiCtx& e, SlotScratch* sc, 
     sc->wrow[e.row] = alpha * tr;
   }
   slot_bar(e);
+  PROF(e, kPWeights);
   return sc->wrow[e.row];
 }
 
@@ -107,11 +109,13 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
       double carry = 0.0;
       for (int tile = 0; tile < g.T; ++tile) {
         RowState rs;
+        PROF(e, kPOther);
         row_setup(g, group, tile, e.row, rs);
-        if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf);
+        if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
         write_posenc(e, rs.cam, rs.ray >= 0, g.debug);
         epi_publish(e);  // -> lin_in
         __syncwarp();
+        PROF(e, kPSetup);
         gather_segment<128>(e, g, sc->taps, 0);
         epi_wait_acc(e);
         trunk_blocks_epilogue(e, g, p.trunk, 0, rs, sc->taps);
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
           tmem_ld16(e.tmem + 128, r);
           tmem_ld_wait();
           // density = trunc_exp(x - 1) (density_decoder.py:64-66, activations.py:32-35)
-          const float sigma = expf(__fsub_rn(__uint_as_float(r[0]) + __ldg(p.trunk.b_out), 1.f));
+          const float sigma = expf(__fsub_rn(__uint_as_float(r[0]) + p.trunk.b_out[0], 1.f));
           dd = (rs.ray >= 0 && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
         }
         const float w = tile_weights(e, sc, g, tile, dd, carry);
@@ -131,6 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
         }
       }
       slot_bar(e);
+      PROF(e, kPBar);
       for (int lr = w8; lr < g.G; lr += 8) {
         const int ray = group * g.G + lr;
         if (ray >= g.NR) break;
@@ -139,8 +144,11 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
                           sc->cdf + lr * (g.S + 1), p.bins_out + static_cast<size_t>(ray) * nb,
                           p.inds_out ? p.inds_out + static_cast<size_t>(ray) * nb : nullptr);
       }
+      PROF(e, kPPdf);
       slot_bar(e);
+      PROF(e, kPBar);
     }
+    prof_flush(e);
   }
   cta_teardown(c);
 }
@@ -177,19 +185,18 @@ __device__ __forceinline__ void store32_to_a(const EpiCtx& e, const float (&v)[3
   a_store32(e, 32 * e.half, pk);
 }
 // v[j] += tab[32h + j] (fp32 vector loads)
-__device__ __forceinline__ void add_vec32(const EpiCtx& e, float (&v)[32], const float* __restrict__ tab) {
-  const float4* t4 = reinterpret_cast<const float4*>(tab + 32 * e.half);
+__device__ __forceinline__ void add_vec32(const EpiCtx& e, float (&v)[32], const float* tab) {
+  const float* t = tab + 32 * e.half;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 b = __ldg(t4 + j);
-    const float2 s0 = fadd2(make_float2(v[4 * j], v[4 * j + 1]), make_float2(b.x, b.y));
-    const float2 s1 = fadd2(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(b.z, b.w));
-    v[4 * j] = s0.x; v[4 * j + 1] = s0.y; v[4 * j + 2] = s1.x; v[4 * j + 3] = s1.y;
+  for (int j = 0; j < 16; ++j) {
+    const float2 s0 = fadd2(make_float2(v[2 * j], v[2 * j + 1]), make_float2(t[2 * j], t[2 * j + 1]));
+    v[2 * j] = s0.x;
+    v[2 * j + 1] = s0.y;
   }
 }
 // LayerNorm over the row's 64 values (32 here, 32 in the partner thread) -> fp16 -> A tile
 __device__ __forceinline__ void ln64_to_a(const EpiCtx& e, SlotScratch* sc, const float (&x)[32],
-                                          const float* __restrict__ gam, const float* __restrict__ bet) {
+                                          const float* gam, const float* bet) {
   float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < 32; j += 2) acc = fadd2(acc, make_float2(x[j], x[j + 1]));
@@ -207,18 +214,16 @@ __device__ __forceinline__ void ln64_to_a(const EpiCtx& e, SlotScratch* sc, cons
   pair_bar(e);
   const float var = (sc->xch[e.row][0].y + sc->xch[e.row][1].y) * (1.f / 64.f);
   const float rstd = rsqrtf(var + 1e-5f);
-  const float4* g4 = reinterpret_cast<const float4*>(gam + 32 * e.half);
-  const float4* b4 = reinterpret_cast<const float4*>(bet + 32 * e.half);
+  const float* gg = gam + 32 * e.half;
+  const float* bb = bet + 32 * e.half;
+  const float2 rs2 = make_float2(rstd, rstd);
   uint32_t pk[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 gg = __ldg(g4 + j), bb = __ldg(b4 + j);
-    const float y0 = fmaf((x[4 * j + 0] - mean) * rstd, gg.x, bb.x);
-    const float y1 = fmaf((x[4 * j + 1] - mean) * rstd, gg.y, bb.y);
-    const float y2 = fmaf((x[4 * j + 2] - mean) * rstd, gg.z, bb.z);
-    const float y3 = fmaf((x[4 * j + 3] - mean) * rstd, gg.w, bb.w);
-    pk[2 * j] = pack_f16x2(y0, y1);
-    pk[2 * j + 1] = pack_f16x2(y2, y3);
+  for (int j = 0; j < 16; ++j) {
+    float2 d = fadd2(make_float2(x[2 * j], x[2 * j + 1]), nm);
+    d = ffma2(d, rs2, make_float2(0.f, 0.f));
+    d = ffma2(d, make_float2(gg[2 * j], gg[2 * j + 1]), make_float2(bb[2 * j], bb[2 * j + 1]));
+    pk[j] = pack_f16x2(d.x, d.y);
   }
   a_store32(e, 32 * e.half, pk);
 }
@@ -276,7 +281,7 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const float4 q = __ldg(H.q_e0 + 32 * e.half + j);
+    const float4 q = H.q_e0[32 * e.half + j];
     x[j] += fmaf(q.z, rs.cam[2], fmaf(q.y, rs.cam[1], fmaf(q.x, rs.cam[0], q.w)));
   }
 #pragma unroll 1
@@ -336,15 +341,8 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
   uint32_t r[16];
   tmem_ld16(e.tmem + 128 + 16 * e.half, r);
   tmem_ld_wait();
-  const float4* b4 = reinterpret_cast<const float4*>(H.b_head + 16 * e.half);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float4 b = __ldg(b4 + j);
-    J[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-    J[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-    J[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-    J[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
-  }
+  for (int j = 0; j < 16; ++j) J[j] = __uint_as_float(r[j]) + H.b_head[16 * e.half + j];
 }
 
 // SH degree 4 (tiny-cuda-nn convention) of the unit direction (action_decoder_jacobian.py:194-199)
@@ -412,22 +410,26 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
       float cs0 = 0.f, cs1 = 0.f;  // column sums held by warp 0 of the slot across the tiles of a long ray
       for (int tile = 0; tile < g.T; ++tile) {
         RowState rs;
+        PROF(e, kPOther);
         row_setup(g, group, tile, e.row, rs);
         const bool valid = rs.ray >= 0;
         float J[16];  // this thread's 16 of the 32 (padded) Jacobian columns: 16h .. 16h+15
-        if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf);
+        if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
         write_posenc(e, rs.cam, valid, g.debug);
         epi_publish(e);  // -> lin_in (+ q_enc for the transformer head)
         __syncwarp();
+        PROF(e, kPSetup);
         if (p.head_kind == NJF_HEAD_TRANSFORMER) {
           gather_segment<64>(e, g, sc->taps, 384);
           epi_wait_acc(e);
           transformer_head(e, sc, p.head, A, rs, J);
+          PROF(e, kPHead);
         }
         gather_segment<128>(e, g, sc->taps, 0);
         if (p.head_kind != NJF_HEAD_TRANSFORMER) epi_wait_acc(e);
         trunk_blocks_epilogue(e, g, p.dens, 0, rs, sc->taps);
         // lin_out: 15 geometry features + density pre-activation (action_decoder_jacobian.py:106-112)
+        PROF(e, kPOther);
         float sigma = 0.f;
         if (e.half == 0) {
           float geo[16];
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           tmem_ld16(e.tmem + 128, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) geo[j] = __uint_as_float(r[j]) + __ldg(p.dens.b_out + j);
+          for (int j = 0; j < 16; ++j) geo[j] = __uint_as_float(r[j]) + p.dens.b_out[j];
           sigma = expf(__fsub_rn(geo[15], 1.f));
           // colour head input [geo15 | sh16 | 0...] (action_decoder_jacobian.py:208)
           float sh[16];
@@ -465,27 +467,22 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           float part[3];
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
-            const float4* w4 = reinterpret_cast<const float4*>(p.color.w3 + ch * 64 + 32 * e.half);
+            const float* w3 = p.color.w3 + ch * 64 + 32 * e.half;
             float a = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 ww = __ldg(w4 + j);
-              a = fmaf(ww.x, fmaxf(h2[4 * j + 0], 0.f), a);
-              a = fmaf(ww.y, fmaxf(h2[4 * j + 1], 0.f), a);
-              a = fmaf(ww.z, fmaxf(h2[4 * j + 2], 0.f), a);
-              a = fmaf(ww.w, fmaxf(h2[4 * j + 3], 0.f), a);
-            }
+            for (int j = 0; j < 32; ++j) a = fmaf(w3[j], fmaxf(h2[j], 0.f), a);
             part[ch] = a;
           }
           if (e.half == 1) sc->rgbp[e.row] = make_float4(part[0], part[1], part[2], 0.f);
           pair_bar(e);
           if (e.half == 0) {
             const float4 o = sc->rgbp[e.row];
-            rgb[0] = 1.f / (1.f + expf(-(part[0] + o.x + __ldg(p.color.b3 + 0))));
-            rgb[1] = 1.f / (1.f + expf(-(part[1] + o.y + __ldg(p.color.b3 + 1))));
-            rgb[2] = 1.f / (1.f + expf(-(part[2] + o.z + __ldg(p.color.b3 + 2))));
+            rgb[0] = 1.f / (1.f + expf(-(part[0] + o.x + p.color.b3[0])));
+            rgb[1] = 1.f / (1.f + expf(-(part[1] + o.y + p.color.b3[1])));
+            rgb[2] = 1.f / (1.f + expf(-(part[2] + o.z + p.color.b3[2])));
           }
         }
+        PROF(e, kPColor);
         if (p.head_kind == NJF_HEAD_MLP) {
           // second ResnetFC on the same gathered point (action_decoder_jacobian.py:324-337)
           write_posenc(e, rs.cam, valid, g.debug);
@@ -497,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           tmem_ld16(e.tmem + 128 + 16 * e.half, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) J[j] = __uint_as_float(r[j]) + __ldg(p.jac.b_out + 16 * e.half + j);
+          for (int j = 0; j < 16; ++j) J[j] = __uint_as_float(r[j]) + p.jac.b_out[16 * e.half + j];
         }
         // ---- weights + compositing (model.py:351-367, 384-394)
         const float dd = (valid && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
@@ -598,8 +595,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           if (tile == g.T - 1 && group < g.NR) emit(group, cs0, cs1);
         }
         slot_bar(e);
+        PROF(e, kPComposite);
       }
     }
+    prof_flush(e);
   }
   tc_fence_before();
   __syncthreads();
@@ -829,7 +828,8 @@ int check_args(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a
   if (a->B < 1 || a->R < 1) NJF_FAIL("B=%d R=%d: nothing to render", a->B, a->R);
   if (a->n_levels != f->desc.n_proposal) NJF_FAIL("n_levels %d != field n_proposal %d", a->n_levels, f->desc.n_proposal);
   if (!a->origins || !a->dirs || !a->z_near || !a->z_far || !a->maps) NJF_FAIL("missing ray / map input");
-  if (static_cast<size_t>(a->B) * a->Hf * a->Wf >= (1u << 30)) NJF_FAIL("feature map too large");
+  if (static_cast<size_t>(a->B) * a->Hf * a->Wf * 768 * 2 >= (1ull << 32))
+    NJF_FAIL("hoisted maps of %d views of %dx%d exceed the 4 GiB tap-offset range; render the views in groups", a->B, a->Hf, a->Wf);
   return 0;
 }
 
@@ -844,6 +844,18 @@ int set_smem(K kernel) {
 }
 
 }  // namespace
+
+#ifdef NJF_PROFILE
+extern "C" int njf_prof_read(unsigned long long* out16, int reset) {
+  NJF_CUDA(cudaDeviceSynchronize());
+  NJF_CUDA(cudaMemcpyFromSymbol(out16, g_prof, 16 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[16] = {};
+    NJF_CUDA(cudaMemcpyToSymbol(g_prof, z, sizeof(z)));
+  }
+  return 0;
+}
+#endif
 
 extern "C" size_t njf_hoisted_bytes(const NjfField* f, int B, int Hf, int Wf) {
   return static_cast<size_t>(B) * Hf * Wf * f->ch_total * sizeof(__half);

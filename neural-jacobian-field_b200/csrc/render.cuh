@@ -143,11 +143,11 @@ __device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)
 // Per-row bilinear taps (F.grid_sample align_corners=True, padding_mode="border"): computed ONCE per
 // row by the row's own thread, then broadcast-read by the gathering warp for every channel segment.
 struct TapEntry {
-  int pix[4];   // global pixel index (view*Hf*Wf + y*Wf + x) of the nw, ne, sw, se taps
-  float w[4];   // their weights (all zero for padding rows)
+  uint32_t off[4];  // BYTE offset of the nw, ne, sw, se tap pixels inside the hoisted map (< 4 GiB)
+  float w[4];       // their weights (all zero for padding rows)
 };
-__device__ __forceinline__ void write_taps(TapEntry* tab, int row, const RowState& rs, int Hf, int Wf) {
-  int4 px = make_int4(0, 0, 0, 0);
+__device__ __forceinline__ void write_taps(TapEntry* tab, int row, const RowState& rs, int Hf, int Wf, int CH) {
+  uint4 px = make_uint4(0u, 0u, 0u, 0u);
   float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
   if (rs.pixbase >= 0) {
     const float x0 = floorf(rs.ix), y0 = floorf(rs.iy);
@@ -158,12 +158,13 @@ __device__ __forceinline__ void write_taps(TapEntry* tab, int row, const RowStat
     w.w = (rs.ix - x0) * (rs.iy - y0);
     const int xi = static_cast<int>(x0), yi = static_cast<int>(y0);
     const int xj = min(xi + 1, Wf - 1), yj = min(yi + 1, Hf - 1);  // out-of-range taps have weight 0
-    px.x = rs.pixbase + yi * Wf + xi;
-    px.y = rs.pixbase + yi * Wf + xj;
-    px.z = rs.pixbase + yj * Wf + xi;
-    px.w = rs.pixbase + yj * Wf + xj;
+    const uint32_t pb = static_cast<uint32_t>(CH) * 2u;  // bytes per pixel
+    px.x = static_cast<uint32_t>(rs.pixbase + yi * Wf + xi) * pb;
+    px.y = static_cast<uint32_t>(rs.pixbase + yi * Wf + xj) * pb;
+    px.z = static_cast<uint32_t>(rs.pixbase + yj * Wf + xi) * pb;
+    px.w = static_cast<uint32_t>(rs.pixbase + yj * Wf + xj) * pb;
   }
-  *reinterpret_cast<int4*>(tab[row].pix) = px;
+  *reinterpret_cast<uint4*>(tab[row].off) = px;
   *reinterpret_cast<float4*>(tab[row].w) = w;
 }
 
@@ -172,15 +173,16 @@ __device__ __forceinline__ void write_taps(TapEntry* tab, int row, const RowStat
 // (8 B / lane), interpolation in packed fp32 (FFMA2).  Result (fp16) goes to the slot's staging
 // buffer, which the row's two epilogue threads read: pair barriers fence both directions.
 template <int NCH>
-__device__ __forceinline__ void gather_segment(const EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0) {
+__device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0) {
+  PROF(e, kPOther);
   static_assert(NCH == 128 || NCH == 64, "segment width");
   pair_bar(e);  // the partner warp has finished reading the previous segment
+  PROF(e, kPBar);
   if (g.debug & 1) { pair_bar(e); return; }
   const int lane = threadIdx.x & 31;
   const int wrow0 = e.q * 32 + e.half * 16;
   const bool active = (NCH == 128) || lane < 16;
-  const uint2* mp = reinterpret_cast<const uint2*>(g.map + ch0) + lane;
-  const size_t pstride = static_cast<size_t>(g.CH) / 4;  // uint2 per pixel
+  const uint8_t* mp = reinterpret_cast<const uint8_t*>(g.map + ch0) + lane * 8;
   constexpr int U = 4;
 #pragma unroll 1
   for (int j0 = 0; j0 < 16; j0 += U) {
@@ -189,13 +191,13 @@ __device__ __forceinline__ void gather_segment(const EpiCtx& e, const PassGeom& 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const TapEntry* te = taps + wrow0 + j0 + u;
-      const int4 px = *reinterpret_cast<const int4*>(te->pix);
+      const uint4 px = *reinterpret_cast<const uint4*>(te->off);
       w[u] = *reinterpret_cast<const float4*>(te->w);
       if (active) {
-        t[u][0] = __ldg(mp + static_cast<size_t>(px.x) * pstride);
-        t[u][1] = __ldg(mp + static_cast<size_t>(px.y) * pstride);
-        t[u][2] = __ldg(mp + static_cast<size_t>(px.z) * pstride);
-        t[u][3] = __ldg(mp + static_cast<size_t>(px.w) * pstride);
+        t[u][0] = __ldg(reinterpret_cast<const uint2*>(mp + px.x));
+        t[u][1] = __ldg(reinterpret_cast<const uint2*>(mp + px.y));
+        t[u][2] = __ldg(reinterpret_cast<const uint2*>(mp + px.z));
+        t[u][3] = __ldg(reinterpret_cast<const uint2*>(mp + px.w));
       } else {
         t[u][0] = t[u][1] = t[u][2] = t[u][3] = make_uint2(0u, 0u);
       }
@@ -218,12 +220,14 @@ __device__ __forceinline__ void gather_segment(const EpiCtx& e, const PassGeom& 
       }
     }
   }
+  PROF(e, kPGather);
   pair_bar(e);
+  PROF(e, kPBar);
 }
 
 // ----------------------------------------------------------------------------- trunk epilogues
 // x[c0..c0+32) += (W_in[:,60:63] . cam + b_in) + staged segment ; write back ; ReLU -> A tile
-__device__ __forceinline__ void epi_x_first(const EpiCtx& e, int c0, const float4* __restrict__ e0,
+__device__ __forceinline__ void epi_x_first(const EpiCtx& e, int c0, const float4* e0,
                                             const float (&cam)[3]) {
   uint32_t r[32];
   tmem_ld32(e.tmem + c0, r);
@@ -232,7 +236,7 @@ __device__ __forceinline__ void epi_x_first(const EpiCtx& e, int c0, const float
   const float2 cx = make_float2(cam[0], cam[0]), cy = make_float2(cam[1], cam[1]), cz = make_float2(cam[2], cam[2]);
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
-    const float4 q0 = __ldg(e0 + c0 + j), q1 = __ldg(e0 + c0 + j + 1);
+    const float4 q0 = e0[c0 + j], q1 = e0[c0 + j + 1];
     float2 t = ffma2(make_float2(q0.x, q1.x), cx, make_float2(q0.w, q1.w));
     t = ffma2(make_float2(q0.y, q1.y), cy, t);
     t = ffma2(make_float2(q0.z, q1.z), cz, t);
@@ -257,7 +261,7 @@ __device__ __forceinline__ void epi_x_first(const EpiCtx& e, int c0, const float
   uint32_t p[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j)
-    p[j] = pack_relu_f16x2(fminf(v[2 * j], kF16Max), fminf(v[2 * j + 1], kF16Max));
+    p[j] = pack_relu_f16x2(v[2 * j], v[2 * j + 1]);
   a_store32(e, c0, p);
   tmem_st_wait();
 }
@@ -275,9 +279,11 @@ __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom&
   for (int k = 0; k < 5; ++k) {
     // overlap: gather the next hoisted segment while the tensor pipe runs fc_0
     if (k < 2) gather_segment<128>(e, g, taps, seg_ch0 + 128 * (k + 1));
+    PROF(e, kPEpi);
     epi_wait_acc(e);
     for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_relu_to_a(e, 128 + c0, c0, tab.bias + (2 * k) * 128);
     epi_publish(e);  // -> fc_1 (block k), accumulates onto x
+    PROF(e, kPEpi);
     epi_wait_acc(e);
     const float* bn = tab.bias + (2 * k + 1) * 128;
     if (k < 2) {
@@ -287,6 +293,7 @@ __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom&
     }
     epi_publish(e);  // -> fc_0 (block k+1) or lin_out
   }
+  PROF(e, kPEpi);
   epi_wait_acc(e);  // lin_out accumulator ready
 }
 

@@ -11,7 +11,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libnjf_b200.so"))
+LIB_PATH = os.environ.get("NJF_LIB") or os.path.normpath(os.path.join(_HERE, "..", "lib", "libnjf_b200.so"))
 
 _lib = None
 
