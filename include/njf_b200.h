@@ -133,6 +133,18 @@ int njf_field_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArg
                    int bins_stride, void* stream);
 int njf_finish_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* args, void* stream);
 
+/* ---- Model.compute_density (models/model.py:416-456): density head + Jacobian head at explicit
+ * world-space points (no rays).  points [B][N][3]; sigma [B][N], geo [B][N][15], jac [B][N][3A]. */
+int njf_query_points(const NjfField* f, const float* ctxt_w2c, const float* ctxt_k, const void* maps, int Hf,
+                     int Wf, const float* points, int B, int N, float* sigma, float* geo, float* jac,
+                     void* stream);
+/* by-products returned by the reference's DensityHeadOutput: positional encoding (63) of the
+ * context-camera point and the bilinear gather of the RAW encoder features (NCHW fp32, C channels);
+ * either output may be NULL.  (pixel_aligned_features.py:11-35, action_decoder_jacobian.py:97-104) */
+int njf_point_features(const float* feat_nchw, const float* ctxt_w2c, const float* ctxt_k, const float* points,
+                       int B, int N, int C, int Hf, int Wf, float* xyz_features, float* pixel_aligned_features,
+                       void* stream);
+
 /* ---- PDFSampler alone (rendering/ray_samplers.py:351-451, eval/train u supplied by the caller) */
 int njf_pdf_sample(const float* weights, const float* bins_in, int bins_in_stride, const float* u, int u_stride,
                    int n_rays, int s_in, int n_out, float anneal, int sum_vec_width, float* bins_out,

@@ -167,6 +167,7 @@ struct FieldParams {
   float* rgb; float* depth; float* jbar; float* p;
   // per-sample outputs
   float* steps; float* weights; float* sigma; float* jac_out; float* positions; float* rgb_samples;
+  float* geo_out;    // [NR*S][15] density-head geometry features (point queries)
   uint32_t* minmax;  // [2] ordered-uint encoded min / max of steps
 };
 
@@ -439,10 +440,19 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
 #pragma unroll
           for (int j = 0; j < 16; ++j) geo[j] = __uint_as_float(r[j]) + p.dens.b_out[j];
           sigma = expf(__fsub_rn(geo[15], 1.f));
+          if (p.geo_out && valid) {
+            float* gp = p.geo_out + (static_cast<size_t>(rs.ray) * g.S + rs.s) * 15;
+#pragma unroll
+            for (int j = 0; j < 15; ++j) gp[j] = geo[j];
+          }
           // colour head input [geo15 | sh16 | 0...] (action_decoder_jacobian.py:208)
           float sh[16];
-          const float* dp = g.dirs + static_cast<size_t>(valid ? rs.ray : 0) * 3;
-          sh16(__ldg(dp), __ldg(dp + 1), __ldg(dp + 2), sh);
+          if (g.dirs) {
+            const float* dp = g.dirs + static_cast<size_t>(valid ? rs.ray : 0) * 3;
+            sh16(__ldg(dp), __ldg(dp + 1), __ldg(dp + 2), sh);
+          } else {
+            sh16(0.f, 0.f, 1.f, sh);
+          }
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 7; ++j) pk[j] = pack_f16x2(geo[2 * j], geo[2 * j + 1]);
@@ -771,6 +781,52 @@ __global__ void tw_kernel(const float* deltas, const float* sigma, int n_rays, i
   for (int j = lane; j < S; j += 32) out[static_cast<size_t>(ray) * S + j] = (1.f - expf(-dd[j])) * expf(-cum[j]);
 }
 
+// ---- by-products of Model.compute_density (DensityHeadOutput.xyz_features / pixel_aligned_features)
+// one warp per point: the 63-column positional encoding of the context-camera point and the
+// bilinear gather of the RAW encoder features (NCHW fp32, like F.grid_sample in the reference)
+__global__ void point_features_kernel(const float* __restrict__ points, const float* __restrict__ w2c,
+                                      const float* __restrict__ kn, const float* __restrict__ feat, int B, int N,
+                                      int C, int Hf, int Wf, float* __restrict__ xyz_feat,
+                                      float* __restrict__ pix_feat) {
+  const int lane = threadIdx.x & 31;
+  const int pt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pt >= B * N) return;
+  PassGeom g{};
+  g.NR = B * N; g.R = N; g.S = 1; g.G = kRows; g.T = 1;
+  g.points = points; g.ctxt_w2c = w2c; g.ctxt_k = kn; g.Hf = Hf; g.Wf = Wf;
+  RowState rs;
+  row_setup(g, pt / kRows, 0, pt % kRows, rs);
+  if (xyz_feat) {
+    for (int c = lane; c < 63; c += 32) {
+      float v;
+      if (c >= 60) {
+        v = rs.cam[c - 60];
+      } else {
+        const int cc = c < 30 ? c : c - 30, i = cc / 10, k = cc - 10 * i;
+        float t = __fmul_rn(6.2831855f, rs.cam[i]) * static_cast<float>(1 << k);
+        if (c >= 30) t = __fadd_rn(t, 1.5707964f);
+        v = sin_cw(t);
+      }
+      xyz_feat[static_cast<size_t>(pt) * 63 + c] = v;
+    }
+  }
+  if (pix_feat) {
+    const float x0 = floorf(rs.ix), y0 = floorf(rs.iy);
+    const float x1 = x0 + 1.f, y1 = y0 + 1.f;
+    const float wnw = (x1 - rs.ix) * (y1 - rs.iy), wne = (rs.ix - x0) * (y1 - rs.iy);
+    const float wsw = (x1 - rs.ix) * (rs.iy - y0), wse = (rs.ix - x0) * (rs.iy - y0);
+    const int xi = static_cast<int>(x0), yi = static_cast<int>(y0);
+    const int xj = min(xi + 1, Wf - 1), yj = min(yi + 1, Hf - 1);
+    const int b = pt / N;
+    const float* F = feat + static_cast<size_t>(b) * C * Hf * Wf;
+    for (int c = lane; c < C; c += 32) {
+      const float* fc = F + static_cast<size_t>(c) * Hf * Wf;
+      const float v = fc[yi * Wf + xi] * wnw + fc[yi * Wf + xj] * wne + fc[yj * Wf + xi] * wsw + fc[yj * Wf + xj] * wse;
+      pix_feat[static_cast<size_t>(pt) * C + c] = v;
+    }
+  }
+}
+
 }  // namespace njf
 
 // ============================================================================= host launchers
@@ -812,6 +868,7 @@ int make_geom(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a,
   g.Wf = a->Wf;
   const char* dbg = getenv("NJF_DEBUG_SKIP");
   g.debug = dbg ? atoi(dbg) : 0;
+  g.points = nullptr;
   (void)f;
   return 0;
 }
@@ -940,6 +997,55 @@ extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const N
   const int grid = nitems < num_sms() ? nitems : num_sms();
   field_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
   decode_minmax_kernel<<<1, 1, 0, stream>>>(p.minmax);
+  NJF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int njf_query_points(const NjfField* f, const float* ctxt_w2c, const float* ctxt_k, const void* maps,
+                                int Hf, int Wf, const float* points, int B, int N, float* sigma, float* geo,
+                                float* jac, void* stream_) {
+  if (!f || !ctxt_w2c || !ctxt_k || !maps || !points) NJF_FAIL("njf_query_points: null argument");
+  if (B < 1 || N < 1) NJF_FAIL("njf_query_points: B=%d N=%d", B, N);
+  if (static_cast<size_t>(B) * Hf * Wf * 768 * 2 >= (1ull << 32)) NJF_FAIL("njf_query_points: maps too large");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FieldParams p{};
+  p.prog = f->field_prog;
+  p.blob = f->field_blob;
+  p.dens = f->dens_trunk;
+  p.jac = f->jac_trunk;
+  p.head = f->head;
+  p.color = f->color;
+  PassGeom& g = p.g;
+  g.NR = B * N; g.R = N; g.S = 1; g.G = kRows; g.T = 1;
+  g.NG = (g.NR + g.G - 1) / g.G;
+  g.ctxt_w2c = ctxt_w2c;
+  g.ctxt_k = ctxt_k;
+  const size_t px = static_cast<size_t>(B) * Hf * Wf;
+  g.map = static_cast<const __half*>(maps) + px * f->ch_prop * f->desc.n_proposal;
+  g.CH = f->ch_main; g.Hf = Hf; g.Wf = Wf;
+  g.points = points;
+  p.head_kind = f->desc.head;
+  p.A = f->desc.action_dim;
+  p.sigma = sigma;
+  p.geo_out = geo;
+  p.jac_out = jac;
+  if (set_smem(field_kernel)) return 1;
+  const int nitems = (g.NG + 1) / 2;
+  const int grid = nitems < num_sms() ? nitems : num_sms();
+  field_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  NJF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int njf_point_features(const float* feat_nchw, const float* ctxt_w2c, const float* ctxt_k,
+                                  const float* points, int B, int N, int C, int Hf, int Wf, float* xyz_features,
+                                  float* pixel_aligned_features, void* stream_) {
+  if (!ctxt_w2c || !ctxt_k || !points) NJF_FAIL("njf_point_features: null argument");
+  if (pixel_aligned_features && !feat_nchw) NJF_FAIL("njf_point_features: feature map required");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int wpb = 8;
+  point_features_kernel<<<(B * N + wpb - 1) / wpb, wpb * 32, 0, stream>>>(points, ctxt_w2c, ctxt_k, feat_nchw, B, N, C,
+                                                                       Hf, Wf, xyz_features, pixel_aligned_features);
   NJF_CUDA(cudaGetLastError());
   return 0;
 }

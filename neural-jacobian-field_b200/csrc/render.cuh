@@ -25,6 +25,7 @@ struct PassGeom {
   const __half* map;      // hoisted map of this pass [B][Hf*Wf][CH]
   int CH, Hf, Wf;
   int debug;              // NJF_DEBUG_SKIP bits (timing attribution only): 1 skip gather, 2 skip posenc
+  const float* points;    // point-query mode (Model.compute_density): [NR][3] world points, S == 1
 };
 
 struct RowState {
@@ -65,6 +66,12 @@ __device__ __forceinline__ void row_setup(const PassGeom& g, int group, int tile
   }
   rs.ray = ray;
   const int b = ray / g.R;
+  if (g.points) {  // explicit world-space points instead of (ray, bin) samples
+    rs.tmid = 0.f;
+    rs.delta = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rs.pos[i] = __ldg(g.points + static_cast<size_t>(ray) * 3 + i);
+  } else {
   const float* bp = g.bins + static_cast<size_t>(ray) * g.bins_stride;
   const float b0 = __ldg(bp + s), b1 = __ldg(bp + s + 1);
   const float nr = __ldg(g.z_near + b), fr = __ldg(g.z_far + b);
@@ -79,6 +86,7 @@ __device__ __forceinline__ void row_setup(const PassGeom& g, int group, int tile
 #pragma unroll
   for (int i = 0; i < 3; ++i)  // origins + directions * (starts + ends) / 2
     rs.pos[i] = __fadd_rn(__ldg(o + i), __fmul_rn(__fmul_rn(__ldg(d + i), se), 0.5f));
+  }
   // world -> context camera (pixel_aligned_features.py:18-20, geometry.py:59-65)
   const float* W = g.ctxt_w2c + b * 16;
 #pragma unroll
@@ -144,7 +152,7 @@ __device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)
 // row by the row's own thread, then broadcast-read by the gathering warp for every channel segment.
 struct TapEntry {
   uint32_t off[4];  // BYTE offset of the nw, ne, sw, se tap pixels inside the hoisted map (< 4 GiB)
-  float w[4];       // their weights (all zero for padding rows)
+  uint32_t w2[4];   // their weights as packed fp16 pairs {w, w} (all zero for padding rows)
 };
 __device__ __forceinline__ void write_taps(TapEntry* tab, int row, const RowState& rs, int Hf, int Wf, int CH) {
   uint4 px = make_uint4(0u, 0u, 0u, 0u);
@@ -165,13 +173,15 @@ __device__ __forceinline__ void write_taps(TapEntry* tab, int row, const RowStat
     px.w = static_cast<uint32_t>(rs.pixbase + yj * Wf + xj) * pb;
   }
   *reinterpret_cast<uint4*>(tab[row].off) = px;
-  *reinterpret_cast<float4*>(tab[row].w) = w;
+  *reinterpret_cast<uint4*>(tab[row].w2) =
+      make_uint4(pack_f16x2(w.x, w.x), pack_f16x2(w.y, w.y), pack_f16x2(w.z, w.z), pack_f16x2(w.w, w.w));
 }
 
 // Gather of NCH hoisted channels starting at channel ch0 for the 16 rows owned by this warp
 // (rows 32q + 16h ..); each tap is one contiguous NCH*2-byte read spread over the lanes
-// (8 B / lane), interpolation in packed fp32 (FFMA2).  Result (fp16) goes to the slot's staging
-// buffer, which the row's two epilogue threads read: pair barriers fence both directions.
+// (8 B / lane).  The four taps are blended in packed fp16 (HFMA2; the map, the weights and the
+// staged result are fp16 anyway -- 4 instead of 1 fp16 roundings).
+// The staging buffer is read by the row's two epilogue threads: pair barriers fence both ways.
 template <int NCH>
 __device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0) {
   PROF(e, kPOther);
@@ -187,12 +197,12 @@ __device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, con
 #pragma unroll 1
   for (int j0 = 0; j0 < 16; j0 += U) {
     uint2 t[U][4];
-    float4 w[U];
+    uint4 w[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const TapEntry* te = taps + wrow0 + j0 + u;
       const uint4 px = *reinterpret_cast<const uint4*>(te->off);
-      w[u] = *reinterpret_cast<const float4*>(te->w);
+      w[u] = *reinterpret_cast<const uint4*>(te->w2);
       if (active) {
         t[u][0] = __ldg(reinterpret_cast<const uint2*>(mp + px.x));
         t[u][1] = __ldg(reinterpret_cast<const uint2*>(mp + px.y));
@@ -204,18 +214,18 @@ __device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, con
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const float wq[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
-      float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+      const uint32_t wq[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+      __half2 lo = __hmul2(*reinterpret_cast<const __half2*>(&t[u][0].x), *reinterpret_cast<const __half2*>(&wq[0]));
+      __half2 hi = __hmul2(*reinterpret_cast<const __half2*>(&t[u][0].y), *reinterpret_cast<const __half2*>(&wq[0]));
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 ww = make_float2(wq[q], wq[q]);
-        lo = ffma2(__half22float2(*reinterpret_cast<const __half2*>(&t[u][q].x)), ww, lo);
-        hi = ffma2(__half22float2(*reinterpret_cast<const __half2*>(&t[u][q].y)), ww, hi);
+      for (int q = 1; q < 4; ++q) {
+        lo = __hfma2(*reinterpret_cast<const __half2*>(&t[u][q].x), *reinterpret_cast<const __half2*>(&wq[q]), lo);
+        hi = __hfma2(*reinterpret_cast<const __half2*>(&t[u][q].y), *reinterpret_cast<const __half2*>(&wq[q]), hi);
       }
       if (active) {
         uint2 o;
-        o.x = pack_f16x2(lo.x, lo.y);
-        o.y = pack_f16x2(hi.x, hi.y);
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
         *reinterpret_cast<uint2*>(e.tz + tz_offset(wrow0 + j0 + u, lane >> 1) + (lane & 1) * 8) = o;
       }
     }

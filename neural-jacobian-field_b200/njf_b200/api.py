@@ -70,6 +70,11 @@ def _declare():
                                     c_void_p]
     L.njf_field_pass.restype = c_int
     L.njf_field_pass.argtypes = [c_void_p, POINTER(NjfCameras), POINTER(NjfRenderArgs), c_void_p, c_int, c_void_p]
+    L.njf_query_points.restype = c_int
+    L.njf_query_points.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]
+    L.njf_point_features.restype = c_int
+    L.njf_point_features.argtypes = [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_void_p, c_void_p]
     L.njf_pdf_sample.restype = c_int
     L.njf_pdf_sample.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
                                  c_void_p, c_void_p, c_void_p]

@@ -127,6 +127,14 @@ class ModelInferenceEncoding:
 
 
 @dataclass
+class DensityHeadOutput:  # action_decoder_jacobian.py:63-68
+    density: Tensor
+    density_features: Tensor
+    xyz_features: Tensor
+    pixel_aligned_features: Tensor
+
+
+@dataclass
 class PixelEncoding:
     features: Tensor
     extrinsics: Tensor
@@ -364,5 +372,31 @@ class Model(nn.Module):
         out["flow_rgb"] = flow_to_image(out["flow_raw"].permute(0, 3, 1, 2).contiguous()).permute(0, 2, 3, 1)
         return RenderingOutput(**out)
 
-    def compute_density(self, world_space_xyz, pixel_encoding):
-        raise NotImplementedError("point-query API (model.py:416-456) is not built yet: next scope row")
+    # ------------------------------------------------------------------ point queries (model.py:416-456)
+    def compute_density(self, world_space_xyz: Tensor, pixel_encoding: PixelEncoding):
+        """Density head (+ Jacobian head) at explicit world-space points (B,N,3).  Returns
+        ``(DensityHeadOutput, extras)`` like the reference; ``extras["jacobian_head_output"]`` is (B,N,3A)."""
+        self._check_mode()
+        L = api._declare()
+        dev = self._device()
+        if pixel_encoding.hoisted is None:
+            pixel_encoding.hoisted = self.field().hoist(pixel_encoding.features.to(dev).float().contiguous())
+        pts = world_space_xyz.detach().to(dev, torch.float32).contiguous()
+        B, N = pts.shape[:2]
+        A = self.cfg.action_dim
+        f = lambda t: t.detach().to("cpu", torch.float32)
+        w2c = torch.inverse(f(pixel_encoding.extrinsics)).contiguous().to(dev)
+        kn = f(pixel_encoding.intrinsics).contiguous().to(dev)
+        feats = pixel_encoding.features.to(dev).float().contiguous()
+        C, Hf, Wf = feats.shape[1:]
+        o = dict(device=dev, dtype=torch.float32)
+        sigma, geo, jac = torch.empty(B, N, 1, **o), torch.empty(B, N, 15, **o), torch.empty(B, N, 3 * A, **o)
+        xyzf, pixf = torch.empty(B, N, 63, **o), torch.empty(B, N, C, **o)
+        with torch.cuda.device(dev):
+            _lib.check(L.njf_query_points(self.field().handle, api.dptr(w2c), api.dptr(kn), api.dptr(pixel_encoding.hoisted),
+                                          Hf, Wf, api.dptr(pts), B, N, api.dptr(sigma), api.dptr(geo), api.dptr(jac),
+                                          api.stream_ptr()))
+            _lib.check(L.njf_point_features(api.dptr(feats), api.dptr(w2c), api.dptr(kn), api.dptr(pts), B, N, C, Hf, Wf,
+                                            api.dptr(xyzf), api.dptr(pixf), api.stream_ptr()))
+        out = DensityHeadOutput(density=sigma, density_features=geo, xyz_features=xyzf, pixel_aligned_features=pixf)
+        return out, {"jacobian_head_output": jac}

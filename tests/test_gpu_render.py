@@ -189,3 +189,38 @@ def test_render_vs_oracle_seeded(head, A, s_prop, s_nerf, R, B):
     psnr = 10 * np.log10(1.0 / max(mse, 1e-12))
     print(f"{head} A={A} S={s_prop}->{s_nerf}: PSNR vs oracle {psnr:.1f} dB")
     assert psnr > 50.0
+
+
+def test_compute_density_point_queries():
+    """Model.compute_density (models/model.py:416-456) at random world points vs the oracle heads."""
+    from njf_b200 import api
+
+    fx, t, head, A, s_prop, s_nerf, w = load_fixture("render_transformer")
+    feat = t("feat")
+    g = torch.Generator().manual_seed(4)
+    pts = torch.rand(1, 333, 3, generator=g) * torch.tensor([1.0, 0.8, 2.0]) + torch.tensor([-0.5, -0.4, 0.6])
+    spec = O.FieldSpec(head=head, action_dim=A)
+    with torch.no_grad():
+        sig, geo, jac, z, enc = O.field_heads(w, pts, feat, t("ctxt_c2w"), t("ctxt_k"), spec)
+    fld, maps = _field_and_maps(head, A, s_prop, w, feat)
+    L = api._declare()
+    from njf_b200 import _lib
+    w2c = torch.inverse(t("ctxt_c2w")).contiguous().to(DEV)
+    kn = t("ctxt_k").contiguous().to(DEV)
+    B, N = pts.shape[:2]
+    o = dict(device=DEV, dtype=torch.float32)
+    s_d, g_d, j_d = torch.empty(B, N, 1, **o), torch.empty(B, N, 15, **o), torch.empty(B, N, 3 * A, **o)
+    x_d, p_d = torch.empty(B, N, 63, **o), torch.empty(B, N, 512, **o)
+    pd = pts.to(DEV).contiguous()
+    fd = feat.to(DEV).contiguous()
+    Hf, Wf = feat.shape[-2:]
+    _lib.check(L.njf_query_points(fld.handle, api.dptr(w2c), api.dptr(kn), api.dptr(maps), Hf, Wf, api.dptr(pd), B, N,
+                                  api.dptr(s_d), api.dptr(g_d), api.dptr(j_d), api.stream_ptr()))
+    _lib.check(L.njf_point_features(api.dptr(fd), api.dptr(w2c), api.dptr(kn), api.dptr(pd), B, N, 512, Hf, Wf,
+                                    api.dptr(x_d), api.dptr(p_d), api.stream_ptr()))
+    torch.cuda.synchronize()
+    assert _rel(s_d.cpu().numpy(), sig.numpy(), 0.05) < 2e-2
+    np.testing.assert_allclose(g_d.cpu().numpy(), geo.numpy(), atol=2e-2 * float(geo.abs().max()), rtol=0)
+    np.testing.assert_allclose(j_d.cpu().numpy(), jac.numpy(), atol=2e-2 * float(jac.abs().max()), rtol=0)
+    np.testing.assert_allclose(x_d.cpu().numpy(), enc.numpy(), atol=2e-5, rtol=0)
+    np.testing.assert_allclose(p_d.cpu().numpy(), z.numpy(), atol=1e-5, rtol=1e-5)
