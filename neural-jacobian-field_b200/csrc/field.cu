@@ -241,6 +241,7 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
   NJF_CUDA(cudaMemcpy(f->d_blob, b.blob.data(), b.blob.size(), cudaMemcpyHostToDevice));
   NJF_CUDA(cudaMemcpy(f->d_hoist_w, b.hoist_w.data(), b.hoist_w.size() * sizeof(float), cudaMemcpyHostToDevice));
   NJF_CUDA(cudaMemcpy(f->d_hoist_b, b.hoist_b.data(), b.hoist_b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (njf_hoist_build(f, b.hoist_w, b.hoist_b)) return 1;
   for (int i = 0; i < desc->n_proposal; ++i) f->prop_blob[i] = f->d_blob;
   f->field_blob = f->d_blob;
   *out = f;
@@ -250,6 +251,7 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
 extern "C" void njf_field_destroy(NjfField* f) {
   if (!f) return;
   cudaFree(f->d_blob);
+  cudaFree(f->d_hoist_img);
   cudaFree(f->d_hoist_w);
   cudaFree(f->d_hoist_b);
   delete f;

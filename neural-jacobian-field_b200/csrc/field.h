@@ -27,8 +27,13 @@ struct ColorTab {
 
 }  // namespace njf
 
+#include <vector>
+
 struct NjfField {
+  struct HoistJobHost { int map, c0, N; uint32_t w_off; int bias_off; };
   NjfFieldDesc desc;
+  uint8_t* d_hoist_img = nullptr;          // tcgen05 weight images of the hoist GEMM (hoist_tc.cu)
+  std::vector<HoistJobHost> hoist_jobs;
   uint8_t* d_blob = nullptr;   // all layer images
   float* d_hoist_w = nullptr;  // [ch_total][512] rows of the hoisted linear maps
   float* d_hoist_b = nullptr;  // [ch_total]
@@ -44,3 +49,8 @@ struct NjfField {
   njf::HeadTab head;
   njf::ColorTab color;
 };
+
+// hoist_tc.cu
+int njf_hoist_build(NjfField* f, const std::vector<float>& w, const std::vector<float>& b);
+int njf_hoist_launch(const NjfField* f, const float* feat_nchw, int B, int Hf, int Wf, void* maps_out,
+                     cudaStream_t stream);

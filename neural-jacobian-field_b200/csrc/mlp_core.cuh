@@ -166,7 +166,8 @@ __device__ __forceinline__ void issuer_role(const CtaCtx& c, const Program& prog
 // ----------------------------------------------------------------------------- optional phase profiler
 // -DNJF_PROFILE: lane 0 of every epilogue warp attributes SM-clock cycles to phases; summed per
 // phase into g_prof (read with njf_prof_read).  Zero cost in the normal build.
-enum ProfPhase { kPSetup = 0, kPGather, kPWaitAcc, kPEpi, kPWeights, kPPdf, kPHead, kPColor, kPComposite, kPBar, kPOther, kPCount };
+enum ProfPhase { kPSetup = 0, kPGather, kPWaitAcc, kPEpi, kPWeights, kPPdf, kPHead, kPColor, kPComposite, kPBar, kPOther,
+                 kPLn, kPSoftmax, kPGelu, kPRes, kPCount };
 #ifdef NJF_PROFILE
 __device__ unsigned long long g_prof[16];
 #define PROF(e, ph)                                   \

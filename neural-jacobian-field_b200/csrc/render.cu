@@ -288,8 +288,10 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
 #pragma unroll 1
   for (int l = 0; l < 3; ++l) {
     const XfLayerTab& L = H.layer[l];
+    PROF(e, kPOther);
     ln64_to_a(e, sc, x, L.ln1_g, L.ln1_b);
     epi_publish(e);  // -> M1: scaled logits over (head, key)
+    PROF(e, kPLn);
     epi_wait_acc(e);
     {
       float lg[32];
@@ -307,6 +309,7 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
       store32_to_a(e, lg);
     }
     epi_publish(e);  // -> M2: attention . (V W_out)
+    PROF(e, kPSoftmax);
     epi_wait_acc(e);
     {
       float t[32];
@@ -315,8 +318,10 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] += t[j];
     }
+    PROF(e, kPRes);
     ln64_to_a(e, sc, x, L.ln2_g, L.ln2_b);
     epi_publish(e);  // -> W1
+    PROF(e, kPLn);
     epi_wait_acc(e);
     {
       float t[32];
@@ -327,6 +332,7 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
       store32_to_a(e, t);
     }
     epi_publish(e);  // -> W2
+    PROF(e, kPGelu);
     epi_wait_acc(e);
     {
       float t[32];
@@ -335,6 +341,7 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] += t[j];
     }
+    PROF(e, kPRes);
   }
   store32_to_a(e, x);
   epi_publish(e);  // -> jacobian_head Linear(64, 3A)
@@ -922,6 +929,8 @@ extern "C" int njf_hoist_features(const NjfField* f, const float* feat_nchw, int
                                   void* stream_) {
   if (!f || !feat_nchw || !maps_out) NJF_FAIL("njf_hoist_features: null argument");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  static const bool simt = getenv("NJF_HOIST_SIMT") != nullptr;  // fp32 SIMT variant, kept for A/B checks
+  if (!simt) return njf_hoist_launch(f, feat_nchw, B, Hf, Wf, maps_out, stream);
   const int HW = Hf * Wf;
   __half* out = static_cast<__half*>(maps_out);
   int n0 = 0;

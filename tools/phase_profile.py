@@ -12,7 +12,8 @@ import torch
 import bench  # noqa: E402  (sets sys.path for the package)
 from njf_b200 import _lib, api
 
-PH = ["setup", "gather", "wait_acc", "epilogue", "weights", "pdf", "head", "color", "composite", "barrier", "other"]
+PH = ["setup", "gather", "wait_acc", "epilogue", "weights", "pdf", "head", "color", "composite", "barrier", "other",
+      "xf_layernorm", "xf_softmax", "xf_gelu", "xf_residual"]
 
 
 def main():
