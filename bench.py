@@ -235,6 +235,8 @@ def main():
     a.s_prop[0] = S_PROP[0]
     a.origins, a.dirs = api.dptr(sc["origins"]), api.dptr(sc["dirs"])
     a.z_near, a.z_far, a.action = api.dptr(sc["z_near"]), api.dptr(sc["z_far"]), api.dptr(sc["action"])
+    h_nf = (sc["z_near"].cpu().contiguous(), sc["z_far"].cpu().contiguous())
+    a.h_z_near, a.h_z_far = h_nf[0].data_ptr(), h_nf[1].data_ptr()
     a.bins0, a.bins0_stride = api.dptr(bins0), 0
     a.u[0], a.u_stride[0] = api.dptr(us[0]), 0
     a.anneal, a.sum_vec_width = 1.0, api.default_sum_vec_width()
@@ -357,7 +359,7 @@ def main():
         "roofline": roof,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(te_t.item()) / e2e_steps * 1e3},
-        "gpu_launches": 6 * args.steps,
+        "gpu_launches": 7 * args.steps,
         "clocks": clk,
     }
     if not args.no_cpu_baseline:

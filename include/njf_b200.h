@@ -77,6 +77,11 @@ typedef struct NjfCameras {
   const float* ctxt_k;    /* [B][9]  normalised intrinsics (pixel_aligned_features.py:21) */
   const float* trgt_w2c;  /* [B][16] inverse of CameraInput.trgt_extrinsics (geometry.py:206-215) */
   const float* trgt_k_px; /* [B][9]  pixel-unit intrinsics (models/model.py:305-312) */
+  /* optional HOST copies of ctxt_w2c / ctxt_k (NULL if unknown): when present together with
+     NjfRenderArgs.h_z_near / h_z_far and B <= 16, the per-view constants ride in the kernel
+     parameter block (constant bank) and row set-up issues no global loads for them */
+  const float* h_ctxt_w2c;
+  const float* h_ctxt_k;
 } NjfCameras;
 
 /* ---- Model.forward / encode_image ------------------------------------------------------------
@@ -93,6 +98,8 @@ typedef struct NjfRenderArgs {
   const float* dirs;              /* [B][R][3] */
   const float* z_near;            /* [B] */
   const float* z_far;             /* [B] */
+  const float* h_z_near;          /* optional HOST copy of z_near (see NjfCameras.h_ctxt_w2c) */
+  const float* h_z_far;           /* optional HOST copy of z_far */
   const float* action;            /* [B][A] */
   const float* bins0;             /* level-0 spacing bins: [s_prop[0]+1] shared (stride 0) or per ray */
   int bins0_stride;               /* 0 or s_prop[0]+1 (train-mode stratified jitter comes in this way) */

@@ -252,6 +252,7 @@ extern "C" void njf_field_destroy(NjfField* f) {
   if (!f) return;
   cudaFree(f->d_blob);
   cudaFree(f->d_hoist_img);
+  cudaFree(f->d_scratch);
   cudaFree(f->d_hoist_w);
   cudaFree(f->d_hoist_b);
   delete f;

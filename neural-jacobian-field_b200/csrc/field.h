@@ -33,6 +33,8 @@ struct NjfField {
   struct HoistJobHost { int map, c0, N; uint32_t w_off; int bias_off; };
   NjfFieldDesc desc;
   uint8_t* d_hoist_img = nullptr;          // tcgen05 weight images of the hoist GEMM (hoist_tc.cu)
+  mutable float* d_scratch = nullptr;      // grow-only per-field scratch (proposal weights between the
+  mutable size_t scratch_bytes = 0;        // proposal kernel and the PDF kernel); one stream at a time
   std::vector<HoistJobHost> hoist_jobs;
   uint8_t* d_blob = nullptr;   // all layer images
   float* d_hoist_w = nullptr;  // [ch_total][512] rows of the hoisted linear maps

@@ -74,8 +74,10 @@ struct ProposalParams {
   float anneal;
   int sum_vec;
   float* bins_out;       // [NR][n_out+1]
-  float* weights_out;    // optional [NR][S]
+  float* weights_out;    // [NR][S] (required when the PDF step runs as its own kernel)
   int32_t* inds_out;     // optional [NR][n_out+1]
+  int fused_pdf;         // 1: resample inside this kernel; 0: pdf_kernel runs afterwards (one warp per ray,
+                         //    fully parallel -- in here a single warp per tile would do it while seven wait)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_constant__ ProposalParams p) {
@@ -130,10 +132,11 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
         }
         const float w = tile_weights(e, sc, g, tile, dd, carry);
         if (e.half == 0 && rs.ray >= 0) {
-          sc->wts[g.T == 1 ? e.row : rs.s] = w;
+          if (p.fused_pdf) sc->wts[g.T == 1 ? e.row : rs.s] = w;
           if (p.weights_out) p.weights_out[static_cast<size_t>(rs.ray) * g.S + rs.s] = w;
         }
       }
+      if (!p.fused_pdf) continue;
       slot_bar(e);
       PROF(e, kPBar);
       for (int lr = w8; lr < g.G; lr += 8) {
@@ -876,6 +879,17 @@ int make_geom(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a,
   const char* dbg = getenv("NJF_DEBUG_SKIP");
   g.debug = dbg ? atoi(dbg) : 0;
   g.points = nullptr;
+  g.n_const_views = 0;
+  if (cams->h_ctxt_w2c && cams->h_ctxt_k && a->h_z_near && a->h_z_far && a->B <= kMaxConstViews) {
+    for (int b = 0; b < a->B; ++b) {
+      float* vc = g.view_const[b];
+      for (int i = 0; i < 12; ++i) vc[i] = cams->h_ctxt_w2c[b * 16 + i];
+      for (int i = 0; i < 9; ++i) vc[12 + i] = cams->h_ctxt_k[b * 9 + i];
+      vc[21] = a->h_z_near[b];
+      vc[22] = a->h_z_far[b];
+    }
+    g.n_const_views = a->B;
+  }
   (void)f;
   return 0;
 }
@@ -965,11 +979,27 @@ extern "C" int njf_proposal_pass(const NjfField* f, const NjfCameras* cams, cons
   p.bins_out = a->level_bins[level];
   p.weights_out = a->prop_weights[level];
   p.inds_out = a->level_inds[level];
+  p.fused_pdf = getenv("NJF_FUSED_PDF") ? 1 : 0;
+  if (!p.fused_pdf && !p.weights_out) {
+    // transmittance weights travel through a grow-only scratch buffer owned by the field
+    const size_t need = static_cast<size_t>(p.g.NR) * p.g.S * sizeof(float);
+    if (f->scratch_bytes < need) {
+      if (f->d_scratch) NJF_CUDA(cudaFree(f->d_scratch));
+      f->d_scratch = nullptr;
+      f->scratch_bytes = 0;
+      NJF_CUDA(cudaMalloc(&f->d_scratch, need));
+      f->scratch_bytes = need;
+    }
+    p.weights_out = f->d_scratch;
+  }
   if (set_smem(proposal_kernel)) return 1;
   const int nitems = (p.g.NG + 1) / 2;
   const int grid = nitems < num_sms() ? nitems : num_sms();
   proposal_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
   NJF_CUDA(cudaGetLastError());
+  if (!p.fused_pdf)
+    return njf_pdf_sample(p.weights_out, bins_in, bins_in_stride, p.u, p.u_stride, p.g.NR, p.g.S, p.n_out, p.anneal,
+                          p.sum_vec, p.bins_out, p.inds_out, stream_);
   return 0;
 }
 

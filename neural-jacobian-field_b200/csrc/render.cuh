@@ -26,7 +26,12 @@ struct PassGeom {
   int CH, Hf, Wf;
   int debug;              // NJF_DEBUG_SKIP bits (timing attribution only): 1 skip gather, 2 skip posenc
   const float* points;    // point-query mode (Model.compute_density): [NR][3] world points, S == 1
+  // per-view constants of the first kMaxConstViews views, carried in the parameter constant bank
+  // (row set-up then needs no global loads for cameras / near / far); n_const_views == 0 -> use pointers
+  int n_const_views;
+  float view_const[16][24];  // [view][ w2c rows 0-2 (12) | K (9) | near | far | pad ]
 };
+constexpr int kMaxConstViews = 16;
 
 struct RowState {
   float pos[3];   // world-space sample position (RaySamples.get_positions, ray_samplers.py:48-55)
@@ -66,6 +71,8 @@ __device__ __forceinline__ void row_setup(const PassGeom& g, int group, int tile
   }
   rs.ray = ray;
   const int b = ray / g.R;
+  const bool cv = b < g.n_const_views;
+  const float* vc = g.view_const[cv ? b : 0];
   if (g.points) {  // explicit world-space points instead of (ray, bin) samples
     rs.tmid = 0.f;
     rs.delta = 0.f;
@@ -74,7 +81,7 @@ __device__ __forceinline__ void row_setup(const PassGeom& g, int group, int tile
   } else {
   const float* bp = g.bins + static_cast<size_t>(ray) * g.bins_stride;
   const float b0 = __ldg(bp + s), b1 = __ldg(bp + s + 1);
-  const float nr = __ldg(g.z_near + b), fr = __ldg(g.z_far + b);
+  const float nr = cv ? vc[21] : __ldg(g.z_near + b), fr = cv ? vc[22] : __ldg(g.z_far + b);
   // spacing -> euclidean: x * s_far + (1 - x) * s_near  (ray_samplers.py:242-245)
   const float st = __fadd_rn(__fmul_rn(b0, fr), __fmul_rn(__fsub_rn(1.f, b0), nr));
   const float en = __fadd_rn(__fmul_rn(b1, fr), __fmul_rn(__fsub_rn(1.f, b1), nr));
@@ -88,16 +95,25 @@ __device__ __forceinline__ void row_setup(const PassGeom& g, int group, int tile
     rs.pos[i] = __fadd_rn(__ldg(o + i), __fmul_rn(__fmul_rn(__ldg(d + i), se), 0.5f));
   }
   // world -> context camera (pixel_aligned_features.py:18-20, geometry.py:59-65)
-  const float* W = g.ctxt_w2c + b * 16;
+  float Wm[12], Km[9];
+  if (cv) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Wm[i] = vc[i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Km[i] = vc[12 + i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Wm[i] = __ldg(g.ctxt_w2c + b * 16 + i);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Km[i] = __ldg(g.ctxt_k + b * 9 + i);
+  }
 #pragma unroll
   for (int i = 0; i < 3; ++i)
-    rs.cam[i] = fmaf(__ldg(W + 4 * i + 2), rs.pos[2],
-                     fmaf(__ldg(W + 4 * i + 1), rs.pos[1], fmaf(__ldg(W + 4 * i), rs.pos[0], __ldg(W + 4 * i + 3))));
+    rs.cam[i] = fmaf(Wm[4 * i + 2], rs.pos[2], fmaf(Wm[4 * i + 1], rs.pos[1], fmaf(Wm[4 * i], rs.pos[0], Wm[4 * i + 3])));
   // project with normalised intrinsics, z-divide with +1e-9 (geometry.py:137-154)
-  const float* K = g.ctxt_k + b * 9;
-  const float u = fmaf(__ldg(K + 2), rs.cam[2], fmaf(__ldg(K + 1), rs.cam[1], __ldg(K + 0) * rs.cam[0]));
-  const float v = fmaf(__ldg(K + 5), rs.cam[2], fmaf(__ldg(K + 4), rs.cam[1], __ldg(K + 3) * rs.cam[0]));
-  const float w = fmaf(__ldg(K + 8), rs.cam[2], fmaf(__ldg(K + 7), rs.cam[1], __ldg(K + 6) * rs.cam[0]));
+  const float u = fmaf(Km[2], rs.cam[2], fmaf(Km[1], rs.cam[1], Km[0] * rs.cam[0]));
+  const float v = fmaf(Km[5], rs.cam[2], fmaf(Km[4], rs.cam[1], Km[3] * rs.cam[0]));
+  const float w = fmaf(Km[8], rs.cam[2], fmaf(Km[7], rs.cam[1], Km[6] * rs.cam[0]));
   const float zd = __fadd_rn(w, 1e-9f);
   const float un = __fdiv_rn(u, zd), vn = __fdiv_rn(v, zd);
   // grid = (uv - 0.5) * 2 ; align_corners=True: ((g + 1) / 2) * (size - 1) ; border clamp

@@ -28,13 +28,15 @@ class NjfTensor(Structure):
 
 
 class NjfCameras(Structure):
-    _fields_ = [("ctxt_w2c", c_void_p), ("ctxt_k", c_void_p), ("trgt_w2c", c_void_p), ("trgt_k_px", c_void_p)]
+    _fields_ = [("ctxt_w2c", c_void_p), ("ctxt_k", c_void_p), ("trgt_w2c", c_void_p), ("trgt_k_px", c_void_p),
+                ("h_ctxt_w2c", c_void_p), ("h_ctxt_k", c_void_p)]
 
 
 class NjfRenderArgs(Structure):
     _fields_ = [
         ("B", c_int), ("R", c_int), ("n_levels", c_int), ("s_prop", c_int * NJF_MAX_LEVELS), ("s_nerf", c_int),
-        ("origins", c_void_p), ("dirs", c_void_p), ("z_near", c_void_p), ("z_far", c_void_p), ("action", c_void_p),
+        ("origins", c_void_p), ("dirs", c_void_p), ("z_near", c_void_p), ("z_far", c_void_p),
+        ("h_z_near", c_void_p), ("h_z_far", c_void_p), ("action", c_void_p),
         ("bins0", c_void_p), ("bins0_stride", c_int),
         ("u", c_void_p * NJF_MAX_LEVELS), ("u_stride", c_int * NJF_MAX_LEVELS),
         ("anneal", c_float), ("sum_vec_width", c_int),
@@ -154,12 +156,14 @@ def make_cameras(ctxt_c2w, ctxt_k, trgt_c2w, trgt_k_px, device):
     """The reference inverts the 4x4 poses with torch.inverse inside the path (geometry.py:59-65);
     the 4x4 inversions stay on the host side (fp32, CPU LAPACK like the CPU reference)."""
     f = lambda t: t.detach().to("cpu", torch.float32)
-    cw = torch.inverse(f(ctxt_c2w)).contiguous().to(device)
+    cw_h = torch.inverse(f(ctxt_c2w)).contiguous()
+    ck_h = f(ctxt_k).contiguous()
+    cw = cw_h.to(device)
     tw = torch.inverse(f(trgt_c2w)).contiguous().to(device) if trgt_c2w is not None else None
-    ck = f(ctxt_k).contiguous().to(device)
+    ck = ck_h.to(device)
     tk = f(trgt_k_px).contiguous().to(device) if trgt_k_px is not None else None
-    cams = NjfCameras(dptr(cw), dptr(ck), dptr(tw), dptr(tk))
-    return cams, (cw, ck, tw, tk)
+    cams = NjfCameras(dptr(cw), dptr(ck), dptr(tw), dptr(tk), cw_h.data_ptr(), ck_h.data_ptr())
+    return cams, (cw, ck, tw, tk, cw_h, ck_h)
 
 
 def eval_tables(s_prop: Sequence[int], s_nerf: int, device):

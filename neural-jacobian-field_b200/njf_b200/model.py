@@ -302,7 +302,9 @@ class Model(nn.Module):
             res = render(self.field(), pe.hoisted, Hf, Wf, cams, mv(rendering_input.origins),
                          mv(rendering_input.directions), mv(rendering_input.z_near), mv(rendering_input.z_far),
                          mv(robot_input.robot_action), tuple(r.num_proposal_samples), r.num_nerf_samples,
-                         anneal=self._anneal, **kw)
+                         anneal=self._anneal,
+                         host_near_far=((rendering_input.z_near, rendering_input.z_far)
+                                        if rendering_input.z_near.device.type == "cpu" else None), **kw)
         res._cams = keep
         return res
 

@@ -35,7 +35,8 @@ def render(fld: api.Field, maps: torch.Tensor, Hf: int, Wf: int, cams: api.NjfCa
            s_prop: Sequence[int], s_nerf: int, *, vis: bool = True, per_sample: bool = False,
            sampler_outputs: bool = False, bins0: Optional[torch.Tensor] = None,
            us: Optional[Sequence[torch.Tensor]] = None, anneal: float = 1.0,
-           sum_vec_width: Optional[int] = None, final_bins: Optional[torch.Tensor] = None) -> RenderResult:
+           sum_vec_width: Optional[int] = None, final_bins: Optional[torch.Tensor] = None,
+           host_near_far: Optional[Sequence[torch.Tensor]] = None) -> RenderResult:
     """One fused render of B x R rays.  All tensors live on the field's CUDA device.
 
     ``final_bins`` (B,R,s_nerf+1): skip the proposal levels and render the field at the given
@@ -61,12 +62,17 @@ def render(fld: api.Field, maps: torch.Tensor, Hf: int, Wf: int, cams: api.NjfCa
         a.s_prop[i] = int(s)
     a.origins, a.dirs = api.dptr(origins), api.dptr(dirs)
     a.z_near, a.z_far, a.action = api.dptr(z_near), api.dptr(z_far), api.dptr(action)
+    if host_near_far is not None:  # host copies let the kernels read per-view constants from the constant bank
+        hn, hf = (t.detach().to("cpu", torch.float32).contiguous() for t in host_near_far)
+        a.h_z_near, a.h_z_far = hn.data_ptr(), hf.data_ptr()
     a.bins0 = api.dptr(bins0)
     a.bins0_stride = 0 if bins0.dim() == 1 else bins0.shape[-1]
     a.anneal = float(anneal)
     a.sum_vec_width = api.default_sum_vec_width() if sum_vec_width is None else int(sum_vec_width)
     a.maps, a.Hf, a.Wf = api.dptr(maps), int(Hf), int(Wf)
     keep = [origins, dirs, z_near, z_far, action, bins0, maps] + list(us)
+    if host_near_far is not None:
+        keep += [hn, hf]
     for lvl in range(len(s_prop)):
         n = s_prop[lvl + 1] if lvl + 1 < len(s_prop) else s_nerf
         u = us[lvl]

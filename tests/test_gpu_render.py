@@ -40,7 +40,8 @@ def _run(fx_tuple, **kw):
     Hf, Wf = fx["feat"].shape[-2:]
     g = lambda k: t(k).to(DEV)
     res = render(fld, maps, Hf, Wf, cams, g("origins"), g("dirs"), g("z_near"), g("z_far"), g("action"),
-                 s_prop, s_nerf, vis=True, per_sample=True, sampler_outputs=True, **kw)
+                 s_prop, s_nerf, vis=True, per_sample=True, sampler_outputs=True,
+                 host_near_far=(t("z_near"), t("z_far")), **kw)   # per-view constants via the constant bank
     torch.cuda.synchronize()
     return res
 
