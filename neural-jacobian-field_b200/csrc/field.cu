@@ -39,9 +39,11 @@ struct Builder {
     return it->second.first;
   }
   // append an MMA step whose B image is W[n_real][k_real] (row stride ld)
+  // bias != nullptr: append the [n_pad x 16] SW32 bias block (kStepBias)
   void step(Program& p, const float* w, int n_real, int k_real, int ld, int n_pad, int k_pad, int d_col,
-            int acc, int flags = 0) {
+            int acc, int flags = 0, const float* bias = nullptr, bool want_bias = false) {
     MmaStep st{};
+    if (want_bias) flags |= kStepBias;
     st.flags = static_cast<uint16_t>(flags);
     st.w_off = static_cast<uint32_t>(blob.size());
     st.w_bytes = static_cast<uint32_t>(n_pad * k_pad * 2);
@@ -51,6 +53,12 @@ struct Builder {
     st.d_col = static_cast<uint16_t>(d_col);
     blob.resize(blob.size() + st.w_bytes);
     if (w) pack_sw128_f16(w, n_real, k_real, ld, n_pad, k_pad, blob.data() + st.w_off);
+    if (want_bias) {
+      const size_t off = blob.size();
+      blob.resize(off + static_cast<size_t>(n_pad) * 32);
+      if (bias) pack_sw32_bias_f16(bias, n_real, n_pad, blob.data() + off);
+      st.w_bytes += static_cast<uint32_t>(n_pad * 32);
+    }
     p.steps[p.nsteps++] = st;
   }
 };
@@ -72,32 +80,19 @@ void trunk_lin_in(Builder& b, Program& prog, const std::string& p, TrunkTab& tab
     }
   }
 }
-void trunk_blocks(Builder& b, Program& prog, const std::string& p, int d_out, int n_out_pad, TrunkTab& tab) {
-  const float* b1[5] = {};
+void trunk_blocks(Builder& b, Program& prog, const std::string& p, int d_out, int n_out_pad) {
   for (int k = 0; k < 5; ++k) {
     const std::string q = p + ".blocks." + std::to_string(k);
     const float* w0 = b.get(q + ".fc_0.weight", 128 * 128);
     const float* b0 = b.get(q + ".fc_0.bias", 128);
     const float* w1 = b.get(q + ".fc_1.weight", 128 * 128);
-    b1[k] = b.get(q + ".fc_1.bias", 128);
-    b.step(prog, w0, 128, 128, 128, 128, 128, /*d_col=*/128, 0);
-    b.step(prog, w1, 128, 128, 128, 128, 128, /*d_col=*/0, 1);
-    if (b0) std::memcpy(&tab.bias[(2 * k) * 128], b0, 128 * sizeof(float));
-  }
-  if (b1[0] && b1[1] && b1[2] && b1[3] && b1[4]) {
-    float* T = tab.bias;
-    for (int c = 0; c < 128; ++c) {
-      T[1 * 128 + c] = b1[0][c];                         // added (with tz_1) before block 1
-      T[3 * 128 + c] = b1[1][c];                         // added (with tz_2) before block 2
-      T[5 * 128 + c] = b1[2][c];                         // c3
-      T[7 * 128 + c] = b1[2][c] + b1[3][c];              // c4
-      T[9 * 128 + c] = (b1[2][c] + b1[3][c]) + b1[4][c]; // c5
-    }
+    const float* b1 = b.get(q + ".fc_1.bias", 128);
+    b.step(prog, w0, 128, 128, 128, 128, 128, /*d_col=*/128, 0, 0, b0, true);
+    b.step(prog, w1, 128, 128, 128, 128, 128, /*d_col=*/0, 1, 0, b1, true);  // x += fc_1(.) + b1
   }
   const float* wo = b.get(p + ".lin_out.weight", static_cast<int64_t>(d_out) * 128);
   const float* bo = b.get(p + ".lin_out.bias", d_out);
-  b.step(prog, wo, d_out, 128, 128, n_out_pad, 128, /*d_col=*/128, 0);
-  if (bo) std::memcpy(tab.b_out, bo, d_out * sizeof(float));
+  b.step(prog, wo, d_out, 128, 128, n_out_pad, 128, /*d_col=*/128, 0, 0, bo, true);
 }
 
 }  // namespace
@@ -124,7 +119,7 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
   for (int i = 0; i < desc->n_proposal; ++i) {
     const std::string p = "proposal_networks." + std::to_string(i) + ".density_head";
     trunk_lin_in(b, f->prop_prog[i], p, f->prop_trunk[i]);
-    trunk_blocks(b, f->prop_prog[i], p, 1, 16, f->prop_trunk[i]);
+    trunk_blocks(b, f->prop_prog[i], p, 1, 16);
   }
   Program& fp = f->field_prog;
   // transformer head: lin_in and q_enc read the same A tile (the positional encoding) and are
@@ -190,21 +185,20 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
           }
       }
       b.step(fp, m1.data(), 64, 64, 64, 64, 64, 128, 0);
-      b.step(fp, m2.data(), 64, 64, 64, 64, 64, 128, 0);
-      b.step(fp, w1, 64, 64, 64, 64, 64, 128, 0);
-      b.step(fp, w2, 64, 64, 64, 64, 64, 128, 0);
-      const float* src[7] = {g1, be1, bo, g2, be2, bb1, bb2};
+      b.step(fp, m2.data(), 64, 64, 64, 64, 64, 128, 0, 0, bo, true);
+      b.step(fp, w1, 64, 64, 64, 64, 64, 128, 0, 0, bb1, true);
+      b.step(fp, w2, 64, 64, 64, 64, 64, 128, 0, 0, bb2, true);
+      const float* src[4] = {g1, be1, g2, be2};
       XfLayerTab& T = f->head.layer[l];
-      float* dst[7] = {T.ln1_g, T.ln1_b, T.b_o, T.ln2_g, T.ln2_b, T.b_1, T.b_2};
-      for (int i = 0; i < 7; ++i)
+      float* dst[4] = {T.ln1_g, T.ln1_b, T.ln2_g, T.ln2_b};
+      for (int i = 0; i < 4; ++i)
         if (src[i]) std::memcpy(dst[i], src[i], 64 * sizeof(float));
     }
     const float* wh = b.get("decoder.jacobian_head.weight", static_cast<int64_t>(3 * A) * 64);
     const float* bh = b.get("decoder.jacobian_head.bias", 3 * A);
-    b.step(fp, wh, 3 * A, 64, 64, 32, 64, 128, 0);
-    if (bh) std::memcpy(f->head.b_head, bh, 3 * A * sizeof(float));
+    b.step(fp, wh, 3 * A, 64, 64, 32, 64, 128, 0, 0, bh, true);
   }
-  trunk_blocks(b, fp, "decoder.density_head", 16, 16, f->dens_trunk);
+  trunk_blocks(b, fp, "decoder.density_head", 16, 16);
   {
     const float* w1 = b.get("decoder.color_head.0.weight", 64 * 31);
     const float* b1 = b.get("decoder.color_head.0.bias", 64);
@@ -212,11 +206,9 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
     const float* b2 = b.get("decoder.color_head.2.bias", 64);
     const float* w3 = b.get("decoder.color_head.4.weight", 3 * 64);
     const float* b3 = b.get("decoder.color_head.4.bias", 3);
-    b.step(fp, w1, 64, 31, 31, 64, 64, 128, 0);
-    b.step(fp, w2, 64, 64, 64, 64, 64, 128, 0);
-    if (b1 && b2 && w3 && b3) {
-      std::memcpy(f->color.b1, b1, 64 * 4);
-      std::memcpy(f->color.b2, b2, 64 * 4);
+    b.step(fp, w1, 64, 31, 31, 64, 64, 128, 0, 0, b1, true);
+    b.step(fp, w2, 64, 64, 64, 64, 64, 128, 0, 0, b2, true);
+    if (w3 && b3) {
       std::memcpy(f->color.w3, w3, 192 * 4);
       std::memcpy(f->color.b3, b3, 3 * 4);
     }
@@ -224,7 +216,7 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
   if (desc->head == NJF_HEAD_MLP) {
     f->ch_main = 768;
     trunk_lin_in(b, fp, "decoder.jacobian_head", f->jac_trunk);
-    trunk_blocks(b, fp, "decoder.jacobian_head", 3 * A, 32, f->jac_trunk);
+    trunk_blocks(b, fp, "decoder.jacobian_head", 3 * A, 32);
   }
   if (!b.err.empty()) {
     delete f;

@@ -8,21 +8,19 @@ namespace njf {
 // fp32 side tables.  They travel BY VALUE inside the kernel parameter structs (constant bank:
 // every epilogue access is warp-uniform, so it is a broadcast constant-cache read instead of an
 // L1-thrashed global load).
+// All other biases ride inside the weight images (kStepBias) and are accumulated by the tensor core.
 struct TrunkTab {
   float4 e0[128];       // (W_in[:,60], W_in[:,61], W_in[:,62], b_in): raw-xyz columns kept in fp32
-  float bias[10 * 128]; // b0_0, b1_0, b0_1, b1_1, b0_2, c3, b0_3, c4, b0_4, c5 (c* cumulative fc_1 biases)
-  float b_out[32];      // lin_out bias (zero padded)
 };
 struct XfLayerTab {
-  float ln1_g[64], ln1_b[64], b_o[64], ln2_g[64], ln2_b[64], b_1[64], b_2[64];
+  float ln1_g[64], ln1_b[64], ln2_g[64], ln2_b[64];
 };
 struct HeadTab {
   float4 q_e0[64];      // (Wq[:,60..62], bq)
   XfLayerTab layer[3];
-  float b_head[32];
 };
 struct ColorTab {
-  float b1[64], b2[64], w3[3 * 64], b3[4];
+  float w3[3 * 64], b3[4];   // last colour layer (3 outputs) stays on the fp32 pipes
 };
 
 }  // namespace njf

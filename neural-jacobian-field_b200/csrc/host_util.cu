@@ -32,6 +32,14 @@ void pack_sw128_f16(const float* w, int n_real, int k_real, int ld, int n_pad, i
   }
 }
 
+void pack_sw32_bias_f16(const float* bias, int n_real, int n_pad, uint8_t* out) {
+  std::memset(out, 0, static_cast<size_t>(n_pad) * 32);
+  for (int n = 0; n < n_real; ++n) {
+    const uint16_t b = f32_to_f16_bits(bias[n]);
+    std::memcpy(out + sw32_offset(n, 0), &b, 2);
+  }
+}
+
 }  // namespace njf
 
 extern "C" const char* njf_last_error(void) { return njf::last_error().c_str(); }

@@ -25,7 +25,8 @@ constexpr int kIssuerWarp = 16;
 constexpr int kLoaderWarp = 17;
 constexpr int kThreads = 576;
 constexpr int kStages = 2;
-constexpr uint32_t kStageBytes = 32768;  // up to N=128 x K=128 fp16
+constexpr uint32_t kBiasBlkBytes = 4096; // N<=128 rows x 16 cols fp16 (SW32): column 0 = bias
+constexpr uint32_t kStageBytes = 32768 + kBiasBlkBytes;  // up to N=128 x K=128 fp16 + bias block
 constexpr uint32_t kATileBytes = 32768;  // 128 rows x 128 cols fp16 (2 K-blocks of 16 KB)
 constexpr uint32_t kAKbStride = kRows * 128;  // bytes between K-blocks of an A tile
 constexpr uint32_t kTzBytes = 32768;     // 128 rows x 128 ch fp16 (256 B rows, chunk-swizzled)
@@ -44,6 +45,10 @@ struct MmaStep {
                      // kStepNoCommit: the NEXT step's commit also covers this accumulator
 };
 constexpr uint16_t kStepReuseA = 1, kStepNoCommit = 2;
+// kStepBias: the image is followed by an [N x 16] SW32 block whose column 0 is the layer bias; one
+// extra MMA multiplies it with the CTA's constant "ones" A block (column 0 = 1), so the bias is
+// accumulated by the tensor core and the epilogues carry no bias loads / adds.
+constexpr uint16_t kStepBias = 4;
 struct Program {
   int nsteps;
   MmaStep steps[kMaxSteps];
@@ -54,7 +59,8 @@ struct SmemMap {
   static constexpr uint32_t kA = 0;                                 // 2 x 32 KB
   static constexpr uint32_t kW = kA + kSlots * kATileBytes;         // 2 x 32 KB
   static constexpr uint32_t kTz = kW + kStages * kStageBytes;       // 2 x 32 KB
-  static constexpr uint32_t kMisc = kTz + kSlots * kTzBytes;        // barriers etc.
+  static constexpr uint32_t kOnes = kTz + kSlots * kTzBytes;        // 4 KB constant "ones" A block
+  static constexpr uint32_t kMisc = kOnes + kBiasBlkBytes;          // barriers etc.
   static constexpr uint32_t kMiscBytes = 1024;
   static constexpr uint32_t kScratch = kMisc + kMiscBytes;          // kernel-specific
 };
@@ -92,6 +98,13 @@ __device__ __forceinline__ CtaCtx cta_setup(uint8_t* smem_raw) {
     mbar_fence_init();
   }
   if (warp == kIssuerWarp) tmem_alloc(&c.bars->tmem_base, kTmemCols);
+  if (threadIdx.x < kRows) {  // ones block: element (row, 0) = 1.0, everything else 0
+    uint4* rowp = reinterpret_cast<uint4*>(c.smem + SmemMap::kOnes + threadIdx.x * 32);
+    rowp[0] = make_uint4(0, 0, 0, 0);
+    rowp[1] = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint16_t*>(c.smem + SmemMap::kOnes + sw32_offset(threadIdx.x, 0)) = 0x3C00;  // 1.0h
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -156,6 +169,9 @@ __device__ __forceinline__ void issuer_role(const CtaCtx& c, const Program& prog
             acc = 1;
           }
         }
+        if (st.flags & kStepBias)
+          umma_f16(d_tmem, make_sw32_desc(smem_u32(c.smem + SmemMap::kOnes)),
+                   make_sw32_desc(w0 + st.kblocks * w_kb_stride), idesc, 1);
         if (!(st.flags & kStepNoCommit)) umma_commit(&c.bars->acc_ready[slot]);
       }
       umma_commit(&c.bars->w_empty[stage]);
@@ -267,40 +283,25 @@ __device__ __forceinline__ uint32_t tz_offset(int row, int chunk) {
   return row * 256 + ((chunk ^ (row & 7)) << 4);
 }
 
-// acc[c0..c0+32) of this slot (+ bias) -> ReLU -> fp16 -> A tile.  `col` = TMEM column of c0.
-__device__ __forceinline__ void epi_relu_to_a(const EpiCtx& e, int tcol, int c0,
-                                              const float* __restrict__ bias) {
+// acc[c0..c0+32) of this slot (bias already accumulated by the tensor core) -> ReLU -> fp16 -> A tile.
+// `tcol` = TMEM column of c0.
+__device__ __forceinline__ void epi_relu_to_a(const EpiCtx& e, int tcol, int c0) {
   uint32_t r[32];
   tmem_ld32(e.tmem + tcol, r);
   tmem_ld_wait();
   uint32_t p[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float2 s0 = fadd2(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])),
-                            make_float2(bias[c0 + 2 * j], bias[c0 + 2 * j + 1]));
-    p[j] = pack_relu_f16x2(s0.x, s0.y);
-  }
+  for (int j = 0; j < 16; ++j) p[j] = pack_relu_f16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
   a_store32(e, c0, p);
 }
 
-// x[c0..c0+32) += tz_staging[row][c0..] + bias ; write the sum back to TMEM (so later
-// accumulating MMAs see it) ; ReLU -> fp16 -> A tile.  `extra` (optional, per-thread
-// fp32[32]) is added as well (raw-xyz columns of lin_in kept in fp32).
-template <bool kHasTz, bool kHasExtra>
-__device__ __forceinline__ void epi_x_update(const EpiCtx& e, int c0,
-                                             const float* __restrict__ bias,
-                                             const float* extra) {
+// x[c0..c0+32) (+= tz_staging[row][c0..], written back to TMEM so later accumulating MMAs see it)
+// -> ReLU -> fp16 -> A tile.  Biases are accumulated by the tensor core (kStepBias).
+template <bool kHasTz>
+__device__ __forceinline__ void epi_x_update(const EpiCtx& e, int c0) {
   uint32_t r[32];
   tmem_ld32(e.tmem + c0, r);
   tmem_ld_wait();
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float2 s0 = fadd2(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])),
-                            make_float2(bias[c0 + 2 * j], bias[c0 + 2 * j + 1]));
-    v[2 * j] = s0.x;
-    v[2 * j + 1] = s0.y;
-  }
   if (kHasTz) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -308,27 +309,19 @@ __device__ __forceinline__ void epi_x_update(const EpiCtx& e, int c0,
       const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float2 s = fadd2(make_float2(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]), __half22float2(h[t]));
-        v[8 * j + 2 * t] = s.x;
-        v[8 * j + 2 * t + 1] = s.y;
+        const float2 s = fadd2(make_float2(__uint_as_float(r[8 * j + 2 * t]), __uint_as_float(r[8 * j + 2 * t + 1])),
+                               __half22float2(h[t]));
+        r[8 * j + 2 * t] = __float_as_uint(s.x);
+        r[8 * j + 2 * t + 1] = __float_as_uint(s.y);
       }
     }
-  }
-  if (kHasExtra) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += extra[j];
-  }
-  if (kHasTz || kHasExtra) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
     tmem_st32(e.tmem + c0, r);
   }
   uint32_t p[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    p[j] = pack_relu_f16x2(v[2 * j], v[2 * j + 1]);
+  for (int j = 0; j < 16; ++j) p[j] = pack_relu_f16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
   a_store32(e, c0, p);
-  if (kHasTz || kHasExtra) tmem_st_wait();
+  if (kHasTz) tmem_st_wait();
 }
 
 }  // namespace njf

@@ -34,6 +34,9 @@ std::string& last_error();
 void pack_sw128_f16(const float* w, int n_real, int k_real, int ld, int n_pad, int k_pad,
                     uint8_t* out);
 
+// [n_pad x 16] fp16 SWIZZLE_32B block whose column 0 holds bias[0..n_real) (kStepBias); n_pad*32 bytes
+void pack_sw32_bias_f16(const float* bias, int n_real, int n_pad, uint8_t* out);
+
 uint16_t f32_to_f16_bits(float f);
 
 }  // namespace njf

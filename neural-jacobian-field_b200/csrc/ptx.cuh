@@ -112,6 +112,17 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return d;
 }
 
+// K-major operand block of 16 columns (32 B rows), SWIZZLE_32B, 8-row atoms of 256 B (SBO).
+__device__ __forceinline__ uint64_t make_sw32_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;           // SBO = 256 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;                  // layout: SWIZZLE_32B
+  return d;
+}
+
 // Instruction descriptor, kind::f16: A,B = fp16 (K-major), D = fp32, M = 128.
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t n) {
   return (1u << 4)            // D format: f32
@@ -227,6 +238,13 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t
                                                           uint32_t kb_stride) {
   const uint32_t kb = col >> 6, c = (col & 63) >> 3, e = col & 7;
   return kb * kb_stride + row * 128u + (((c ^ (row & 7u)) << 4) | (e << 1));
+}
+
+// byte offset of element (row, col<16) in a [rows x 16] fp16 K-major SWIZZLE_32B block
+// (Swizzle<1,4,3>: the 16 B chunk index is XORed with address bit 7 = (row >> 2) & 1)
+__host__ __device__ __forceinline__ uint32_t sw32_offset(uint32_t row, uint32_t col) {
+  const uint32_t c = col >> 3, e = col & 7;
+  return row * 32u + (((c ^ ((row >> 2) & 1u)) << 4) | (e << 1));
 }
 
 }  // namespace njf

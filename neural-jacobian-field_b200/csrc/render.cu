@@ -16,8 +16,6 @@ struct SlotScratch {
   float dd[kRows];       // delta * sigma of the current tile
   float cum[kRows];      // exclusive prefix sums (fp32) of dd
   float wrow[kRows];     // transmittance weight of each row (shared between the row's two threads)
-  float wts[528];        // transmittance weights of the ray group (proposal: PDF input)
-  float cdf[544];        // PDF scratch
   TapEntry taps[kRows];  // bilinear taps of the current tile
   float2 xch[kRows][2];  // per-row exchange between the two column-half threads (LayerNorm sums)
   float4 rgbp[kRows];    // colour-head partial dot products of the upper column half
@@ -74,10 +72,9 @@ struct ProposalParams {
   float anneal;
   int sum_vec;
   float* bins_out;       // [NR][n_out+1]
-  float* weights_out;    // [NR][S] (required when the PDF step runs as its own kernel)
+  float* weights_out;    // [NR][S]: input of the PDF step, which runs as its own kernel afterwards (one warp
+                         // per ray, fully parallel -- in here a single warp per tile would do it while seven wait)
   int32_t* inds_out;     // optional [NR][n_out+1]
-  int fused_pdf;         // 1: resample inside this kernel; 0: pdf_kernel runs afterwards (one warp per ray,
-                         //    fully parallel -- in here a single warp per tile would do it while seven wait)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_constant__ ProposalParams p) {
@@ -127,29 +124,12 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
           tmem_ld16(e.tmem + 128, r);
           tmem_ld_wait();
           // density = trunc_exp(x - 1) (density_decoder.py:64-66, activations.py:32-35)
-          const float sigma = expf(__fsub_rn(__uint_as_float(r[0]) + p.trunk.b_out[0], 1.f));
+          const float sigma = expf(__fsub_rn(__uint_as_float(r[0]), 1.f));
           dd = (rs.ray >= 0 && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
         }
         const float w = tile_weights(e, sc, g, tile, dd, carry);
-        if (e.half == 0 && rs.ray >= 0) {
-          if (p.fused_pdf) sc->wts[g.T == 1 ? e.row : rs.s] = w;
-          if (p.weights_out) p.weights_out[static_cast<size_t>(rs.ray) * g.S + rs.s] = w;
-        }
+        if (e.half == 0 && rs.ray >= 0) p.weights_out[static_cast<size_t>(rs.ray) * g.S + rs.s] = w;
       }
-      if (!p.fused_pdf) continue;
-      slot_bar(e);
-      PROF(e, kPBar);
-      for (int lr = w8; lr < g.G; lr += 8) {
-        const int ray = group * g.G + lr;
-        if (ray >= g.NR) break;
-        pdf_resample_warp(sc->wts + lr * g.S, g.S, g.bins + static_cast<size_t>(ray) * g.bins_stride,
-                          p.u + static_cast<size_t>(ray) * p.u_stride, nb, p.anneal, p.sum_vec,
-                          sc->cdf + lr * (g.S + 1), p.bins_out + static_cast<size_t>(ray) * nb,
-                          p.inds_out ? p.inds_out + static_cast<size_t>(ray) * nb : nullptr);
-      }
-      PROF(e, kPPdf);
-      slot_bar(e);
-      PROF(e, kPBar);
     }
     prof_flush(e);
   }
@@ -317,7 +297,6 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
     {
       float t[32];
       ld_acc32(e, t);
-      add_vec32(e, t, L.b_o);
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] += t[j];
     }
@@ -329,7 +308,6 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
     {
       float t[32];
       ld_acc32(e, t);
-      add_vec32(e, t, L.b_1);
 #pragma unroll
       for (int j = 0; j < 32; ++j) t[j] = gelu_erf(t[j]);
       store32_to_a(e, t);
@@ -340,7 +318,6 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
     {
       float t[32];
       ld_acc32(e, t);
-      add_vec32(e, t, L.b_2);
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] += t[j];
     }
@@ -353,7 +330,7 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
   tmem_ld16(e.tmem + 128 + 16 * e.half, r);
   tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < 16; ++j) J[j] = __uint_as_float(r[j]) + H.b_head[16 * e.half + j];
+  for (int j = 0; j < 16; ++j) J[j] = __uint_as_float(r[j]);
 }
 
 // SH degree 4 (tiny-cuda-nn convention) of the unit direction (action_decoder_jacobian.py:194-199)
@@ -448,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           tmem_ld16(e.tmem + 128, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) geo[j] = __uint_as_float(r[j]) + p.dens.b_out[j];
+          for (int j = 0; j < 16; ++j) geo[j] = __uint_as_float(r[j]);
           sigma = expf(__fsub_rn(geo[15], 1.f));
           if (p.geo_out && valid) {
             float* gp = p.geo_out + (static_cast<size_t>(rs.ray) * g.S + rs.s) * 15;
@@ -476,14 +453,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         }
         epi_publish(e);  // -> color1
         epi_wait_acc(e);
-        epi_relu_to_a(e, 128 + 32 * e.half, 32 * e.half, p.color.b1);
+        epi_relu_to_a(e, 128 + 32 * e.half, 32 * e.half);
         epi_publish(e);  // -> color2
         epi_wait_acc(e);
         float rgb[3] = {0.f, 0.f, 0.f};
         {
           float h2[32];
           ld_acc32(e, h2);
-          add_vec32(e, h2, p.color.b2);
           float part[3];
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
@@ -514,7 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           tmem_ld16(e.tmem + 128 + 16 * e.half, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) J[j] = __uint_as_float(r[j]) + p.jac.b_out[16 * e.half + j];
+          for (int j = 0; j < 16; ++j) J[j] = __uint_as_float(r[j]);
         }
         // ---- weights + compositing (model.py:351-367, 384-394)
         const float dd = (valid && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
@@ -979,8 +955,7 @@ extern "C" int njf_proposal_pass(const NjfField* f, const NjfCameras* cams, cons
   p.bins_out = a->level_bins[level];
   p.weights_out = a->prop_weights[level];
   p.inds_out = a->level_inds[level];
-  p.fused_pdf = getenv("NJF_FUSED_PDF") ? 1 : 0;
-  if (!p.fused_pdf && !p.weights_out) {
+  if (!p.weights_out) {
     // transmittance weights travel through a grow-only scratch buffer owned by the field
     const size_t need = static_cast<size_t>(p.g.NR) * p.g.S * sizeof(float);
     if (f->scratch_bytes < need) {
@@ -997,10 +972,8 @@ extern "C" int njf_proposal_pass(const NjfField* f, const NjfCameras* cams, cons
   const int grid = nitems < num_sms() ? nitems : num_sms();
   proposal_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
   NJF_CUDA(cudaGetLastError());
-  if (!p.fused_pdf)
-    return njf_pdf_sample(p.weights_out, bins_in, bins_in_stride, p.u, p.u_stride, p.g.NR, p.g.S, p.n_out, p.anneal,
-                          p.sum_vec, p.bins_out, p.inds_out, stream_);
-  return 0;
+  return njf_pdf_sample(p.weights_out, bins_in, bins_in_stride, p.u, p.u_stride, p.g.NR, p.g.S, p.n_out, p.anneal,
+                        p.sum_vec, p.bins_out, p.inds_out, stream_);
 }
 
 extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a, const float* bins,

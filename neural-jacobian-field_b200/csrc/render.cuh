@@ -307,15 +307,14 @@ __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom&
     if (k < 2) gather_segment<128>(e, g, taps, seg_ch0 + 128 * (k + 1));
     PROF(e, kPEpi);
     epi_wait_acc(e);
-    for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_relu_to_a(e, 128 + c0, c0, tab.bias + (2 * k) * 128);
+    for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_relu_to_a(e, 128 + c0, c0);
     epi_publish(e);  // -> fc_1 (block k), accumulates onto x
     PROF(e, kPEpi);
     epi_wait_acc(e);
-    const float* bn = tab.bias + (2 * k + 1) * 128;
     if (k < 2) {
-      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<true, false>(e, c0, bn, nullptr);
+      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<true>(e, c0);
     } else {
-      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<false, false>(e, c0, bn, nullptr);
+      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<false>(e, c0);
     }
     epi_publish(e);  // -> fc_0 (block k+1) or lin_out
   }

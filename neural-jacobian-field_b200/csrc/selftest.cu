@@ -12,7 +12,7 @@ namespace njf {
 struct SelftestParams {
   Program prog;
   const uint8_t* blob;   // packed weight images (4 layers)
-  const float* bias;     // [3][128] biases for the three ReLU epilogues
+  const float* bias;     // unused by the kernel (biases ride in the weight images)
   const float* a_in;     // [ntiles*128][64]  fp32 inputs (rounded to fp16 in-kernel)
   const float* tz_in;    // [ntiles*128][128] fp32 "gathered" term (rounded to fp16)
   float* x_out;          // [ntiles*128][128]
@@ -68,10 +68,10 @@ __global__ void __launch_bounds__(kThreads, 1) selftest_kernel(const __grid_cons
         pair_bar(e);
       }
       epi_wait_acc(e);
-      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<true, false>(e, c0, p.bias, nullptr);
+      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<true>(e, c0);
       epi_publish(e);  // step 1: net = relu(x) * W1^T
       epi_wait_acc(e);
-      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_relu_to_a(e, 128 + c0, c0, p.bias + 128);
+      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_relu_to_a(e, 128 + c0, c0);
       epi_publish(e);  // step 2: x += relu(net) * W2^T
       epi_wait_acc(e);
       for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) {
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, 1) selftest_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r[j]);
       }
-      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_relu_to_a(e, c0, c0, p.bias + 256);
+      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_relu_to_a(e, c0, c0);
       epi_publish(e);  // step 3: y = relu(x) * W3^T (N=16)
       epi_wait_acc(e);
       if (e.half == 0) {
@@ -112,7 +112,9 @@ extern "C" int njf_selftest_chain(const float* w0, const float* w1, const float*
   // inputs are HOST pointers for the weights/bias, DEVICE pointers for a_in/tz_in/x_out/y_out
   SelftestParams p{};
   std::vector<uint8_t> blob;
-  auto add = [&](const float* w, int n_real, int k_real, int n_pad, int k_pad, int d_col, int acc) {
+  // step s carries bias row `bias + 128*(s)` through the tensor core (kStepBias), the way the
+  // render kernels do: x = a W0^T + b0 ; v = x + tz ; net = relu(v) W1^T + b1 ; x += relu(net) W2^T + b2
+  auto add = [&](const float* w, const float* b, int n_real, int k_real, int n_pad, int k_pad, int d_col, int acc) {
     MmaStep st{};
     st.w_off = static_cast<uint32_t>(blob.size());
     st.w_bytes = static_cast<uint32_t>(n_pad * k_pad * 2);
@@ -122,12 +124,19 @@ extern "C" int njf_selftest_chain(const float* w0, const float* w1, const float*
     st.d_col = static_cast<uint16_t>(d_col);
     blob.resize(blob.size() + st.w_bytes);
     pack_sw128_f16(w, n_real, k_real, k_real, n_pad, k_pad, blob.data() + st.w_off);
+    if (b) {
+      st.flags |= kStepBias;
+      const size_t off = blob.size();
+      blob.resize(off + static_cast<size_t>(n_pad) * 32);
+      pack_sw32_bias_f16(b, n_real, n_pad, blob.data() + off);
+      st.w_bytes += static_cast<uint32_t>(n_pad * 32);
+    }
     p.prog.steps[p.prog.nsteps++] = st;
   };
-  add(w0, 128, 64, 128, 64, 0, 0);
-  add(w1, 128, 128, 128, 128, 128, 0);
-  add(w2, 128, 128, 128, 128, 0, 1);
-  add(w3, 16, 128, 16, 128, 128, 0);
+  add(w0, bias, 128, 64, 128, 64, 0, 0);
+  add(w1, bias + 128, 128, 128, 128, 128, 128, 0);
+  add(w2, bias + 256, 128, 128, 128, 128, 0, 1);
+  add(w3, nullptr, 16, 128, 16, 128, 128, 0);
   uint8_t* d_blob = nullptr;
   float* d_bias = nullptr;
   NJF_CUDA(cudaMalloc(&d_blob, blob.size()));

