@@ -163,7 +163,7 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nrays = 512
+    nrays = int(os.environ.get("NJF_BENCH_REF_RAYS", "512"))
     rps, dt, _ = oracle_rays_per_s(nrays, args.steps, min(args.warmup, 1))
     cores = torch.get_num_threads()
     line = {

@@ -105,7 +105,6 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
     for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
       const int group = 2 * it + e.slot;
       if (group >= g.NG) continue;
-      double carry = 0.0;
       for (int tile = 0; tile < g.T; ++tile) {
         RowState rs;
         PROF(e, kPOther);
@@ -127,8 +126,10 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
           const float sigma = expf(__fsub_rn(__uint_as_float(r[0]), 1.f));
           dd = (rs.ray >= 0 && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
         }
-        const float w = tile_weights(e, sc, g, tile, dd, carry);
-        if (e.half == 0 && rs.ray >= 0) p.weights_out[static_cast<size_t>(rs.ray) * g.S + rs.s] = w;
+        // delta*sigma goes out; the per-ray kernel that follows does the transmittance scan
+        // (RaySamples.get_weights) and the PDF resampling with one warp per ray
+        if (e.half == 0 && rs.ray >= 0) p.weights_out[static_cast<size_t>(rs.ray) * g.S + rs.s] = dd;
+        PROF(e, kPWeights);
       }
     }
     prof_flush(e);
@@ -731,17 +732,30 @@ __global__ void __launch_bounds__(256) hoist_kernel(const float* __restrict__ fe
 }
 
 // standalone PDFSampler: one warp per ray
-__global__ void pdf_kernel(const float* weights, const float* bins_in, int bins_stride, const float* u, int u_stride,
-                           int n_rays, int S, int n_out, float anneal, int sum_vec, float* bins_out,
-                           int32_t* inds_out) {
+// `from_dd` != 0: the input holds delta*sigma; the warp first turns it into transmittance weights
+// (RaySamples.get_weights, ray_samplers.py:77-101) and, if `weights_io` is writable, stores them back.
+__global__ void pdf_kernel(float* weights_io, int from_dd, int store_weights, const float* bins_in, int bins_stride,
+                           const float* u, int u_stride, int n_rays, int S, int n_out, float anneal, int sum_vec,
+                           float* bins_out, int32_t* inds_out) {
   extern __shared__ float sm[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ray = blockIdx.x * (blockDim.x >> 5) + wib;
   float* w = sm + wib * (2 * S + 8);
   float* cdf = w + S;
   if (ray >= n_rays) return;
-  for (int j = lane; j < S; j += 32) w[j] = weights[static_cast<size_t>(ray) * S + j];
+  for (int j = lane; j < S; j += 32) w[j] = weights_io[static_cast<size_t>(ray) * S + j];
   __syncwarp();
+  if (from_dd) {
+    double carry = 0.0;
+    excl_scan_warp(w, S, carry, cdf);
+    __syncwarp();
+    for (int j = lane; j < S; j += 32) {
+      const float wt = (1.f - expf(-w[j])) * expf(-cdf[j]);
+      w[j] = wt;
+      if (store_weights) weights_io[static_cast<size_t>(ray) * S + j] = wt;
+    }
+    __syncwarp();
+  }
   const int nb = n_out + 1;
   pdf_resample_warp(w, S, bins_in + static_cast<size_t>(ray) * bins_stride, u + static_cast<size_t>(ray) * u_stride,
                     nb, anneal, sum_vec, cdf, bins_out + static_cast<size_t>(ray) * nb,
@@ -972,8 +986,15 @@ extern "C" int njf_proposal_pass(const NjfField* f, const NjfCameras* cams, cons
   const int grid = nitems < num_sms() ? nitems : num_sms();
   proposal_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
   NJF_CUDA(cudaGetLastError());
-  return njf_pdf_sample(p.weights_out, bins_in, bins_in_stride, p.u, p.u_stride, p.g.NR, p.g.S, p.n_out, p.anneal,
-                        p.sum_vec, p.bins_out, p.inds_out, stream_);
+  {
+    const int wpb = 4;
+    const size_t smem = static_cast<size_t>(wpb) * (2 * p.g.S + 8) * sizeof(float);
+    pdf_kernel<<<(p.g.NR + wpb - 1) / wpb, wpb * 32, smem, stream>>>(
+        p.weights_out, /*from_dd=*/1, /*store_weights=*/a->prop_weights[level] != nullptr, bins_in, bins_in_stride, p.u,
+        p.u_stride, p.g.NR, p.g.S, p.n_out, p.anneal, p.sum_vec, p.bins_out, p.inds_out);
+    NJF_CUDA(cudaGetLastError());
+  }
+  return 0;
 }
 
 extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a, const float* bins,
@@ -1108,9 +1129,9 @@ extern "C" int njf_pdf_sample(const float* weights, const float* bins_in, int bi
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int wpb = 4;
   const size_t smem = static_cast<size_t>(wpb) * (2 * s_in + 8) * sizeof(float);
-  pdf_kernel<<<(n_rays + wpb - 1) / wpb, wpb * 32, smem, stream>>>(weights, bins_in, bins_in_stride, u, u_stride,
-                                                                 n_rays, s_in, n_out, anneal, sum_vec_width,
-                                                                 bins_out, inds_out);
+  pdf_kernel<<<(n_rays + wpb - 1) / wpb, wpb * 32, smem, stream>>>(const_cast<float*>(weights), 0, 0, bins_in,
+                                                                 bins_in_stride, u, u_stride, n_rays, s_in, n_out,
+                                                                 anneal, sum_vec_width, bins_out, inds_out);
   NJF_CUDA(cudaGetLastError());
   return 0;
 }
