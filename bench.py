@@ -163,7 +163,7 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nrays = int(os.environ.get("NJF_BENCH_REF_RAYS", "512"))
+    nrays = int(os.environ.get("NJF_BENCH_REF_RAYS", "256"))
     rps, dt, _ = oracle_rays_per_s(nrays, args.steps, min(args.warmup, 1))
     cores = torch.get_num_threads()
     line = {
@@ -364,7 +364,7 @@ def main():
     }
     if not args.no_cpu_baseline:
         # bounded CPU sample of the same workload + quality vs the oracle on those rays
-        nrays = 512
+        nrays = 256
         rps, dt, (ofeat, idx, oref) = oracle_rays_per_s(nrays, 1, 0, want_outputs=True)
         from njf_b200.render import render
         m2 = fld.hoist(ofeat.to(dev))
