@@ -1,0 +1,102 @@
+"""The host mirror end to end on a GPU: njf_b200.Model (encoder + fused render) against the oracle,
+through the same calls the reference's notebooks make (forward, patch_render, encode_image,
+infer_optical_flow with autograd w.r.t. the action, compute_density)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(head, A, s_prop, s_nerf):
+    from njf_b200 import model as M, modules as mod
+
+    mlp = mod.MlpCfg()
+    dec = (mod.ActionDecoderJacobianTransformerCfg(name=head, mlp=mlp, transformer=mod.TransformerCfg())
+           if head == "jacobian_transformer" else mod.ActionDecoderJacobianMlpCfg(name=head, mlp=mlp))
+    cfg = M.ModelCfg(action_dim=A, rendering=M.RenderingCfg(tuple(s_prop), s_nerf), encoder=mod.EncoderResnetCfg(),
+                     density_decoder=mod.DensityDecoderMlpCfg("density_mlp", mlp), action_decoder=dec)
+    m = M.Model(cfg).eval()
+    sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 31)
+    m.load_state_dict(sd)
+    return m.to(DEV), sd
+
+
+def _scene(A, H=24, W=32, rh=10, rw=12):
+    g = torch.Generator().manual_seed(8)
+    img = torch.rand(1, 3, H, W, generator=g)
+    K = synth.normalized_intrinsics(**synth.ALLEGRO_INTRINSICS_PX)[None]
+    kpx = K.clone(); kpx[:, 0] *= 640; kpx[:, 1] *= 480
+    ctxt, trgt = torch.eye(4)[None], synth.relative_target_pose(1)[None]
+    o, d = synth.world_rays(synth.pixel_grid(rh, rw), K[0], trgt[0])
+    return dict(img=img, K=K, kpx=kpx, ctxt=ctxt, trgt=trgt, o=o[None], d=d[None], zn=torch.tensor([0.5]),
+                zf=torch.tensor([3.0]), act=0.1 * torch.randn(1, A, generator=g))
+
+
+@pytest.mark.parametrize("head,A", [("jacobian_transformer", 8), ("jacobian_mlp", 6)])
+def test_model_api_matches_oracle(head, A):
+    from njf_b200.model import CameraInput, RenderingInput, RobotInput
+
+    s_prop, s_nerf = (32,), 32
+    m, sd = _model(head, A, s_prop, s_nerf)
+    sc = _scene(A)
+    cam = CameraInput(sc["img"], sc["ctxt"], sc["K"], sc["trgt"], sc["kpx"])      # HOST tensors in
+    rin = RenderingInput(sc["o"], sc["d"], sc["zn"], sc["zf"])
+    with torch.no_grad():
+        out = m.forward(cam, rin, RobotInput(sc["act"]), compute_vis_features=True)
+        feat = O.encoder_resnet34(sd, sc["img"])
+        ref = O.render_forward(sd, O.FieldSpec(head, A), feat, sc["ctxt"], sc["K"], sc["trgt"], sc["kpx"], sc["o"], sc["d"],
+                               sc["zn"], sc["zf"], sc["act"], s_prop, s_nerf)
+    so, vo = out.standard_output, out.vis_output
+    assert so.rgb.device.type == "cpu"          # results come back where the inputs lived
+    np.testing.assert_allclose(so.rgb.numpy(), ref["rgb"].numpy(), atol=4e-3)
+    np.testing.assert_allclose(so.depth.numpy(), ref["depth"].numpy(), atol=5e-3)
+    jm = float(ref["action_features"].abs().max())
+    np.testing.assert_allclose(vo.action_features.numpy(), ref["action_features"].numpy(), atol=4e-2 * jm)
+    fm = float(ref["optical_flow"].abs().max())
+    np.testing.assert_allclose(so.optical_flow.numpy(), ref["optical_flow"].numpy(), atol=4e-2 * fm + 0.1)
+    assert vo.weights.shape == (1, 120, s_nerf) and vo.steps.shape == (1, 120, s_nerf)
+
+    # patch_render: same pixels, reshaped to the frame; the encoder runs once
+    pr = m.patch_render(cam, rin, RobotInput(sc["act"]), patch_size=50, render_height=10, render_width=12)
+    assert pr.rgb.shape == (1, 10, 12, 3) and pr.action_features.shape == (1, 10, 12, 3 * A)
+    assert pr.depth_rgb.shape == (1, 10, 12, 3) and pr.flow_rgb.shape == (1, 10, 12, 3)
+    np.testing.assert_allclose(pr.rgb.reshape(1, 120, 3).cpu().numpy(), ref["rgb"].numpy(), atol=4e-3)
+
+    # inverse dynamics: encode once, then differentiate the flow w.r.t. the action
+    enc = m.encode_image(cam, rin, RobotInput(sc["act"]))
+    assert enc.density.shape == (1, 120, s_nerf, 1) and enc.action_features.shape == (1, 120, s_nerf, 3 * A)
+    act = torch.nn.Parameter((0.5 * sc["act"] + 0.02).to(DEV))
+    flow = m.infer_optical_flow(enc, cam, RobotInput(act))
+    loss = torch.nn.functional.smooth_l1_loss(flow, torch.zeros_like(flow))
+    loss.backward()
+    a_ref = torch.nn.Parameter(act.detach().cpu().clone())
+    flow_ref = O.infer_optical_flow(enc.action_features.cpu(), enc.weights.cpu(), enc.ray_samples_positions.cpu(), a_ref,
+                                    sc["trgt"], sc["kpx"])
+    torch.nn.functional.smooth_l1_loss(flow_ref, torch.zeros_like(flow_ref)).backward()
+    np.testing.assert_allclose(flow.detach().cpu().numpy(), flow_ref.detach().numpy(), atol=2e-2 * float(flow_ref.abs().max()) + 1e-3)
+    np.testing.assert_allclose(act.grad.cpu().numpy(), a_ref.grad.numpy(), rtol=5e-2, atol=1e-3 * float(a_ref.grad.abs().max()) + 1e-6)
+
+    # point queries
+    pe = m.compute_pixel_encoding(cam, rin, RobotInput(sc["act"]))
+    pts = torch.rand(1, 50, 3) * torch.tensor([1.0, 0.8, 2.0]) + torch.tensor([-0.5, -0.4, 0.6])
+    dho, extras = m.compute_density(pts, pe)
+    with torch.no_grad():
+        sig, geo, jac, z, encf = O.field_heads(sd, pts, feat, sc["ctxt"], sc["K"], O.FieldSpec(head, A))
+    np.testing.assert_allclose(dho.density.cpu().numpy(), sig.numpy(), rtol=3e-2, atol=2e-3)
+    np.testing.assert_allclose(extras["jacobian_head_output"].cpu().numpy(), jac.numpy(), atol=3e-2 * float(jac.abs().max()))
+    np.testing.assert_allclose(dho.xyz_features.cpu().numpy(), encf.numpy(), atol=2e-5)
+
+
+def test_training_mode_is_rejected_loudly():
+    m, _ = _model("jacobian_transformer", 8, (16,), 16)
+    from njf_b200.model import CameraInput, RenderingInput, RobotInput
+
+    sc = _scene(8)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.forward(CameraInput(sc["img"], sc["ctxt"], sc["K"], sc["trgt"], sc["kpx"]),
+                  RenderingInput(sc["o"], sc["d"], sc["zn"], sc["zf"]), RobotInput(sc["act"]))

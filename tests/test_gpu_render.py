@@ -225,3 +225,97 @@ def test_compute_density_point_queries():
     np.testing.assert_allclose(j_d.cpu().numpy(), jac.numpy(), atol=2e-2 * float(jac.abs().max()), rtol=0)
     np.testing.assert_allclose(x_d.cpu().numpy(), enc.numpy(), atol=2e-5, rtol=0)
     np.testing.assert_allclose(p_d.cpu().numpy(), z.numpy(), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("R,s_prop,s_nerf", [(1, (37,), 53), (7, (24,), 8), (129, (130,), 129), (33, (512,), 300)])
+def test_ragged_sizes_vs_oracle(R, s_prop, s_nerf):
+    """Ragged shapes: a single ray, ray counts that do not fill a tile, sample counts that are not
+    powers of two / not multiples of the tile, and rays longer than one tile (S > 128)."""
+    from njf_b200 import api
+    from njf_b200.render import render
+
+    head, A = "jacobian_transformer", 8
+    g = torch.Generator().manual_seed(R)
+    w = synth.synth_state_dict(synth.field_shapes(head, A), 21)
+    feat = torch.randn(1, 512, 10, 14, generator=g).abs() * 0.7
+    K = synth.normalized_intrinsics(**synth.ALLEGRO_INTRINSICS_PX)[None]
+    kpx = K.clone(); kpx[:, 0] *= 640; kpx[:, 1] *= 480
+    ctxt, trgt = torch.eye(4)[None], synth.relative_target_pose(2)[None]
+    o, d = synth.world_rays(torch.rand(R, 2, generator=g), K[0], trgt[0])
+    o, d = o[None], d[None]
+    zn, zf = torch.tensor([0.4]), torch.tensor([2.5])
+    act = 0.1 * torch.randn(1, A, generator=g)
+    with torch.no_grad():
+        ref = O.render_forward(w, O.FieldSpec(head, A), feat, ctxt, K, trgt, kpx, o, d, zn, zf, act, s_prop, s_nerf)
+    ref = {k: v.numpy() for k, v in ref.items()}
+    fld, maps = _field_and_maps(head, A, s_prop, w, feat)
+    cams, keep = api.make_cameras(ctxt, K, trgt, kpx, DEV)
+    st = render(fld, maps, 10, 14, cams, o.to(DEV), d.to(DEV), zn.to(DEV), zf.to(DEV), act.to(DEV), s_prop, s_nerf,
+                per_sample=True, final_bins=torch.from_numpy(ref["final_bins"]).to(DEV))
+    torch.cuda.synchronize()
+    _check_samples(st, ref, 2.1)
+    _check_composites(st, ref, 2.1)
+    full = render(fld, maps, 10, 14, cams, o.to(DEV), d.to(DEV), zn.to(DEV), zf.to(DEV), act.to(DEV), s_prop, s_nerf)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(full.level_bins[-1].cpu().numpy(), ref["final_bins"], atol=3e-3, rtol=0)
+    _check_composites(full, ref, 2.1, loose=2.5)
+
+
+def test_full_size_properties():
+    """BASELINE.json's full size (400x400 rays, 128+128 samples): size-independent properties.
+    bins sorted in [0,1]; weights >= 0 with sum <= 1; depth inside [near, far]; flow linear in the action
+    (Jbar and p do not depend on it, pw - p doubles); results of a ray do not depend on which other rays
+    are rendered with it (ray-shard invariance, bit-exact) except the call-global depth clip."""
+    from njf_b200 import api
+    from njf_b200.render import render
+
+    head, A, s_prop, s_nerf = "jacobian_transformer", 8, (128,), 128
+    H = W = 400
+    g = torch.Generator().manual_seed(42)
+    w = synth.synth_state_dict(synth.field_shapes(head, A), 11)
+    feat = torch.randn(1, 512, 60, 80, generator=g).abs() * 0.7
+    K = synth.normalized_intrinsics(**synth.ALLEGRO_INTRINSICS_PX)[None]
+    kpx = K.clone(); kpx[:, 0] *= 640; kpx[:, 1] *= 480
+    ctxt, trgt = torch.eye(4)[None], synth.relative_target_pose(1)[None]
+    o, d = synth.world_rays(synth.pixel_grid(H, W), K[0], trgt[0])
+    o, d = o[None].to(DEV), d[None].to(DEV)
+    zn, zf = torch.tensor([0.65], device=DEV), torch.tensor([3.2], device=DEV)
+    act = (0.1 * torch.randn(1, A, generator=g)).to(DEV)
+    fld, maps = _field_and_maps(head, A, s_prop, w, feat)
+    cams, keep = api.make_cameras(ctxt, K, trgt, kpx, DEV)
+    r1 = render(fld, maps, 60, 80, cams, o, d, zn, zf, act, s_prop, s_nerf, vis=True)
+    r2 = render(fld, maps, 60, 80, cams, o, d, zn, zf, 2.0 * act, s_prop, s_nerf, vis=False)
+    n_sub = 9999
+    r3 = render(fld, maps, 60, 80, cams, o[:, :n_sub].contiguous(), d[:, :n_sub].contiguous(), zn, zf, act, s_prop, s_nerf, vis=False)
+    torch.cuda.synchronize()
+    bins = r1.level_bins[-1]
+    assert bool((bins[..., 1:] >= bins[..., :-1]).all()) and float(bins.min()) >= 0.0 and float(bins.max()) <= 1.0
+    wts = r1.weights
+    assert float(wts.min()) >= 0.0 and float(wts.sum(-1).max()) <= 1.0 + 1e-4
+    assert bool(torch.isfinite(r1.rgb).all() and torch.isfinite(r1.jbar).all() and torch.isfinite(r1.flow).all())
+    assert float(r1.depth.min()) >= 0.65 - 1e-5 and float(r1.depth.max()) <= 3.2 + 1e-5
+    assert float(r1.rgb.min()) >= 0.0 and float(r1.rgb.max()) <= 1.0 + 1e-5
+    # linearity in the action
+    assert torch.equal(r1.jbar, r2.jbar) and torch.equal(r1.p, r2.p) and torch.equal(r1.rgb, r2.rgb)
+    torch.testing.assert_close(r2.pw - r2.p, 2.0 * (r1.pw - r1.p), rtol=1e-4, atol=1e-6)
+    # ray-shard invariance (what the multi-GPU path relies on)
+    for k in ("rgb", "jbar", "p", "pw", "flow"):
+        assert torch.equal(getattr(r3, k), getattr(r1, k)[:, :n_sub]), k
+    # composite consistency: rgb recomputed from weights is bounded by sum of weights
+    assert bool((r1.rgb.sum(-1) <= 3.0 * wts.sum(-1) + 1e-4).all())
+
+
+def test_bad_arguments_fail_loudly():
+    from njf_b200 import _lib, api
+    from njf_b200.render import render
+
+    fx, t, head, A, s_prop, s_nerf, w = load_fixture("render_transformer")
+    fld, maps = _field_and_maps(head, A, s_prop, w, t("feat"))
+    cams, keep = api.make_cameras(t("ctxt_c2w"), t("ctxt_k"), t("trgt_c2w"), t("trgt_k_px"), DEV)
+    g = lambda k: t(k).to(DEV)
+    with pytest.raises(_lib.NjfError):   # sample count beyond the supported range
+        render(fld, maps, 12, 16, cams, g("origins"), g("dirs"), g("z_near"), g("z_far"), g("action"), (1024,), 24)
+    with pytest.raises(_lib.NjfError):   # wrong number of proposal levels for this field
+        render(fld, maps, 12, 16, cams, g("origins"), g("dirs"), g("z_near"), g("z_far"), g("action"), (16, 16), 24)
+    with pytest.raises(_lib.NjfError):   # unsupported head size
+        api.Field("jacobian_transformer", 9, 1, w)
