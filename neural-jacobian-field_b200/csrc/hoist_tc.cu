@@ -155,18 +155,20 @@ int njf_hoist_build(NjfField* f, const std::vector<float>& w, const std::vector<
   int nmaps = f->desc.n_proposal + 1;
   for (int m = 0; m < nmaps; ++m) {
     const int CH = (m < f->desc.n_proposal) ? f->ch_prop : f->ch_main;
-    for (int c0 = 0; c0 < CH; c0 += 384) slabs.push_back({m, c0, (CH - c0 > 448) ? 384 : CH - c0});
+    for (int c0 = 0; c0 < CH;) {
+      const int n = (CH - c0 > kHoistMaxN) ? 384 : CH - c0;
+      slabs.push_back({m, c0, n});
+      c0 += n;
+    }
   }
   if (slabs.size() > 8) NJF_FAIL("internal: too many hoist slabs");
   std::vector<uint8_t> blob;
   f->hoist_jobs.clear();
-  int row0 = 0;
   std::vector<int> map_row0(nmaps);
   for (int m = 0, r = 0; m < nmaps; ++m) {
     map_row0[m] = r;
     r += (m < f->desc.n_proposal) ? f->ch_prop : f->ch_main;
   }
-  (void)row0;
   for (const Slab& s : slabs) {
     NjfField::HoistJobHost j{};
     j.map = s.map;

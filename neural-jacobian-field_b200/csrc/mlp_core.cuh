@@ -295,22 +295,6 @@ __device__ __forceinline__ void epi_relu_to_a(const EpiCtx& e, int tcol, int c0)
   a_store32(e, c0, p);
 }
 
-// both 32-column chunks of this thread's column half in one go: the two TMEM loads are in flight
-// together (one exposed tcgen05.ld latency per step instead of two)
-__device__ __forceinline__ void epi_relu_to_a64(const EpiCtx& e, int tcol0) {
-  uint32_t r0[32], r1[32];
-  tmem_ld32(e.tmem + tcol0 + e.col0, r0);
-  tmem_ld32(e.tmem + tcol0 + e.col0 + 32, r1);
-  tmem_ld_wait();
-  uint32_t p[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) p[j] = pack_relu_f16x2(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
-  a_store32(e, e.col0, p);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) p[j] = pack_relu_f16x2(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
-  a_store32(e, e.col0 + 32, p);
-}
-
 // x[c0..c0+32) (+= tz_staging[row][c0..], written back to TMEM so later accumulating MMAs see it)
 // -> ReLU -> fp16 -> A tile.  Biases are accumulated by the tensor core (kStepBias).
 template <bool kHasTz>

@@ -99,9 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
   } else {
     EpiCtx e = epi_ctx(c);
     SlotScratch* sc = slot_scratch(c, e.slot);
-    const int w8 = warp & 7;
     const int lane = threadIdx.x & 31;
-    const int nb = p.n_out + 1;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
       const int group = 2 * it + e.slot;
       if (group >= g.NG) continue;
@@ -168,16 +166,6 @@ __device__ __forceinline__ void store32_to_a(const EpiCtx& e, const float (&v)[3
 #pragma unroll
   for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
   a_store32(e, 32 * e.half, pk);
-}
-// v[j] += tab[32h + j] (fp32 vector loads)
-__device__ __forceinline__ void add_vec32(const EpiCtx& e, float (&v)[32], const float* tab) {
-  const float* t = tab + 32 * e.half;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float2 s0 = fadd2(make_float2(v[2 * j], v[2 * j + 1]), make_float2(t[2 * j], t[2 * j + 1]));
-    v[2 * j] = s0.x;
-    v[2 * j + 1] = s0.y;
-  }
 }
 // LayerNorm over the row's 64 values (32 here, 32 in the partner thread) -> fp16 -> A tile
 __device__ __forceinline__ void ln64_to_a(const EpiCtx& e, SlotScratch* sc, const float (&x)[32],
