@@ -135,8 +135,9 @@ def build_model(device):
     return m.to(device)
 
 
-def oracle_rays_per_s(nrays: int, steps: int, warmup: int, want_outputs=False):
-    """The reference algorithm (CPU oracle port, fp32, all host threads) on a bounded ray sample."""
+def oracle_rays_per_s(nrays: int, steps: int, warmup: int, want_outputs=False, device=None):
+    """The reference algorithm (oracle port, fp32) on a bounded ray sample: on the host cores (all threads)
+    or, with `device`, as eager PyTorch on the GPU (what the reference's own code path does on one GPU)."""
     import njf_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
@@ -146,15 +147,24 @@ def oracle_rays_per_s(nrays: int, steps: int, warmup: int, want_outputs=False):
     feat = torch.randn(1, 512, IMG_H // 2, IMG_W // 2, generator=g).abs() * 0.7
     idx = torch.randperm(RENDER_H * RENDER_W, generator=g)[:nrays]
     spec = O.FieldSpec(HEAD, A)
+    if device is not None:
+        w = {k: v.to(device) for k, v in w.items()}
+        sc = {k: v.to(device) for k, v in sc.items()}
+        feat, idx = feat.to(device), idx.to(device)
+        sync = torch.cuda.synchronize
+    else:
+        sync = lambda: None
     run = lambda: O.render_forward(w, spec, feat, sc["ctxt_c2w"], sc["ctxt_k"], sc["trgt_c2w"], sc["trgt_k_px"],
                                    sc["origins"][:, idx], sc["dirs"][:, idx], sc["z_near"], sc["z_far"], sc["action"],
                                    S_PROP, S_NERF)
     with torch.no_grad():
         for _ in range(warmup):
             run()
+        sync()
         t0 = time.perf_counter()
         for _ in range(steps):
             out = run()
+        sync()
         dt = (time.perf_counter() - t0) / steps
     return nrays / dt, dt, (feat, idx, out) if want_outputs else None
 
@@ -375,6 +385,13 @@ def main():
         jr = float((res.jbar.cpu() - oref["action_features"]).norm() / oref["action_features"].norm())
         line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{nrays} random rays of the frame, 128+128 samples, oracle/njf_oracle.py (torch CPU fp32), {dt:.1f} s"}
+        try:  # the same port as eager PyTorch on this GPU (reference-style single-GPU path), for scale only
+            grays = 2048
+            grps, gdt, _ = oracle_rays_per_s(grays, 3, 1, device=dev)
+            line["cpu_baseline"]["torch_gpu_port"] = {"value": grps, "unit": "rays/s",
+                                                      "sample": f"{grays} rays/step (the reference's patch size), eager torch fp32 on cuda:0, {gdt * 1e3:.0f} ms/step"}
+        except Exception as ex:  # noqa: BLE001 -- a baseline leg must not break the bench line
+            line["cpu_baseline"]["torch_gpu_port"] = {"error": repr(ex)[:200]}
         line["quality"] = {"psnr_rgb_vs_oracle_db": 10 * __import__("math").log10(1.0 / max(mse, 1e-12)),
                            "jacobian_rel_l2_vs_oracle": jr, "rays": nrays}
     print(json.dumps(line))

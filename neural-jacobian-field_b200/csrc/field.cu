@@ -63,12 +63,23 @@ struct Builder {
   }
 };
 
+// The kernels write the positional encoding as [sin block (30) | 0 0 | cos block (30) | 0 0] so that each
+// of a row's two threads owns one block with compile-time (dim, freq) per column (write_posenc);
+// the 60 encoding columns of W[n][ld] are re-ordered to match (K order is free on the weight side).
+std::vector<float> enc_cols(const float* w, int n, int ld) {
+  std::vector<float> o(static_cast<size_t>(n) * 64, 0.f);
+  if (w)
+    for (int r = 0; r < n; ++r)
+      for (int c = 0; c < 60; ++c) o[r * 64 + (c < 30 ? c : c + 2)] = w[static_cast<size_t>(r) * ld + c];
+  return o;
+}
+
 // lin_in step + hoisted lin_z rows; the block steps are appended separately (program order differs
 // between heads).
 void trunk_lin_in(Builder& b, Program& prog, const std::string& p, TrunkTab& tab, int flags = 0) {
   const float* w = b.get(p + ".lin_in.weight", 128 * 63);
   const float* bi = b.get(p + ".lin_in.bias", 128);
-  b.step(prog, w, 128, 60, 63, 128, 64, /*d_col=*/0, /*acc=*/0, flags);
+  b.step(prog, w ? enc_cols(w, 128, 63).data() : nullptr, 128, 64, 64, 128, 64, /*d_col=*/0, /*acc=*/0, flags);
   if (w && bi)
     for (int c = 0; c < 128; ++c) tab.e0[c] = make_float4(w[c * 63 + 60], w[c * 63 + 61], w[c * 63 + 62], bi[c]);
   for (int k = 0; k < 3; ++k) {
@@ -131,7 +142,7 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
     const float* wq = b.get("decoder.jacobian_query_mlp.weight", 64 * 575);
     const float* bq = b.get("decoder.jacobian_query_mlp.bias", 64);
     const float* emb = b.get("decoder.jacobian_index_embedding", static_cast<int64_t>(A) * 64);
-    b.step(fp, wq, 64, 60, 575, 64, 64, /*d_col=*/128, 0, kStepReuseA);
+    b.step(fp, wq ? enc_cols(wq, 64, 575).data() : nullptr, 64, 64, 64, 64, 64, /*d_col=*/128, 0, kStepReuseA);
     if (wq && bq) {
       for (int c = 0; c < 64; ++c)
         f->head.q_e0[c] = make_float4(wq[c * 575 + 60], wq[c * 575 + 61], wq[c * 575 + 62], bq[c]);

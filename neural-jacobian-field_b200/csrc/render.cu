@@ -107,8 +107,11 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
         RowState rs;
         PROF(e, kPOther);
         row_setup(g, group, tile, e.row, rs);
+        PROF(e, kPPdf);
         if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
+        PROF(e, kPHead);
         write_posenc(e, rs.cam, rs.ray >= 0, g.debug);
+        PROF(e, kPColor);
         epi_publish(e);  // -> lin_in
         __syncwarp();
         PROF(e, kPSetup);

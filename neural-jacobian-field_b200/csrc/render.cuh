@@ -132,34 +132,36 @@ __device__ __forceinline__ void row_setup(const PassGeom& g, int group, int tile
 // checked against float64 in DESIGN.md section 5).  The argument is the SAME fp32 number the
 // reference feeds to torch.sin, so its large-argument rounding behaviour is reproduced.
 __device__ __forceinline__ float sin_cw(float t) {
-  const float n = rintf(t * 0.15915494f);
+  // round-to-nearest-even of t / 2pi by the 1.5 * 2^23 trick (FMA pipe instead of FRND; |t / 2pi| < 2^22)
+  const float n = __fsub_rn(__fmaf_rn(t, 0.15915494f, 12582912.f), 12582912.f);
   float r = fmaf(n, -6.28125f, t);
   r = fmaf(n, -1.9350052e-3f, r);
   r = fmaf(n, -3.019916e-7f, r);
   return __sinf(r);
 }
 
-// NeRFEncoding(63) of the camera-space point into A-tile K-block 0 (columns 60..63 are zero: the
-// raw-xyz columns are applied in fp32 by the first epilogue).  Column order: sin block
-// (dim-major, freq-minor), cos block (= sin(t + pi/2)), like nerfstudio's torch implementation.
-// Each of the row's two threads writes its 32 columns.
+// NeRFEncoding(63) of the camera-space point into A-tile K-block 0.  nerfstudio's column order is
+// [sin block | cos block], each dim-major / freq-minor, cos(t) evaluated as sin(t + pi/2); here the
+// row's thread of column half 0 writes the 30 sin columns (+2 zero columns) and the thread of half 1
+// the 30 cos columns (+2 zeros), so (dim, freq) of every column is a compile-time constant; the
+// weight packer re-orders lin_in / query-MLP columns to match (field.cu enc_cols).  The raw-xyz
+// columns are applied in fp32 by the first epilogue.
 __device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)[3], bool valid,
                                              int debug = 0) {
   if (debug & 2) valid = false;
+  const float off = e.half ? 1.5707964f : 0.f;  // t + 0 is exact
+  const float base[3] = {__fmul_rn(6.2831855f, cam[0]), __fmul_rn(6.2831855f, cam[1]), __fmul_rn(6.2831855f, cam[2])};
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int c = 32 * e.half + j;           // 0..63
-    const int cc = c < 30 ? c : c - 30;      // index inside the sin / cos block
-    const int i = cc / 10, k = cc - 10 * i;
-    const float x = i == 0 ? cam[0] : (i == 1 ? cam[1] : cam[2]);
-    float t = __fmul_rn(6.2831855f, x) * static_cast<float>(1 << k);  // exact power-of-two scaling
-    if (c >= 30) t = __fadd_rn(t, 1.5707964f);
-    v[j] = (valid && c < 60) ? sin_cw(t) : 0.f;
+  for (int j = 0; j < 30; ++j) {
+    const int i = j / 10, k = j - 10 * i;
+    const float t = __fadd_rn(base[i] * static_cast<float>(1 << k), off);  // exact power-of-two scaling
+    v[j] = sin_cw(t);
   }
+  v[30] = v[31] = 0.f;
   uint32_t pk[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
+  for (int j = 0; j < 16; ++j) pk[j] = valid ? pack_f16x2(v[2 * j], v[2 * j + 1]) : 0u;
   a_store32(e, 32 * e.half, pk);
 }
 

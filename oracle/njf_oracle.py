@@ -46,7 +46,7 @@ def posenc(x: torch.Tensor, num_freq: int = 10) -> torch.Tensor:
     """nerfstudio NeRFEncoding(in_dim=3, num_frequencies=10, min 0, max 9, include_input=True)
     (call sites models/decoder/action_decoder_jacobian.py:275-282, density_decoder.py:31-38):
     [sin(2 pi x 2^k) (dim-major, freq-minor) ; sin(. + pi/2) ; x] -> 63 columns."""
-    freqs = 2.0 ** torch.linspace(0.0, num_freq - 1.0, num_freq)
+    freqs = (2.0 ** torch.linspace(0.0, num_freq - 1.0, num_freq)).to(x.device)
     t = ((2.0 * torch.pi * x)[..., None] * freqs).reshape(*x.shape[:-1], -1)
     return torch.cat([torch.sin(torch.cat([t, t + torch.pi / 2.0], -1)), x], -1)
 
@@ -101,7 +101,7 @@ def bilinear_border(feat: torch.Tensor, uv: torch.Tensor) -> torch.Tensor:
     w_sw = (x1 - ix) * (iy - y0)
     w_se = (ix - x0) * (iy - y0)
     flat = feat.permute(0, 2, 3, 1).reshape(B, H * Wd, C)
-    out = torch.zeros(B, uv.shape[1], C, dtype=feat.dtype)
+    out = torch.zeros(B, uv.shape[1], C, dtype=feat.dtype, device=feat.device)
     for xx, yy, ww in ((x0, y0, w_nw), (x1, y0, w_ne), (x0, y1, w_sw), (x1, y1, w_se)):
         inb = (xx <= Wd - 1) & (yy <= H - 1)  # xx,yy >= 0 after the border clamp
         idx = (yy.clamp(max=H - 1) * Wd + xx.clamp(max=Wd - 1)).long()
@@ -216,7 +216,7 @@ def pdf_resample(weights: torch.Tensor, bins: torch.Tensor, n_samples: int,
     cdf = torch.min(torch.ones_like(pdf), torch.cumsum(pdf, dim=-1))
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
     if u is None:
-        u = torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb) + 1.0 / (2 * nb)
+        u = (torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb) + 1.0 / (2 * nb)).to(cdf.device)
         u = u.expand(size=(*cdf.shape[:-1], nb))
     u = u.contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
@@ -266,7 +266,7 @@ def render_forward(w: W, spec: FieldSpec, feat: torch.Tensor, ctxt_c2w, ctxt_k, 
     B, R = origins.shape[:2]
     near = torch.ones_like(origins[..., :1]) * z_near[:, None, None]   # model.py:215-226
     far = torch.ones_like(origins[..., :1]) * z_far[:, None, None]
-    bins = uniform_bins((B, R), s_prop[0])
+    bins = uniform_bins((B, R), s_prop[0]).to(origins.device)
     out: Dict[str, torch.Tensor] = {}
     prop_w: List[torch.Tensor] = []
     prop_bins: List[torch.Tensor] = [bins]
@@ -306,7 +306,7 @@ def render_forward(w: W, spec: FieldSpec, feat: torch.Tensor, ctxt_c2w, ctxt_k, 
         action_features=torch.sum(weights * jac, dim=-2), steps=steps.squeeze(-1),
         weights=weights.squeeze(-1), ray_positions=p, ray_positions_warped=pw,
         sigma=sigma, jacobian=jac, rgb_samples=rgb, positions=pos, final_bins=bins,
-        proposal_weights=prop_w[-1].squeeze(-1) if prop_w else torch.zeros(0),
+        proposal_weights=prop_w[-1].squeeze(-1) if prop_w else torch.zeros(0, device=origins.device),
     )
     return out
 
