@@ -38,7 +38,12 @@ FLOP_PROPOSAL_SAMPLE = 737_280
 FLOP_FIELD_SAMPLE = 1_321_904
 GATHER_BYTES_SAMPLE_F16 = 4 * 512 * 2   # 4 taps x 512 channels at the kernels' fp16 storage precision
 EXEC_MAC_PROPOSAL = 128 * 64 + 10 * 128 * 128 + 16 * 128            # executed tensor-core MACs / sample
-EXEC_MAC_FIELD = EXEC_MAC_PROPOSAL + 64 * 64 + 12 * 64 * 64 + 32 * 64 + 2 * 64 * 64
+EXEC_MAC_FIELD = EXEC_MAC_PROPOSAL + 64 * 64 + 2 * 64 * 64           # + q_enc + colour head (field_kernel)
+EXEC_MAC_XF = 12 * 64 * 64 + 32 * 64                                 # xf_kernel: 3 x (M1, M2, W1, W2) + jacobian_head
+# reference-formulation split of the main sample (370 560 + 284 096 + 6 272 + 24 MAC):
+# field_kernel = density trunk + colour + the 575->64 query MLP + J.u ; xf_kernel = the rest of the cross-attention head
+FLOP_FIELD_KERNEL_SAMPLE = 2 * (370_560 + 6_272 + 575 * 64 + 24)
+FLOP_XF_KERNEL_SAMPLE = FLOP_FIELD_SAMPLE - FLOP_FIELD_KERNEL_SAMPLE
 
 
 def peaks():
@@ -287,6 +292,7 @@ def main():
     if rank == 0: clocks.start()
     timers = []
     torch.cuda.synchronize()
+    _lib.check(L.njf_debug_field_timing(1, None, None))   # per-kernel CUDA events inside njf_field_pass
     for _ in range(args.steps):
         step(timers)
         flush.zero_()          # L2 flush between timed steps (outside the per-step event pairs)
@@ -297,6 +303,9 @@ def main():
     t_hoist = sum(e[0].elapsed_time(e[1]) for e in timers) / args.steps
     t_prop = sum(e[1].elapsed_time(e[2]) for e in timers) / args.steps
     t_field = sum(e[2].elapsed_time(e[3]) for e in timers) / args.steps
+    c_fk, c_xf = ctypes.c_float(0), ctypes.c_float(0)
+    _lib.check(L.njf_debug_field_timing(0, ctypes.byref(c_fk), ctypes.byref(c_xf)))
+    t_fk, t_xf = c_fk.value / args.steps, c_xf.value / args.steps
     tt = torch.tensor([tot], device=dev)
     if dist: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     tot = float(tt.item())
@@ -331,11 +340,16 @@ def main():
         return
     pk = peaks()
     # ---- roofline of the dominant kernel (reference-formulation algorithmic work)
-    dom, t_dom, flop_s, = ("field_kernel", t_field, FLOP_FIELD_SAMPLE) if t_field >= t_prop else ("proposal_kernel", t_prop, FLOP_PROPOSAL_SAMPLE)
+    cands = [("field_kernel", t_fk, FLOP_FIELD_KERNEL_SAMPLE, EXEC_MAC_FIELD, True),
+             ("proposal_kernel", t_prop, FLOP_PROPOSAL_SAMPLE, EXEC_MAC_PROPOSAL, True),
+             ("xf_kernel", t_xf, FLOP_XF_KERNEL_SAMPLE, EXEC_MAC_XF, False)]
+    dom, t_dom, flop_s, exec_mac, gathers = max(cands, key=lambda c: c[1])
     evals = R * S_NERF
     alg_flop = evals * flop_s
-    alg_bytes = evals * GATHER_BYTES_SAMPLE_F16 + R * (24 + 144)
-    exec_flop = 2 * evals * (EXEC_MAC_FIELD if dom == "field_kernel" else EXEC_MAC_PROPOSAL)
+    # algorithmic bytes: the 4-tap x 512-channel gather (trunk kernels) / the 64-float query stream + weight in,
+    # J-bar out (xf_kernel); per-ray inputs and outputs
+    alg_bytes = evals * (GATHER_BYTES_SAMPLE_F16 if gathers else 65 * 4) + R * (24 + 144)
+    exec_flop = 2 * evals * exec_mac
     t_flop_bound = alg_flop / (pk["tf_sustained"] * 1e12)
     t_byte_bound = alg_bytes / (pk["hbm_gbs"] * 1e9)
     if t_flop_bound >= t_byte_bound:
@@ -364,12 +378,12 @@ def main():
                    "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
                    "encoder": "excluded from value (once per image, cuDNN), included in e2e",
                    "weights": "synthetic seeded (oracle/synth.py), random-init architecture of model_allegro.yaml"},
-        "breakdown_ms": {"hoist": t_hoist, "proposal_kernel": t_prop, "field_kernel": t_field,
+        "breakdown_ms": {"hoist": t_hoist, "proposal_kernel": t_prop, "field_pass": t_field, "field_kernel": t_fk, "xf_kernel": t_xf,
                          "finish+gather": ms_step - t_hoist - t_prop - t_field if world == 1 else None},
         "roofline": roof,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(te_t.item()) / e2e_steps * 1e3},
-        "gpu_launches": 7 * args.steps,
+        "gpu_launches": 8 * args.steps,
         "clocks": clk,
     }
     if not args.no_cpu_baseline:

@@ -172,6 +172,11 @@ int njf_selftest_chain(const float* w0, const float* w1, const float* w2, const 
                        const float* a_in, const float* tz_in, float* x_out, float* y_out, int ntiles, int grid,
                        void* stream);
 
+/* ---- measurement aid (bench.py): with enable != 0 every njf_field_pass brackets its kernels with CUDA events on
+ * the launching stream; a later call returns the accumulated milliseconds of field_kernel and of xf_kernel (the
+ * cross-attention head; 0 for the MLP head) since the previous call and resets the counters.  Either pointer may be NULL. */
+int njf_debug_field_timing(int enable, float* field_kernel_ms, float* xf_kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

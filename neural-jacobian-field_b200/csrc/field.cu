@@ -3,7 +3,8 @@
 //
 // Layer order of the step programs MUST match the epilogue code in render.cu:
 //   proposal : lin_in | (fc_0, fc_1) x5 | lin_out(N=16)
-//   field/T  : lin_in | q_enc | (M1, M2, W1, W2) x3 | jhead(N=32) | (fc_0, fc_1) x5 | lin_out(16) | color1 | color2
+//   field/T  : lin_in | q_enc | (fc_0, fc_1) x5 | lin_out(16) | color1 | color2
+//   head/T   : (M1, M2, W1, W2) x3 | jhead(N=32)            (xf_kernel, resident in shared memory)
 //   field/M  : lin_in | (fc_0, fc_1) x5 | lin_out(16) | color1 | color2 | lin_in(jac) | (fc_0, fc_1) x5 | lin_out(N=32)
 #include <cmath>
 #include <cstring>
@@ -133,6 +134,7 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
     trunk_blocks(b, f->prop_prog[i], p, 1, 16);
   }
   Program& fp = f->field_prog;
+  std::vector<uint8_t> xf_blob;
   // transformer head: lin_in and q_enc read the same A tile (the positional encoding) and are
   // covered by ONE accumulator commit (two arrivals on one mbarrier phase would be unsafe)
   trunk_lin_in(b, fp, "decoder.density_head", f->dens_trunk,
@@ -150,6 +152,12 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
       for (int c = 0; c < 64; ++c) b.hoist_w.insert(b.hoist_w.end(), wq + c * 575 + 63, wq + c * 575 + 575);
       b.hoist_b.insert(b.hoist_b.end(), 64, 0.f);
     }
+    // ---- the attention / feed-forward layers and jacobian_head run in xf_kernel from their own blob.
+    // Exact folds done here in fp64: keys/values (they depend only on the learned index embedding,
+    // transformer.py:63-78, action_decoder_jacobian.py:431-435), the LayerNorm affine (PreNorm,
+    // transformer.py:14-21: W (g*n + b) = (W diag g) n + W b) and log2(e) into the logits.
+    Builder hb;
+    Program& hp = f->head_prog;
     for (int l = 0; l < 3; ++l) {
       const std::string p = "decoder.jacobian_attn_decoder.layers." + std::to_string(l);
       const float* g1 = b.get(p + ".0.norm.weight", 64);
@@ -164,10 +172,8 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
       const float* bb1 = b.get(p + ".1.fn.net.0.bias", 64);
       const float* w2 = b.get(p + ".1.fn.net.3.weight", 64 * 64);
       const float* bb2 = b.get(p + ".1.fn.net.3.bias", 64);
-      std::vector<float> m1(64 * 64, 0.f), m2(64 * 64, 0.f);
-      if (wq_ && wkv && wo && emb) {
-        // keys/values depend only on the learned index embedding (transformer.py:63-78,
-        // action_decoder_jacobian.py:431-435): fold  scale * to_q_h^T K_h  and  to_out_h V_h.
+      std::vector<float> m1(64 * 64, 0.f), m1b(64, 0.f), m2(64 * 64, 0.f), w1g(64 * 64, 0.f), w1b(64, 0.f);
+      if (wq_ && wkv && wo && emb && g1 && be1) {
         std::vector<double> K(static_cast<size_t>(A) * 512), V(static_cast<size_t>(A) * 512);
         for (int a = 0; a < A; ++a)
           for (int j = 0; j < 512; ++j) {
@@ -179,15 +185,18 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
             K[a * 512 + j] = sk;
             V[a * 512 + j] = sv;
           }
-        const double scale = 1.0 / std::sqrt(64.0);
+        const double scale = 1.4426950408889634 / std::sqrt(64.0);  // log2(e) * dim_head^-0.5
         for (int h = 0; h < 8; ++h)
           for (int a = 0; a < A; ++a) {
             const int n = h * 8 + a;  // logit / attention column (heads padded to 8 keys)
+            double sb = 0;
             for (int k = 0; k < 64; ++k) {
               double s = 0;
               for (int d = 0; d < 64; ++d) s += static_cast<double>(wq_[(h * 64 + d) * 64 + k]) * K[a * 512 + h * 64 + d];
-              m1[n * 64 + k] = static_cast<float>(scale * s);
+              m1[n * 64 + k] = static_cast<float>(scale * s * g1[k]);
+              sb += scale * s * be1[k];
             }
+            m1b[n] = static_cast<float>(sb);
             for (int o = 0; o < 64; ++o) {
               double s = 0;
               for (int d = 0; d < 64; ++d) s += static_cast<double>(wo[o * 512 + h * 64 + d]) * V[a * 512 + h * 64 + d];
@@ -195,19 +204,24 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
             }
           }
       }
-      b.step(fp, m1.data(), 64, 64, 64, 64, 64, 128, 0);
-      b.step(fp, m2.data(), 64, 64, 64, 64, 64, 128, 0, 0, bo, true);
-      b.step(fp, w1, 64, 64, 64, 64, 64, 128, 0, 0, bb1, true);
-      b.step(fp, w2, 64, 64, 64, 64, 64, 128, 0, 0, bb2, true);
-      const float* src[4] = {g1, be1, g2, be2};
-      XfLayerTab& T = f->head.layer[l];
-      float* dst[4] = {T.ln1_g, T.ln1_b, T.ln2_g, T.ln2_b};
-      for (int i = 0; i < 4; ++i)
-        if (src[i]) std::memcpy(dst[i], src[i], 64 * sizeof(float));
+      if (w1 && bb1 && g2 && be2)
+        for (int n = 0; n < 64; ++n) {
+          double sb = bb1[n];
+          for (int k = 0; k < 64; ++k) {
+            w1g[n * 64 + k] = w1[n * 64 + k] * g2[k];
+            sb += static_cast<double>(w1[n * 64 + k]) * be2[k];
+          }
+          w1b[n] = static_cast<float>(sb);
+        }
+      hb.step(hp, m1.data(), 64, 64, 64, 64, 64, /*d_col=*/64, 0, 0, m1b.data(), true);
+      hb.step(hp, m2.data(), 64, 64, 64, 64, 64, /*d_col=*/0, 1, 0, bo, true);      // x += attn out
+      hb.step(hp, w1g.data(), 64, 64, 64, 64, 64, /*d_col=*/64, 0, 0, w1b.data(), true);
+      hb.step(hp, w2, 64, 64, 64, 64, 64, /*d_col=*/0, 1, 0, bb2, true);             // x += feed-forward out
     }
     const float* wh = b.get("decoder.jacobian_head.weight", static_cast<int64_t>(3 * A) * 64);
     const float* bh = b.get("decoder.jacobian_head.bias", 3 * A);
-    b.step(fp, wh, 3 * A, 64, 64, 32, 64, 128, 0, 0, bh, true);
+    hb.step(hp, wh, 3 * A, 64, 64, 32, 64, /*d_col=*/64, 0, 0, bh, true);
+    xf_blob.swap(hb.blob);
   }
   trunk_blocks(b, fp, "decoder.density_head", 16, 16);
   {
@@ -244,6 +258,12 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
   NJF_CUDA(cudaMemcpy(f->d_blob, b.blob.data(), b.blob.size(), cudaMemcpyHostToDevice));
   NJF_CUDA(cudaMemcpy(f->d_hoist_w, b.hoist_w.data(), b.hoist_w.size() * sizeof(float), cudaMemcpyHostToDevice));
   NJF_CUDA(cudaMemcpy(f->d_hoist_b, b.hoist_b.data(), b.hoist_b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (!xf_blob.empty()) {
+    if (xf_blob.size() > kXfMaxBlob) NJF_FAIL("internal: head blob %zu B exceeds the resident budget", xf_blob.size());
+    f->xf_bytes = static_cast<uint32_t>(xf_blob.size());
+    NJF_CUDA(cudaMalloc(&f->d_xf_blob, xf_blob.size()));
+    NJF_CUDA(cudaMemcpy(f->d_xf_blob, xf_blob.data(), xf_blob.size(), cudaMemcpyHostToDevice));
+  }
   if (njf_hoist_build(f, b.hoist_w, b.hoist_b)) return 1;
   for (int i = 0; i < desc->n_proposal; ++i) f->prop_blob[i] = f->d_blob;
   f->field_blob = f->d_blob;
@@ -256,6 +276,8 @@ extern "C" void njf_field_destroy(NjfField* f) {
   cudaFree(f->d_blob);
   cudaFree(f->d_hoist_img);
   cudaFree(f->d_scratch);
+  cudaFree(f->d_xf_scratch);
+  cudaFree(f->d_xf_blob);
   cudaFree(f->d_hoist_w);
   cudaFree(f->d_hoist_b);
   delete f;

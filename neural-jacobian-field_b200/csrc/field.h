@@ -12,15 +12,27 @@ namespace njf {
 struct TrunkTab {
   float4 e0[128];       // (W_in[:,60], W_in[:,61], W_in[:,62], b_in): raw-xyz columns kept in fp32
 };
-struct XfLayerTab {
-  float ln1_g[64], ln1_b[64], ln2_g[64], ln2_b[64];
-};
 struct HeadTab {
-  float4 q_e0[64];      // (Wq[:,60..62], bq)
-  XfLayerTab layer[3];
+  float4 q_e0[64];      // (Wq[:,60..62], bq) of jacobian_query_mlp
 };
 struct ColorTab {
   float w3[3 * 64], b3[4];   // last colour layer (3 outputs) stays on the fp32 pipes
+};
+
+
+// ---- cross-attention head kernel (xf_head.cu)
+constexpr uint32_t kXfMaxBlob = 125 * 1024;  // all head layer images, resident in shared memory
+struct XfParams {
+  Program prog;        // filled by njf_xf_launch: 12 layer steps + jacobian_head; MmaStep::acc = accumulate onto x
+  const uint8_t* blob;
+  uint32_t blob_bytes;
+  int A;
+  // tiling of the pass: identical to field_kernel's (render.cuh PassGeom)
+  int NR, S, G, T, NG, group0;
+  const float4* qs;    // [tile][16 chunks][128 rows] float4: the 64-wide query embedding of every row
+  const float* wts;    // [tile][128 rows] transmittance weight of the sample (0 for padding rows)
+  float* jbar;         // [NR][3A] or null
+  float* jac_out;      // [NR*S][3A] or null
 };
 
 }  // namespace njf
@@ -33,6 +45,11 @@ struct NjfField {
   uint8_t* d_hoist_img = nullptr;          // tcgen05 weight images of the hoist GEMM (hoist_tc.cu)
   mutable float* d_scratch = nullptr;      // grow-only per-field scratch (proposal weights between the
   mutable size_t scratch_bytes = 0;        // proposal kernel and the PDF kernel); one stream at a time
+  mutable float* d_xf_scratch = nullptr;   // grow-only: query stream + sample weights between field_kernel
+  mutable size_t xf_scratch_bytes = 0;     // and xf_kernel (transformer head)
+  njf::Program head_prog;                  // transformer head: steps of xf_kernel
+  uint8_t* d_xf_blob = nullptr;
+  uint32_t xf_bytes = 0;
   std::vector<HoistJobHost> hoist_jobs;
   uint8_t* d_blob = nullptr;   // all layer images
   float* d_hoist_w = nullptr;  // [ch_total][512] rows of the hoisted linear maps
@@ -54,3 +71,5 @@ struct NjfField {
 int njf_hoist_build(NjfField* f, const std::vector<float>& w, const std::vector<float>& b);
 int njf_hoist_launch(const NjfField* f, const float* feat_nchw, int B, int Hf, int Wf, void* maps_out,
                      cudaStream_t stream);
+// xf_head.cu (prog / blob / A are taken from the field)
+int njf_xf_launch(const NjfField* f, const njf::XfParams& params, cudaStream_t stream);

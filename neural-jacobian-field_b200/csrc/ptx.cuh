@@ -207,6 +207,12 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   return r;
 }
 constexpr float kF16Max = 65504.0f;
+// 2^x on the SFU (MUFU.EX2), no range fix-ups
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2): one issue slot for two lanes of fp32 math
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {

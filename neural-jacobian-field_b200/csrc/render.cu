@@ -17,7 +17,6 @@ struct SlotScratch {
   float cum[kRows];      // exclusive prefix sums (fp32) of dd
   float wrow[kRows];     // transmittance weight of each row (shared between the row's two threads)
   TapEntry taps[kRows];  // bilinear taps of the current tile
-  float2 xch[kRows][2];  // per-row exchange between the two column-half threads (LayerNorm sums)
   float4 rgbp[kRows];    // colour-head partial dot products of the upper column half
 };
 constexpr uint32_t kScratchSlotBytes = (sizeof(SlotScratch) + 15) & ~15u;
@@ -153,6 +152,9 @@ struct FieldParams {
   // per-sample outputs
   float* steps; float* weights; float* sigma; float* jac_out; float* positions; float* rgb_samples;
   float* geo_out;    // [NR*S][15] density-head geometry features (point queries)
+  // transformer head: hand-over to xf_kernel (indexed by the launch-local tile number)
+  float4* qs;        // [tile][16][128] query embedding
+  float* wts;        // [tile][128] sample weights (0 for padding rows)
   uint32_t* minmax;  // [2] ordered-uint encoded min / max of steps
 };
 
@@ -164,84 +166,11 @@ __device__ __forceinline__ void ld_acc32(const EpiCtx& e, float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
-__device__ __forceinline__ void store32_to_a(const EpiCtx& e, const float (&v)[32]) {
-  uint32_t pk[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
-  a_store32(e, 32 * e.half, pk);
-}
-// LayerNorm over the row's 64 values (32 here, 32 in the partner thread) -> fp16 -> A tile
-__device__ __forceinline__ void ln64_to_a(const EpiCtx& e, SlotScratch* sc, const float (&x)[32],
-                                          const float* gam, const float* bet) {
-  float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int j = 0; j < 32; j += 2) acc = fadd2(acc, make_float2(x[j], x[j + 1]));
-  sc->xch[e.row][e.half].x = acc.x + acc.y;
-  pair_bar(e);
-  const float mean = (sc->xch[e.row][0].x + sc->xch[e.row][1].x) * (1.f / 64.f);
-  float2 sq = make_float2(0.f, 0.f);
-  const float2 nm = make_float2(-mean, -mean);
-#pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    const float2 d = fadd2(make_float2(x[j], x[j + 1]), nm);
-    sq = ffma2(d, d, sq);
-  }
-  sc->xch[e.row][e.half].y = sq.x + sq.y;
-  pair_bar(e);
-  const float var = (sc->xch[e.row][0].y + sc->xch[e.row][1].y) * (1.f / 64.f);
-  const float rstd = rsqrtf(var + 1e-5f);
-  const float* gg = gam + 32 * e.half;
-  const float* bb = bet + 32 * e.half;
-  const float2 rs2 = make_float2(rstd, rstd);
-  uint32_t pk[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    float2 d = fadd2(make_float2(x[2 * j], x[2 * j + 1]), nm);
-    d = ffma2(d, rs2, make_float2(0.f, 0.f));
-    d = ffma2(d, make_float2(gg[2 * j], gg[2 * j + 1]), make_float2(bb[2 * j], bb[2 * j + 1]));
-    pk[j] = pack_f16x2(d.x, d.y);
-  }
-  a_store32(e, 32 * e.half, pk);
-}
-// softmax over the A real keys of each of this thread's 4 heads (heads are padded to 8 columns)
-template <int A>
-__device__ __forceinline__ void softmax_heads(float (&lg)[32]) {
-#pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    float m = -3.0e38f;
-#pragma unroll
-    for (int a = 0; a < A; ++a) m = fmaxf(m, lg[h * 8 + a]);
-    float s = 0.f;
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-      const float ev = __expf(lg[h * 8 + a] - m);
-      lg[h * 8 + a] = ev;
-      s += ev;
-    }
-    const float inv = __fdividef(1.f, s);
-#pragma unroll
-    for (int a = 0; a < 8; ++a) lg[h * 8 + a] = (a < A) ? lg[h * 8 + a] * inv : 0.f;
-  }
-}
-// exact-erf GELU (nn.GELU default): erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7)
-__device__ __forceinline__ float gelu_erf(float v) {
-  const float z = fabsf(v) * 0.70710678f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erfa = 1.f - poly * t * __expf(-z * z);
-  const float erfv = copysignf(erfa, v);
-  return 0.5f * v * (1.f + erfv);
-}
-
-// Cross-attention Jacobian head (action_decoder_jacobian.py:418-446; transformer.py:63-135) with
-// the key/value projections folded into M1/M2 by njf_field_create.  Pre: accumulator wait for
-// (lin_in, q_enc) done; the 64 hoisted query channels are in the staging buffer.  Each thread
-// carries 32 of the row's 64 stream values and produces 16 of the 32 (padded) Jacobian columns.
-__device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, const HeadTab& H, int A,
-                                                 const RowState& rs, float (&J)[16]) {
+// Query embedding of the cross-attention head (action_decoder_jacobian.py:423-430):
+//   q0 = W_q[:, :60] . enc (tensor core, q_enc step) + hoisted W_q[:, 63:] . feat + W_q[:, 60:63] . xyz + b_q
+// Each of the row's two threads owns 32 of the 64 values and streams them to the `qs` scratch that
+// xf_kernel consumes ([tile][16 chunks of 4][128 rows] float4: warp stores are 512 contiguous bytes).
+__device__ __forceinline__ void store_query_stream(const EpiCtx& e, const HeadTab& H, const RowState& rs, float4* qs_tile) {
   float x[32];
   ld_acc32(e, x);
 #pragma unroll
@@ -260,69 +189,9 @@ __device__ __forceinline__ void transformer_head(EpiCtx& e, SlotScratch* sc, con
     const float4 q = H.q_e0[32 * e.half + j];
     x[j] += fmaf(q.z, rs.cam[2], fmaf(q.y, rs.cam[1], fmaf(q.x, rs.cam[0], q.w)));
   }
-#pragma unroll 1
-  for (int l = 0; l < 3; ++l) {
-    const XfLayerTab& L = H.layer[l];
-    PROF(e, kPOther);
-    ln64_to_a(e, sc, x, L.ln1_g, L.ln1_b);
-    epi_publish(e);  // -> M1: scaled logits over (head, key)
-    PROF(e, kPLn);
-    epi_wait_acc(e);
-    {
-      float lg[32];
-      ld_acc32(e, lg);
-      switch (A) {
-        case 1: softmax_heads<1>(lg); break;
-        case 2: softmax_heads<2>(lg); break;
-        case 3: softmax_heads<3>(lg); break;
-        case 4: softmax_heads<4>(lg); break;
-        case 5: softmax_heads<5>(lg); break;
-        case 6: softmax_heads<6>(lg); break;
-        case 7: softmax_heads<7>(lg); break;
-        default: softmax_heads<8>(lg); break;
-      }
-      store32_to_a(e, lg);
-    }
-    epi_publish(e);  // -> M2: attention . (V W_out)
-    PROF(e, kPSoftmax);
-    epi_wait_acc(e);
-    {
-      float t[32];
-      ld_acc32(e, t);
+  float4* dst = qs_tile + (8 * e.half) * kRows + e.row;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] += t[j];
-    }
-    PROF(e, kPRes);
-    ln64_to_a(e, sc, x, L.ln2_g, L.ln2_b);
-    epi_publish(e);  // -> W1
-    PROF(e, kPLn);
-    epi_wait_acc(e);
-    {
-      float t[32];
-      ld_acc32(e, t);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) t[j] = gelu_erf(t[j]);
-      store32_to_a(e, t);
-    }
-    epi_publish(e);  // -> W2
-    PROF(e, kPGelu);
-    epi_wait_acc(e);
-    {
-      float t[32];
-      ld_acc32(e, t);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] += t[j];
-    }
-    PROF(e, kPRes);
-  }
-  store32_to_a(e, x);
-  epi_publish(e);  // -> jacobian_head Linear(64, 3A)
-  epi_wait_acc(e);
-  uint32_t r[16];
-  tmem_ld16(e.tmem + 128 + 16 * e.half, r);
-  tmem_ld_wait();
-#pragma unroll
-  for (int j = 0; j < 16; ++j) J[j] = __uint_as_float(r[j]);
+  for (int j = 0; j < 8; ++j) __stcs(dst + j * kRows, make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
 }
 
 // SH degree 4 (tiny-cuda-nn convention) of the unit direction (action_decoder_jacobian.py:194-199)
@@ -380,12 +249,13 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
     SlotScratch* sc = slot_scratch(c, e.slot);
     const int w8 = warp & 7;
     const int lane = threadIdx.x & 31;
-    const int A = p.A, A3 = 3 * p.A;
+    const int A3 = 3 * p.A;
     const int nch = 8 + A3;  // composite channels: rgb3, t, 1, pos3, J(3A)
     // e.tz doubles as the composite staging buffer: [128 rows][64 fp32], 16 B chunks XOR-swizzled by row
     for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-      const int group = 2 * it + e.slot;
-      if (group >= g.NG) continue;
+      const int lgroup = 2 * it + e.slot;  // launch-local ray group
+      if (lgroup >= g.NG) continue;
+      const int group = g.group0 + lgroup;
       double carry = 0.0;
       float cs0 = 0.f, cs1 = 0.f;  // column sums held by warp 0 of the slot across the tiles of a long ray
       for (int tile = 0; tile < g.T; ++tile) {
@@ -393,16 +263,19 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         PROF(e, kPOther);
         row_setup(g, group, tile, e.row, rs);
         const bool valid = rs.ray >= 0;
-        float J[16];  // this thread's 16 of the 32 (padded) Jacobian columns: 16h .. 16h+15
+        float J[16];  // this thread's 16 of the 32 (padded) Jacobian columns: 16h .. 16h+15 (MLP head)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) J[j] = 0.f;
         if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
         write_posenc(e, rs.cam, valid, g.debug);
         epi_publish(e);  // -> lin_in (+ q_enc for the transformer head)
         __syncwarp();
         PROF(e, kPSetup);
+        const size_t tidx = static_cast<size_t>(lgroup) * g.T + tile;
         if (p.head_kind == NJF_HEAD_TRANSFORMER) {
           gather_segment<64>(e, g, sc->taps, 384);
           epi_wait_acc(e);
-          transformer_head(e, sc, p.head, A, rs, J);
+          if (p.qs) store_query_stream(e, p.head, rs, p.qs + tidx * 16 * kRows);
           PROF(e, kPHead);
         }
         gather_segment<128>(e, g, sc->taps, 0);
@@ -489,7 +362,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         const float w = tile_weights(e, sc, g, tile, dd, carry);
         const float ww = valid ? w : 0.f;
         uint8_t* rowp = e.tz + e.row * 256;
+        const bool stage_j = p.jbar != nullptr;  // MLP head: J composited here; transformer: by xf_kernel
         if (e.half == 0) {
+          if (p.wts) __stcs(p.wts + tidx * kRows + e.row, ww);
           if (valid) {
             const size_t si = static_cast<size_t>(rs.ray) * g.S + rs.s;
             if (p.steps) p.steps[si] = rs.tmid;
@@ -514,6 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           for (int j = 0; j < 16; ++j) v[8 + j] = (j < A3) ? J[j] : 0.f;
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
+            if (q >= 2 && !stage_j) break;
             float4 o;
             o.x = valid ? ww * v[4 * q + 0] : 0.f;
             o.y = valid ? ww * v[4 * q + 1] : 0.f;
@@ -532,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
             atomicMin(&mm[0], f2ord(tmn));
             atomicMax(&mm[1], f2ord(tmx));
           }
-        } else {
+        } else if (stage_j) {
           // J16..31 : composite columns 24..39
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -554,8 +430,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         auto colsum = [&](int r0, int n, float& s0, float& s1) {
           for (int r = r0; r < r0 + n; ++r) {
             const uint8_t* rp = e.tz + r * 256;
-            s0 += *reinterpret_cast<const float*>(rp + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-            if (nch > 32)
+            if (stage_j || lane < 8)
+              s0 += *reinterpret_cast<const float*>(rp + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+            if (stage_j && nch > 32)
               s1 += *reinterpret_cast<const float*>(rp + (((8 + (lane >> 2)) ^ (r & 7)) << 4) + (lane & 3) * 4);
           }
         };
@@ -902,6 +779,73 @@ int set_smem(K kernel) {
   return 0;
 }
 
+// field_kernel (+ xf_kernel for the cross-attention head) over all ray groups of the pass.  The
+// transformer hand-over buffers (32.5 KB per 128-row tile) live in a grow-only scratch owned by the
+// field; passes with more than kXfMaxTiles tiles run as several launch pairs over ray-group ranges.
+constexpr int kXfMaxTiles = 160 * 1024;
+// optional per-kernel timing of the field pass (njf_debug_field_timing): CUDA events on the launching stream
+bool g_time_field = false;
+std::vector<cudaEvent_t> g_field_events;  // triples (before field_kernel, between, after xf_kernel) per launch pair
+size_t g_field_events_used = 0;
+int launch_field(const NjfField* f, FieldParams& p, cudaStream_t stream) {
+  if (set_smem(field_kernel)) return 1;
+  const int NGtot = p.g.NG, T = p.g.T;
+  const bool xf = f->desc.head == NJF_HEAD_TRANSFORMER && (p.jbar || p.jac_out);
+  float* jbar = p.jbar;
+  float* jac = p.jac_out;
+  int gpc = NGtot;  // groups per launch
+  if (xf) {
+    gpc = kXfMaxTiles / T;
+    if (gpc > NGtot) gpc = NGtot;
+    const size_t tiles = static_cast<size_t>(gpc) * T;
+    const size_t need = tiles * (16 * kRows * sizeof(float4) + kRows * sizeof(float));
+    if (f->xf_scratch_bytes < need) {
+      if (f->d_xf_scratch) NJF_CUDA(cudaFree(f->d_xf_scratch));
+      f->d_xf_scratch = nullptr;
+      f->xf_scratch_bytes = 0;
+      NJF_CUDA(cudaMalloc(&f->d_xf_scratch, need));
+      f->xf_scratch_bytes = need;
+    }
+    p.qs = reinterpret_cast<float4*>(f->d_xf_scratch);
+    p.wts = f->d_xf_scratch + tiles * 16 * kRows * 4;
+  }
+  if (f->desc.head == NJF_HEAD_TRANSFORMER) {
+    p.jbar = nullptr;
+    p.jac_out = nullptr;
+  }
+  for (int g0 = 0; g0 < NGtot; g0 += gpc) {
+    p.g.group0 = g0;
+    p.g.NG = (NGtot - g0 < gpc) ? NGtot - g0 : gpc;
+    const int nitems = (p.g.NG + 1) / 2;
+    const int grid = nitems < num_sms() ? nitems : num_sms();
+    cudaEvent_t* ev = nullptr;
+    if (g_time_field) {
+      while (g_field_events.size() < g_field_events_used + 3) {
+        cudaEvent_t e;
+        NJF_CUDA(cudaEventCreate(&e));
+        g_field_events.push_back(e);
+      }
+      ev = &g_field_events[g_field_events_used];
+      g_field_events_used += 3;
+      NJF_CUDA(cudaEventRecord(ev[0], stream));
+    }
+    field_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+    NJF_CUDA(cudaGetLastError());
+    if (ev) NJF_CUDA(cudaEventRecord(ev[1], stream));
+    if (xf) {
+      XfParams x{};
+      x.NR = p.g.NR; x.S = p.g.S; x.G = p.g.G; x.T = T; x.NG = p.g.NG; x.group0 = g0;
+      x.qs = p.qs;
+      x.wts = p.wts;
+      x.jbar = jbar;
+      x.jac_out = jac;
+      if (njf_xf_launch(f, x, stream)) return 1;
+    }
+    if (ev) NJF_CUDA(cudaEventRecord(ev[2], stream));
+  }
+  return 0;
+}
+
 }  // namespace
 
 #ifdef NJF_PROFILE
@@ -915,6 +859,25 @@ extern "C" int njf_prof_read(unsigned long long* out16, int reset) {
   return 0;
 }
 #endif
+
+extern "C" int njf_debug_field_timing(int enable, float* field_kernel_ms, float* xf_kernel_ms) {
+  if (field_kernel_ms || xf_kernel_ms) {
+    float tf = 0.f, tx = 0.f;
+    for (size_t i = 0; i + 2 < g_field_events_used + 0 && i + 2 < g_field_events.size() + 0; i += 3) {
+      float a = 0.f, b = 0.f;
+      NJF_CUDA(cudaEventSynchronize(g_field_events[i + 2]));
+      NJF_CUDA(cudaEventElapsedTime(&a, g_field_events[i], g_field_events[i + 1]));
+      NJF_CUDA(cudaEventElapsedTime(&b, g_field_events[i + 1], g_field_events[i + 2]));
+      tf += a;
+      tx += b;
+    }
+    if (field_kernel_ms) *field_kernel_ms = tf;
+    if (xf_kernel_ms) *xf_kernel_ms = tx;
+  }
+  g_field_events_used = 0;
+  g_time_field = enable != 0;
+  return 0;
+}
 
 extern "C" size_t njf_hoisted_bytes(const NjfField* f, int B, int Hf, int Wf) {
   return static_cast<size_t>(B) * Hf * Wf * f->ch_total * sizeof(__half);
@@ -1016,10 +979,7 @@ extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const N
   p.rgb_samples = a->rgb_samples;
   p.minmax = reinterpret_cast<uint32_t*>(a->minmax);
   init_minmax_kernel<<<1, 1, 0, stream>>>(p.minmax);
-  if (set_smem(field_kernel)) return 1;
-  const int nitems = (p.g.NG + 1) / 2;
-  const int grid = nitems < num_sms() ? nitems : num_sms();
-  field_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  if (launch_field(f, p, stream)) return 1;
   decode_minmax_kernel<<<1, 1, 0, stream>>>(p.minmax);
   NJF_CUDA(cudaGetLastError());
   return 0;
@@ -1053,12 +1013,7 @@ extern "C" int njf_query_points(const NjfField* f, const float* ctxt_w2c, const 
   p.sigma = sigma;
   p.geo_out = geo;
   p.jac_out = jac;
-  if (set_smem(field_kernel)) return 1;
-  const int nitems = (g.NG + 1) / 2;
-  const int grid = nitems < num_sms() ? nitems : num_sms();
-  field_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
-  NJF_CUDA(cudaGetLastError());
-  return 0;
+  return launch_field(f, p, stream);
 }
 
 extern "C" int njf_point_features(const float* feat_nchw, const float* ctxt_w2c, const float* ctxt_k,

@@ -13,7 +13,8 @@ struct PassGeom {
   int S;    // samples per ray in this pass
   int G;    // rays per 128-row tile (S <= 128) else 1
   int T;    // tiles per ray group (ceil(S/128) when S > 128) else 1
-  int NG;   // ray groups = ceil(NR / G)
+  int NG;   // ray groups handled by this launch (ceil(NR / G) unless the pass is chunked)
+  int group0;  // first ray group of this launch
   const float* origins;   // [NR][3]
   const float* dirs;      // [NR][3]
   const float* z_near;    // [B]

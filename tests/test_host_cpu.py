@@ -84,3 +84,24 @@ def test_unsupported_configs_fail_loudly():
         mod.DensityDecoderMlp(mod.DensityDecoderMlpCfg("density_mlp", mod.MlpCfg(n_blocks=4)), 512)
     with pytest.raises(NotImplementedError):
         mod.get_action_decoder(type("C", (), {"name": "flow_mlp"})(), 8, 512)
+
+
+def test_gelu_fit():
+    """The one-MUFU GELU of xf_kernel (csrc/xf_head.cu, coefficients from tools/fit_gelu.py): fp32 evaluation
+    of the committed coefficients against the exact-erf nn.GELU in float64."""
+    import numpy as np
+    from scipy.special import erf
+
+    src = open(os.path.join(ROOT, "neural-jacobian-field_b200", "csrc", "xf_head.cu")).read()
+    m = re.search(r"constexpr float c0 = ([^;]+);", src)
+    c = np.array([float(x.split("=")[-1].strip().rstrip("f")) for x in m.group(0)[len("constexpr float "):-1].split(",")],
+                 dtype=np.float32)
+    assert c.shape == (7,)
+    v = np.linspace(-12, 12, 600001).astype(np.float32)
+    a = np.minimum(np.abs(v), np.float32(6.0))
+    q = np.full_like(a, c[6])
+    for k in range(5, -1, -1):
+        q = q * a + c[k]
+    g = np.maximum(v, 0) - np.float32(0.5) * (np.abs(v) * np.exp2(-q))
+    ref = 0.5 * v.astype(np.float64) * (1 + erf(v.astype(np.float64) / np.sqrt(2)))
+    assert np.abs(g - ref).max() < 5e-7

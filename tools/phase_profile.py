@@ -60,6 +60,17 @@ def main():
         tot = sum(cyc)
         out[name] = {"avg_kcycles_per_warp": {p: round(c / n_warps / 1e3, 1) for p, c in zip(PH, cyc)},
                      "share": {p: round(c / max(tot, 1), 3) for p, c in zip(PH, cyc)}, "ms": ms}
+    if hasattr(L, "njf_xf_prof_read"):
+        xb = (ctypes.c_ulonglong * 8)()
+        L.njf_xf_prof_read.restype = ctypes.c_int
+        L.njf_xf_prof_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        _lib.check(L.njf_xf_prof_read(xb, 1))
+        xph = ["load+ln0", "wait_acc", "layernorm", "softmax", "gelu", "jacobian+composite"]
+        cyc = list(xb)[:len(xph)]
+        tot = sum(cyc)
+        out["xf_kernel"] = {"avg_kcycles_per_warp": {p: round(c / n_warps / 1e3 / 3, 1) for p, c in zip(xph, cyc)},
+                            "share": {p: round(c / max(tot, 1), 3) for p, c in zip(xph, cyc)},
+                            "note": "three renders accumulated; 16 row warps x 148 SMs"}
     print(json.dumps(out, indent=1))
 
 
