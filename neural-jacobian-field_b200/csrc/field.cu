@@ -6,6 +6,8 @@
 //   field/T  : lin_in | q_enc | (fc_0, fc_1) x5 | lin_out(16) | color1 | color2
 //   head/T   : (M1, M2, W1, W2) x3 | jhead(N=32)            (xf_kernel, resident in shared memory)
 //   field/M  : lin_in | (fc_0, fc_1) x5 | lin_out(16) | color1 | color2 | lin_in(jac) | (fc_0, fc_1) x5 | lin_out(N=32)
+#include <cuda_fp16.h>
+
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -64,25 +66,40 @@ struct Builder {
   }
 };
 
-// The kernels write the positional encoding as [sin block (30) | 0 0 | cos block (30) | 0 0] so that each
-// of a row's two threads owns one block with compile-time (dim, freq) per column (write_posenc);
-// the 60 encoding columns of W[n][ld] are re-ordered to match (K order is free on the weight side).
+// The kernels write the encoder input as two K-blocks (write_posenc):
+//   K-block 0: [sin block (30) | 0 0 | cos block (30) | 0 0]  -- each of a row's two threads owns one block with
+//              compile-time (dim, freq) per column; the 60 encoding columns of W[n][ld] are re-ordered to match;
+//   K-block 1, first 16 columns: [x_hi(3) | x_lo(3) | x_hi(3) | 0...] -- the raw xyz input split into an fp16
+//              head and an fp16 remainder; the matching weight columns are [W | W | W_lo] (W rounds to its fp16
+//              head W_hi when packed, W_lo = W - W_hi), so x.W = x_hi W_hi + x_lo W_hi + x_hi W_lo keeps ~22 bits
+//              although every operand is fp16 (kStepK16Tail: one extra K=16 MMA).
 std::vector<float> enc_cols(const float* w, int n, int ld) {
-  std::vector<float> o(static_cast<size_t>(n) * 64, 0.f);
+  std::vector<float> o(static_cast<size_t>(n) * 128, 0.f);
   if (w)
-    for (int r = 0; r < n; ++r)
-      for (int c = 0; c < 60; ++c) o[r * 64 + (c < 30 ? c : c + 2)] = w[static_cast<size_t>(r) * ld + c];
+    for (int r = 0; r < n; ++r) {
+      float* orow = o.data() + static_cast<size_t>(r) * 128;
+      const float* wr = w + static_cast<size_t>(r) * ld;
+      for (int c = 0; c < 60; ++c) orow[c < 30 ? c : c + 2] = wr[c];
+      for (int d = 0; d < 3; ++d) {
+        const float wv = wr[60 + d];
+        const uint16_t hb = f32_to_f16_bits(wv);
+        __half hh;
+        std::memcpy(&hh, &hb, 2);
+        orow[64 + d] = wv;
+        orow[67 + d] = wv;
+        orow[70 + d] = wv - __half2float(hh);
+      }
+    }
   return o;
 }
 
 // lin_in step + hoisted lin_z rows; the block steps are appended separately (program order differs
 // between heads).
-void trunk_lin_in(Builder& b, Program& prog, const std::string& p, TrunkTab& tab, int flags = 0) {
+void trunk_lin_in(Builder& b, Program& prog, const std::string& p, int flags = 0) {
   const float* w = b.get(p + ".lin_in.weight", 128 * 63);
   const float* bi = b.get(p + ".lin_in.bias", 128);
-  b.step(prog, w ? enc_cols(w, 128, 63).data() : nullptr, 128, 64, 64, 128, 64, /*d_col=*/0, /*acc=*/0, flags);
-  if (w && bi)
-    for (int c = 0; c < 128; ++c) tab.e0[c] = make_float4(w[c * 63 + 60], w[c * 63 + 61], w[c * 63 + 62], bi[c]);
+  b.step(prog, w ? enc_cols(w, 128, 63).data() : nullptr, 128, 128, 128, 128, 128, /*d_col=*/0, /*acc=*/0,
+         flags | kStepK16Tail, bi, true);
   for (int k = 0; k < 3; ++k) {
     const float* wz = b.get(p + ".lin_z." + std::to_string(k) + ".weight", 128 * 512);
     const float* bz = b.get(p + ".lin_z." + std::to_string(k) + ".bias", 128);
@@ -130,25 +147,23 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
   // hoist channel order: proposal nets (384 each), then the main map (dens 384 + head part)
   for (int i = 0; i < desc->n_proposal; ++i) {
     const std::string p = "proposal_networks." + std::to_string(i) + ".density_head";
-    trunk_lin_in(b, f->prop_prog[i], p, f->prop_trunk[i]);
+    trunk_lin_in(b, f->prop_prog[i], p);
     trunk_blocks(b, f->prop_prog[i], p, 1, 16);
   }
   Program& fp = f->field_prog;
   std::vector<uint8_t> xf_blob;
   // transformer head: lin_in and q_enc read the same A tile (the positional encoding) and are
   // covered by ONE accumulator commit (two arrivals on one mbarrier phase would be unsafe)
-  trunk_lin_in(b, fp, "decoder.density_head", f->dens_trunk,
-               desc->head == NJF_HEAD_TRANSFORMER ? kStepNoCommit : 0);
+  trunk_lin_in(b, fp, "decoder.density_head", desc->head == NJF_HEAD_TRANSFORMER ? kStepNoCommit : 0);
   if (desc->head == NJF_HEAD_TRANSFORMER) {
     f->ch_main = 448;
     const float* wq = b.get("decoder.jacobian_query_mlp.weight", 64 * 575);
     const float* bq = b.get("decoder.jacobian_query_mlp.bias", 64);
     const float* emb = b.get("decoder.jacobian_index_embedding", static_cast<int64_t>(A) * 64);
-    b.step(fp, wq ? enc_cols(wq, 64, 575).data() : nullptr, 64, 64, 64, 64, 64, /*d_col=*/128, 0, kStepReuseA);
+    b.step(fp, wq ? enc_cols(wq, 64, 575).data() : nullptr, 64, 128, 128, 64, 128, /*d_col=*/128, 0,
+           kStepReuseA | kStepK16Tail, bq, true);
     if (wq && bq) {
-      for (int c = 0; c < 64; ++c)
-        f->head.q_e0[c] = make_float4(wq[c * 575 + 60], wq[c * 575 + 61], wq[c * 575 + 62], bq[c]);
-      // hoisted query channels: the 512 feature columns of jacobian_query_mlp (bias lives in q_e0)
+      // hoisted query channels: the 512 feature columns of jacobian_query_mlp (its bias rides in the q_enc step)
       for (int c = 0; c < 64; ++c) b.hoist_w.insert(b.hoist_w.end(), wq + c * 575 + 63, wq + c * 575 + 575);
       b.hoist_b.insert(b.hoist_b.end(), 64, 0.f);
     }
@@ -240,7 +255,7 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
   }
   if (desc->head == NJF_HEAD_MLP) {
     f->ch_main = 768;
-    trunk_lin_in(b, fp, "decoder.jacobian_head", f->jac_trunk);
+    trunk_lin_in(b, fp, "decoder.jacobian_head");
     trunk_blocks(b, fp, "decoder.jacobian_head", 3 * A, 32);
   }
   if (!b.err.empty()) {

@@ -5,16 +5,9 @@
 
 namespace njf {
 
-// fp32 side tables.  They travel BY VALUE inside the kernel parameter structs (constant bank:
-// every epilogue access is warp-uniform, so it is a broadcast constant-cache read instead of an
-// L1-thrashed global load).
-// All other biases ride inside the weight images (kStepBias) and are accumulated by the tensor core.
-struct TrunkTab {
-  float4 e0[128];       // (W_in[:,60], W_in[:,61], W_in[:,62], b_in): raw-xyz columns kept in fp32
-};
-struct HeadTab {
-  float4 q_e0[64];      // (Wq[:,60..62], bq) of jacobian_query_mlp
-};
+// fp32 side table.  It travels BY VALUE inside the kernel parameter struct (constant bank: every access is
+// warp-uniform, so it is a broadcast constant-cache read).  All biases ride inside the weight images
+// (kStepBias) and are accumulated by the tensor core.
 struct ColorTab {
   float w3[3 * 64], b3[4];   // last colour layer (3 outputs) stays on the fp32 pipes
 };
@@ -59,11 +52,8 @@ struct NjfField {
   int ch_total = 0;
   njf::Program prop_prog[NJF_MAX_LEVELS];
   const uint8_t* prop_blob[NJF_MAX_LEVELS];
-  njf::TrunkTab prop_trunk[NJF_MAX_LEVELS];
   njf::Program field_prog;
   const uint8_t* field_blob = nullptr;
-  njf::TrunkTab dens_trunk, jac_trunk;
-  njf::HeadTab head;
   njf::ColorTab color;
 };
 

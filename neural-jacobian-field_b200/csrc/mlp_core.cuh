@@ -49,6 +49,9 @@ constexpr uint16_t kStepReuseA = 1, kStepNoCommit = 2;
 // extra MMA multiplies it with the CTA's constant "ones" A block (column 0 = 1), so the bias is
 // accumulated by the tensor core and the epilogues carry no bias loads / adds.
 constexpr uint16_t kStepBias = 4;
+// kStepK16Tail: of the LAST K-block only the first 16 columns are multiplied (one MMA instead of four):
+// lin_in / query-MLP steps carry the raw-xyz input there as hi/lo fp16 pairs (render.cuh write_posenc)
+constexpr uint16_t kStepK16Tail = 8;
 struct Program {
   int nsteps;
   MmaStep steps[kMaxSteps];
@@ -162,8 +165,8 @@ __device__ __forceinline__ void issuer_role(const CtaCtx& c, const Program& prog
         const uint32_t w0 = w_base + stage * kStageBytes;
         uint32_t acc = st.acc;
         for (int kb = 0; kb < st.kblocks; ++kb) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          const int nk = ((st.flags & kStepK16Tail) && kb == st.kblocks - 1) ? 1 : 4;
+          for (int k = 0; k < nk; ++k) {
             umma_f16(d_tmem, make_sw128_desc(a0 + kb * kAKbStride + k * 32),
                      make_sw128_desc(w0 + kb * w_kb_stride + k * 32), idesc, acc);
             acc = 1;

@@ -63,7 +63,6 @@ __device__ __forceinline__ float tile_weights(EpiCtx& e, SlotScratch* sc, const 
 struct ProposalParams {
   Program prog;
   const uint8_t* blob;
-  TrunkTab trunk;
   PassGeom g;
   int n_out;             // samples of the next level (PDF draws n_out+1 bin edges)
   const float* u;        // [n_out+1] shared or per ray
@@ -116,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
         PROF(e, kPSetup);
         gather_segment<128>(e, g, sc->taps, 0);
         epi_wait_acc(e);
-        trunk_blocks_epilogue(e, g, p.trunk, 0, rs, sc->taps);
+        trunk_blocks_epilogue(e, g, 0, sc->taps);
         float dd = 0.f;
         if (e.half == 0) {
           uint32_t r[16];
@@ -141,8 +140,6 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
 struct FieldParams {
   Program prog;
   const uint8_t* blob;
-  TrunkTab dens, jac;
-  HeadTab head;
   ColorTab color;
   PassGeom g;
   int head_kind;   // NJF_HEAD_*
@@ -167,10 +164,10 @@ __device__ __forceinline__ void ld_acc32(const EpiCtx& e, float (&v)[32]) {
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 // Query embedding of the cross-attention head (action_decoder_jacobian.py:423-430):
-//   q0 = W_q[:, :60] . enc (tensor core, q_enc step) + hoisted W_q[:, 63:] . feat + W_q[:, 60:63] . xyz + b_q
+//   q0 = W_q . [enc | xyz] + b_q (tensor core, q_enc step) + hoisted W_q[:, 63:] . feat
 // Each of the row's two threads owns 32 of the 64 values and streams them to the `qs` scratch that
 // xf_kernel consumes ([tile][16 chunks of 4][128 rows] float4: warp stores are 512 contiguous bytes).
-__device__ __forceinline__ void store_query_stream(const EpiCtx& e, const HeadTab& H, const RowState& rs, float4* qs_tile) {
+__device__ __forceinline__ void store_query_stream(const EpiCtx& e, float4* qs_tile) {
   float x[32];
   ld_acc32(e, x);
 #pragma unroll
@@ -183,11 +180,6 @@ __device__ __forceinline__ void store_query_stream(const EpiCtx& e, const HeadTa
       x[8 * j + 2 * t] += f.x;
       x[8 * j + 2 * t + 1] += f.y;
     }
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float4 q = H.q_e0[32 * e.half + j];
-    x[j] += fmaf(q.z, rs.cam[2], fmaf(q.y, rs.cam[1], fmaf(q.x, rs.cam[0], q.w)));
   }
   float4* dst = qs_tile + (8 * e.half) * kRows + e.row;
 #pragma unroll
@@ -275,12 +267,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         if (p.head_kind == NJF_HEAD_TRANSFORMER) {
           gather_segment<64>(e, g, sc->taps, 384);
           epi_wait_acc(e);
-          if (p.qs) store_query_stream(e, p.head, rs, p.qs + tidx * 16 * kRows);
+          if (p.qs) store_query_stream(e, p.qs + tidx * 16 * kRows);
           PROF(e, kPHead);
         }
         gather_segment<128>(e, g, sc->taps, 0);
         if (p.head_kind != NJF_HEAD_TRANSFORMER) epi_wait_acc(e);
-        trunk_blocks_epilogue(e, g, p.dens, 0, rs, sc->taps);
+        trunk_blocks_epilogue(e, g, 0, sc->taps);
         // lin_out: 15 geometry features + density pre-activation (action_decoder_jacobian.py:106-112)
         PROF(e, kPOther);
         float sigma = 0.f;
@@ -350,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           epi_publish(e);  // -> lin_in (jacobian head)
           gather_segment<128>(e, g, sc->taps, 384);
           epi_wait_acc(e);
-          trunk_blocks_epilogue(e, g, p.jac, 384, rs, sc->taps);
+          trunk_blocks_epilogue(e, g, 384, sc->taps);
           uint32_t r[16];
           tmem_ld16(e.tmem + 128 + 16 * e.half, r);
           tmem_ld_wait();
@@ -912,7 +904,6 @@ extern "C" int njf_proposal_pass(const NjfField* f, const NjfCameras* cams, cons
   ProposalParams p{};
   p.prog = f->prop_prog[level];
   p.blob = f->prop_blob[level];
-  p.trunk = f->prop_trunk[level];
   if (make_geom(f, cams, a, a->s_prop[level], bins_in, bins_in_stride, map_of(f, a, level), f->ch_prop, p.g)) return 1;
   p.n_out = (level + 1 < a->n_levels) ? a->s_prop[level + 1] : a->s_nerf;
   if (p.n_out < 1 || p.n_out > 512) NJF_FAIL("n_out %d unsupported", p.n_out);
@@ -960,9 +951,6 @@ extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const N
   FieldParams p{};
   p.prog = f->field_prog;
   p.blob = f->field_blob;
-  p.dens = f->dens_trunk;
-  p.jac = f->jac_trunk;
-  p.head = f->head;
   p.color = f->color;
   if (make_geom(f, cams, a, a->s_nerf, bins, bins_stride, map_of(f, a, -1), f->ch_main, p.g)) return 1;
   p.head_kind = f->desc.head;
@@ -995,9 +983,6 @@ extern "C" int njf_query_points(const NjfField* f, const float* ctxt_w2c, const 
   FieldParams p{};
   p.prog = f->field_prog;
   p.blob = f->field_blob;
-  p.dens = f->dens_trunk;
-  p.jac = f->jac_trunk;
-  p.head = f->head;
   p.color = f->color;
   PassGeom& g = p.g;
   g.NR = B * N; g.R = N; g.S = 1; g.G = kRows; g.T = 1;

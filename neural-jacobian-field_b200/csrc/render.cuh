@@ -141,12 +141,12 @@ __device__ __forceinline__ float sin_cw(float t) {
   return __sinf(r);
 }
 
-// NeRFEncoding(63) of the camera-space point into A-tile K-block 0.  nerfstudio's column order is
-// [sin block | cos block], each dim-major / freq-minor, cos(t) evaluated as sin(t + pi/2); here the
-// row's thread of column half 0 writes the 30 sin columns (+2 zero columns) and the thread of half 1
-// the 30 cos columns (+2 zeros), so (dim, freq) of every column is a compile-time constant; the
-// weight packer re-orders lin_in / query-MLP columns to match (field.cu enc_cols).  The raw-xyz
-// columns are applied in fp32 by the first epilogue.
+// NeRFEncoding(63) of the camera-space point into the A tile.  nerfstudio's column order is
+// [sin block | cos block | x], each block dim-major / freq-minor, cos(t) evaluated as sin(t + pi/2).  Here
+// the row's thread of column half 0 writes the 30 sin columns (+2 zero columns) of K-block 0 and the thread
+// of half 1 the 30 cos columns (+2 zeros), so (dim, freq) of every column is a compile-time constant; the
+// raw xyz goes to the first 16 columns of K-block 1 as [x_hi | x_lo | x_hi | 0] (fp16 head + fp16 remainder,
+// ~22 bits through an fp16 tensor-core product).  field.cu enc_cols packs lin_in / query-MLP weights to match.
 __device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)[3], bool valid,
                                              int debug = 0) {
   if (debug & 2) valid = false;
@@ -164,6 +164,23 @@ __device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)
 #pragma unroll
   for (int j = 0; j < 16; ++j) pk[j] = valid ? pack_f16x2(v[2 * j], v[2 * j + 1]) : 0u;
   a_store32(e, 32 * e.half, pk);
+  if (e.half == 0) {
+    float hi[3], lo[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const __half h = __ushort_as_half(static_cast<unsigned short>(pack_f16x2(cam[i], 0.f) & 0xffffu));  // satfinite
+      hi[i] = __half2float(h);
+      lo[i] = cam[i] - hi[i];
+    }
+    uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) {
+      c0 = make_uint4(pack_f16x2(hi[0], hi[1]), pack_f16x2(hi[2], lo[0]), pack_f16x2(lo[1], lo[2]), pack_f16x2(hi[0], hi[1]));
+      c1.x = pack_f16x2(hi[2], 0.f);
+    }
+    uint8_t* rowp = e.a_tile + kAKbStride + e.row * 128;
+    *reinterpret_cast<uint4*>(rowp + ((0 ^ (e.row & 7)) << 4)) = c0;
+    *reinterpret_cast<uint4*>(rowp + ((1 ^ (e.row & 7)) << 4)) = c1;
+  }
 }
 
 // ----------------------------------------------------------------------------- gather
@@ -255,54 +272,13 @@ __device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, con
 }
 
 // ----------------------------------------------------------------------------- trunk epilogues
-// x[c0..c0+32) += (W_in[:,60:63] . cam + b_in) + staged segment ; write back ; ReLU -> A tile
-__device__ __forceinline__ void epi_x_first(const EpiCtx& e, int c0, const float4* e0,
-                                            const float (&cam)[3]) {
-  uint32_t r[32];
-  tmem_ld32(e.tmem + c0, r);
-  tmem_ld_wait();
-  float v[32];
-  const float2 cx = make_float2(cam[0], cam[0]), cy = make_float2(cam[1], cam[1]), cz = make_float2(cam[2], cam[2]);
-#pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    const float4 q0 = e0[c0 + j], q1 = e0[c0 + j + 1];
-    float2 t = ffma2(make_float2(q0.x, q1.x), cx, make_float2(q0.w, q1.w));
-    t = ffma2(make_float2(q0.y, q1.y), cy, t);
-    t = ffma2(make_float2(q0.z, q1.z), cz, t);
-    t = fadd2(t, make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
-    v[j] = t.x;
-    v[j + 1] = t.y;
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4 q = *reinterpret_cast<const uint4*>(e.tz + tz_offset(e.row, (c0 >> 3) + j));
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 s2 = fadd2(make_float2(v[8 * j + 2 * t], v[8 * j + 2 * t + 1]), __half22float2(h[t]));
-      v[8 * j + 2 * t] = s2.x;
-      v[8 * j + 2 * t + 1] = s2.y;
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(v[j]);
-  tmem_st32(e.tmem + c0, r);
-  uint32_t p[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-    p[j] = pack_relu_f16x2(v[2 * j], v[2 * j + 1]);
-  a_store32(e, c0, p);
-  tmem_st_wait();
-}
-
 // The 10 residual-block steps + lin_out of one ResnetFC trunk, epilogue side.  Pre-conditions:
-// lin_in's accumulator wait has completed (x = W_in[:, :60] . enc in TMEM) and segment 0 of this
+// lin_in's accumulator wait has completed (x = W_in . [enc | xyz] + b_in in TMEM) and segment 0 of this
 // trunk's hoisted channels is in the staging buffer.  Leaves the lin_out accumulator (bias NOT
 // yet added) in TMEM columns [128, 128+n_out).
-__device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom& g, const TrunkTab& tab, int seg_ch0,
-                                                      const RowState& rs, const TapEntry* taps) {
-  // E0: X_0 = lin_in + b_in + raw-xyz + tz_0
-  for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_first(e, c0, tab.e0, rs.cam);
+__device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom& g, int seg_ch0, const TapEntry* taps) {
+  // E0: X_0 = lin_in(enc, xyz) + b_in + tz_0
+  for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<true>(e, c0);
   epi_publish(e);  // -> fc_0 (block 0)
 #pragma unroll 1
   for (int k = 0; k < 5; ++k) {

@@ -116,34 +116,42 @@ __device__ __forceinline__ void xf_ln_to_a(const XfEpi& e, float (&x)[64]) {
   }
   const float2 qt = fadd2(fadd2(q[0], q[1]), fadd2(q[2], q[3]));
   const float rstd = rsqrtf((qt.x + qt.y) * (1.f / 64.f) + 1e-5f);
+  const float2 rs2 = make_float2(rstd, rstd), zero = make_float2(0.f, 0.f);
   uint32_t pk[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) pk[j] = pack_f16x2(x[2 * j] * rstd, x[2 * j + 1] * rstd);
+  for (int j = 0; j < 32; ++j) {
+    const float2 y = ffma2(make_float2(x[2 * j], x[2 * j + 1]), rs2, zero);
+    pk[j] = pack_f16x2(y.x, y.y);
+  }
   xf_store_a(e, pk);
 }
 // softmax over the A real keys of each of the 8 heads (heads padded to 8 columns; the logits arrive
 // pre-multiplied by log2(e), so exp is a bare ex2)
 template <int A>
 __device__ __forceinline__ void xf_softmax_to_a(const XfEpi& e, float (&lg)[64]) {
+  uint32_t pk[32];
 #pragma unroll
   for (int h = 0; h < 8; ++h) {
     float m = lg[h * 8];
 #pragma unroll
     for (int a = 1; a < A; ++a) m = fmaxf(m, lg[h * 8 + a]);
-    float s = 0.f;
+    const float2 nm = make_float2(-m, -m);
+    float2 ev[4];
 #pragma unroll
-    for (int a = 0; a < A; ++a) {
-      const float ev = ex2_approx(lg[h * 8 + a] - m);
-      lg[h * 8 + a] = ev;
-      s += ev;
+    for (int a2 = 0; a2 < 4; ++a2) {
+      const float2 d = fadd2(make_float2(lg[h * 8 + 2 * a2], lg[h * 8 + 2 * a2 + 1]), nm);
+      ev[a2].x = (2 * a2 < A) ? ex2_approx(d.x) : 0.f;
+      ev[a2].y = (2 * a2 + 1 < A) ? ex2_approx(d.y) : 0.f;
     }
-    const float inv = __fdividef(1.f, s);
+    const float2 s2 = fadd2(fadd2(ev[0], ev[1]), fadd2(ev[2], ev[3]));
+    const float inv = __fdividef(1.f, s2.x + s2.y);
+    const float2 inv2 = make_float2(inv, inv), zero = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int a = 0; a < 8; ++a) lg[h * 8 + a] = (a < A) ? lg[h * 8 + a] * inv : 0.f;
+    for (int a2 = 0; a2 < 4; ++a2) {
+      const float2 pr = ffma2(ev[a2], inv2, zero);
+      pk[h * 4 + a2] = pack_f16x2(pr.x, pr.y);
+    }
   }
-  uint32_t pk[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) pk[j] = pack_f16x2(lg[2 * j], lg[2 * j + 1]);
   xf_store_a(e, pk);
 }
 // exact-erf GELU (nn.GELU default) as  relu(v) - |v|/2 * erfc(|v|/sqrt2),  erfc(a/sqrt2) = 2^-Q(a) with a
