@@ -787,7 +787,13 @@ int launch_field(const NjfField* f, FieldParams& p, cudaStream_t stream) {
   float* jac = p.jac_out;
   int gpc = NGtot;  // groups per launch
   if (xf) {
-    gpc = kXfMaxTiles / T;
+    static const int max_tiles = [] {  // NJF_XF_MAX_TILES: smaller launch pairs (tests of the chunked path)
+      const char* v = getenv("NJF_XF_MAX_TILES");
+      const int n = v ? atoi(v) : 0;
+      return n > 0 ? n : kXfMaxTiles;
+    }();
+    gpc = max_tiles / T;
+    if (gpc < 1) gpc = 1;
     if (gpc > NGtot) gpc = NGtot;
     const size_t tiles = static_cast<size_t>(gpc) * T;
     const size_t need = tiles * (16 * kRows * sizeof(float4) + kRows * sizeof(float));

@@ -305,6 +305,25 @@ def test_full_size_properties():
     assert bool((r1.rgb.sum(-1) <= 3.0 * wts.sum(-1) + 1e-4).all())
 
 
+@pytest.mark.parametrize("R,s_prop,s_nerf,max_tiles", [(37, 24, 53, 3), (9, 64, 300, 2), (70, 32, 128, 5)])
+def test_chunked_field_pass_is_bit_identical(tmp_path, R, s_prop, s_nerf, max_tiles):
+    """Passes with more tiles than the hand-over scratch holds run as several field_kernel / xf_kernel launch
+    pairs over ray-group ranges (render.cu launch_field); NJF_XF_MAX_TILES shrinks the scratch so that small
+    scenes exercise that path.  Every output must be bit-identical to the single-launch result."""
+    import subprocess
+    import sys
+
+    outs = []
+    for tag, env in (("one", {}), ("chunked", {"NJF_XF_MAX_TILES": str(max_tiles)})):
+        out = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "_render_child.py"), out, str(R),
+                        str(s_prop), str(s_nerf)], check=True, env={**os.environ, **env},
+                       cwd=os.path.dirname(__file__), timeout=300)
+        outs.append(np.load(out))
+    for k in outs[0].files:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
 def test_bad_arguments_fail_loudly():
     from njf_b200 import _lib, api
     from njf_b200.render import render
