@@ -18,6 +18,7 @@ struct SlotScratch {
   float wrow[kRows];     // transmittance weight of each row (shared between the row's two threads)
   TapEntry taps[kRows];  // bilinear taps of the current tile
   float4 rgbp[kRows];    // colour-head partial dot products of the upper column half
+  float part[8][64];     // per-warp partial column sums of the composite
 };
 constexpr uint32_t kScratchSlotBytes = (sizeof(SlotScratch) + 15) & ~15u;
 constexpr uint32_t kSmemBytes = SmemMap::kScratch + kSlots * kScratchSlotBytes + 64 + 1024;
@@ -30,33 +31,60 @@ __device__ __forceinline__ uint32_t* cta_minmax(const CtaCtx& c) {
   return reinterpret_cast<uint32_t*>(c.smem + SmemMap::kScratch + kSlots * kScratchSlotBytes);
 }
 
-// transmittance weights of this tile's rows (RaySamples.get_weights, ray_samplers.py:77-101):
-// the h=0 thread of each row stores dd, one warp per ray scans (double accumulation), every
-// thread of the row gets the row's weight back.
+// transmittance weights of this tile's rows (RaySamples.get_weights, ray_samplers.py:77-101): the h=0 thread
+// of each row stores dd = delta * sigma; exclusive prefix sums are accumulated in double (like torch.cumsum on
+// CPU) and rounded to fp32 per element; every thread of the row returns the row's weight.
+//  * fast path (a warp's 32 rows belong to one ray: S a multiple of 32, or a long ray): ONE barrier; every warp
+//    reduces the ray's rows before its own and scans its own 32 rows with shuffles (both warps of a row quarter
+//    do this redundantly, so no second exchange is needed);
+//  * general path (several ragged rays per tile): one warp per ray scans, results go through shared memory.
 __device__ __forceinline__ float tile_weights(EpiCtx& e, SlotScratch* sc, const PassGeom& g, int tile,
                                               float dd, double& carry) {
   const int w8 = (threadIdx.x >> 5) & 7;
+  const int lane = threadIdx.x & 31;
   PROF(e, kPOther);
   if (e.half == 0) sc->dd[e.row] = dd;
   slot_bar(e);
-  if (g.T == 1) {
+  float w;
+  if (g.T > 1 || (g.S & 31) == 0) {
+    const int row0 = 32 * e.q;                                    // first row of this warp
+    const int ray0 = (g.T > 1) ? 0 : (row0 / g.S) * g.S;          // first row of the warp's ray inside the tile
+    double before = 0.0;                                          // sum of the ray's rows before this warp's
+    for (int r = ray0 + lane; r < row0; r += 32) before += static_cast<double>(sc->dd[r]);
+    double tot = 0.0;                                             // long ray: whole-tile sum for the carry
+    if (g.T > 1)
+      for (int r = lane; r < kRows; r += 32) tot += static_cast<double>(sc->dd[r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, o);
+      if (g.T > 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    }
+    const double own = static_cast<double>(sc->dd[e.row]);
+    double inc = own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const float cum = static_cast<float>(carry + before + (inc - own));
+    carry += tot;
+    w = (1.f - expf(-sc->dd[e.row])) * expf(-cum);
+  } else {
     for (int lr = w8; lr < g.G; lr += 8) {
       double c0 = 0.0;
       excl_scan_warp(sc->dd + lr * g.S, g.S, c0, sc->cum + lr * g.S);
     }
-  } else if (w8 == 0) {
-    const int n = min(kRows, g.S - tile * kRows);
-    excl_scan_warp(sc->dd, n, carry, sc->cum);
+    slot_bar(e);
+    if (e.half == 0) {
+      const float tr = expf(-sc->cum[e.row]);
+      const float alpha = 1.f - expf(-dd);
+      sc->wrow[e.row] = alpha * tr;
+    }
+    slot_bar(e);
+    w = sc->wrow[e.row];
   }
-  slot_bar(e);
-  if (e.half == 0) {
-    const float tr = expf(-sc->cum[e.row]);
-    const float alpha = 1.f - expf(-dd);
-    sc->wrow[e.row] = alpha * tr;
-  }
-  slot_bar(e);
   PROF(e, kPWeights);
-  return sc->wrow[e.row];
+  return w;
 }
 
 // ============================================================================= proposal pass
@@ -439,7 +467,34 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
             if (24 + lane < A3) p.jbar[static_cast<size_t>(ray) * A3 + 24 + lane] = s1;
           }
         };
-        if (g.T == 1) {
+        if (g.T > 1 || (g.S & 31) == 0) {
+          // fast path: every warp sums 16 rows (all of one ray), then one warp per ray adds the partials
+          const int wi = 4 * e.half + e.q;
+          float s0 = 0.f, s1 = 0.f;
+          colsum(16 * wi, 16, s0, s1);
+          sc->part[wi][lane] = s0;
+          sc->part[wi][32 + lane] = s1;
+          slot_bar(e);
+          if (g.T > 1) {
+            if (wi == 0) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                cs0 += sc->part[k][lane];
+                cs1 += sc->part[k][32 + lane];
+              }
+              if (tile == g.T - 1 && group < g.NR) emit(group, cs0, cs1);
+            }
+          } else if (wi < g.G) {
+            const int wpr = g.S >> 4;  // warps per ray
+            float t0 = 0.f, t1 = 0.f;
+            for (int k = 0; k < wpr; ++k) {
+              t0 += sc->part[wi * wpr + k][lane];
+              t1 += sc->part[wi * wpr + k][32 + lane];
+            }
+            const int ray = group * g.G + wi;
+            if (ray < g.NR) emit(ray, t0, t1);
+          }
+        } else {
           for (int lr = w8; lr < g.G; lr += 8) {
             const int ray = group * g.G + lr;
             if (ray >= g.NR) break;
@@ -447,11 +502,8 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
             colsum(lr * g.S, g.S, s0, s1);
             emit(ray, s0, s1);
           }
-        } else if (w8 == 0) {
-          colsum(0, min(kRows, g.S - tile * kRows), cs0, cs1);
-          if (tile == g.T - 1 && group < g.NR) emit(group, cs0, cs1);
+          slot_bar(e);
         }
-        slot_bar(e);
         PROF(e, kPComposite);
       }
     }
