@@ -272,6 +272,14 @@ __device__ __forceinline__ void a_store32(const EpiCtx& e, int c0, const uint32_
     *reinterpret_cast<uint4*>(base + (((ch0 + j) ^ (e.row & 7)) << 4)) = v;
   }
 }
+// 8 packed words -> A tile columns [c0, c0+16) (c0 a multiple of 16)
+__device__ __forceinline__ void a_store16(const EpiCtx& e, int c0, const uint32_t (&p)[8]) {
+  uint8_t* base = e.a_tile + (c0 >> 6) * kAKbStride + e.row * 128;
+  const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    *reinterpret_cast<uint4*>(base + (((ch0 + j) ^ (e.row & 7)) << 4)) = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+}
 // zero-fill A tile columns [c0, c0+32)
 __device__ __forceinline__ void a_zero32(const EpiCtx& e, int c0) {
   uint8_t* base = e.a_tile + (c0 >> 6) * kAKbStride + e.row * 128;

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
         gather_segment<128>(e, g, sc->taps, 0);
         epi_wait_acc(e);
         trunk_blocks_epilogue(e, g, 0, sc->taps);
+        epi_wait_acc(e);  // lin_out accumulator ready
         float dd = 0.f;
         if (e.half == 0) {
           uint32_t r[16];
@@ -301,9 +302,17 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         gather_segment<128>(e, g, sc->taps, 0);
         if (p.head_kind != NJF_HEAD_TRANSFORMER) epi_wait_acc(e);
         trunk_blocks_epilogue(e, g, 0, sc->taps);
-        // lin_out: 15 geometry features + density pre-activation (action_decoder_jacobian.py:106-112)
+        // lin_out: 15 geometry features + density pre-activation (action_decoder_jacobian.py:106-112); colour head
+        // input [geo15 | sh16 | 0...] (:208).  The h=0 thread handles the geometry half (columns 0..15: geo, sh0),
+        // the h=1 thread the view direction (columns 16..31: sh1..15, 0) -- its loads are issued before the wait.
         PROF(e, kPOther);
         float sigma = 0.f;
+        float dv[3] = {0.f, 0.f, 1.f};
+        if (e.half == 1 && g.dirs) {
+          const float* dp = g.dirs + static_cast<size_t>(valid ? rs.ray : 0) * 3;
+          dv[0] = __ldg(dp); dv[1] = __ldg(dp + 1); dv[2] = __ldg(dp + 2);
+        }
+        epi_wait_acc(e);  // lin_out accumulator ready
         if (e.half == 0) {
           float geo[16];
           uint32_t r[16];
@@ -317,23 +326,19 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
 #pragma unroll
             for (int j = 0; j < 15; ++j) gp[j] = geo[j];
           }
-          // colour head input [geo15 | sh16 | 0...] (action_decoder_jacobian.py:208)
-          float sh[16];
-          if (g.dirs) {
-            const float* dp = g.dirs + static_cast<size_t>(valid ? rs.ray : 0) * 3;
-            sh16(__ldg(dp), __ldg(dp + 1), __ldg(dp + 2), sh);
-          } else {
-            sh16(0.f, 0.f, 1.f, sh);
-          }
-          uint32_t pk[16];
+          uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 7; ++j) pk[j] = pack_f16x2(geo[2 * j], geo[2 * j + 1]);
-          pk[7] = pack_f16x2(geo[14], sh[0]);
-#pragma unroll
-          for (int j = 0; j < 7; ++j) pk[8 + j] = pack_f16x2(sh[1 + 2 * j], sh[2 + 2 * j]);
-          pk[15] = pack_f16x2(sh[15], 0.f);
-          a_store32(e, 0, pk);
+          pk[7] = pack_f16x2(geo[14], 0.28209479177387814f);  // SH band 0 is a constant
+          a_store16(e, 0, pk);
         } else {
+          float sh[16];
+          sh16(dv[0], dv[1], dv[2], sh);
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) pk[j] = pack_f16x2(sh[1 + 2 * j], sh[2 + 2 * j]);
+          pk[7] = pack_f16x2(sh[15], 0.f);
+          a_store16(e, 16, pk);
           a_zero32(e, 32);
         }
         epi_publish(e);  // -> color1
@@ -371,6 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           gather_segment<128>(e, g, sc->taps, 384);
           epi_wait_acc(e);
           trunk_blocks_epilogue(e, g, 384, sc->taps);
+          epi_wait_acc(e);
           uint32_t r[16];
           tmem_ld16(e.tmem + 128 + 16 * e.half, r);
           tmem_ld_wait();

@@ -274,8 +274,8 @@ __device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, con
 // ----------------------------------------------------------------------------- trunk epilogues
 // The 10 residual-block steps + lin_out of one ResnetFC trunk, epilogue side.  Pre-conditions:
 // lin_in's accumulator wait has completed (x = W_in . [enc | xyz] + b_in in TMEM) and segment 0 of this
-// trunk's hoisted channels is in the staging buffer.  Leaves the lin_out accumulator (bias NOT
-// yet added) in TMEM columns [128, 128+n_out).
+// trunk's hoisted channels is in the staging buffer.  Ends with lin_out issued: after the caller's
+// epi_wait_acc its accumulator (bias included) is in TMEM columns [128, 128+n_out).
 __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom& g, int seg_ch0, const TapEntry* taps) {
   // E0: X_0 = lin_in(enc, xyz) + b_in + tz_0
   for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<true>(e, c0);
@@ -298,7 +298,7 @@ __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom&
     epi_publish(e);  // -> fc_0 (block k+1) or lin_out
   }
   PROF(e, kPEpi);
-  epi_wait_acc(e);  // lin_out accumulator ready
+  // the caller waits for the lin_out accumulator (it may issue independent loads first)
 }
 
 // ----------------------------------------------------------------------------- per-ray scans (one warp)
