@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(160, 1) roundtrip(int n, int kblocks, int iter
     if ((threadIdx.x & 31) == 0) {
       const uint32_t idesc = make_idesc_f16(n);
       uint32_t par = 0;
-      for (int it = 0; it < iters; ++it) {
+      for (int it = 0; it < ((mode & 8) ? 0 : iters); ++it) {
         wait_mode(&bars[0], par, mode & 1);
         par ^= 1u;
         tc_fence_after();
@@ -105,10 +105,23 @@ __global__ void __launch_bounds__(160, 1) roundtrip(int n, int kblocks, int iter
   } else {
     uint32_t par = 0, acc = 0;
     const uint32_t t0 = tm + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t idesc = make_idesc_f16(n);
     for (int it = 0; it < iters; ++it) {
       if (!(mode & 4)) fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&bars[0]);
+      if (mode & 8) {  // no issuer thread: the epilogue group meets at a named barrier, its first thread issues
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 0) {
+          tc_fence_after();
+          for (int kb = 0; kb < kblocks; ++kb)
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tm, make_sw128_desc(smem_u32(sA) + kb * 16384 + k * 32),
+                       make_sw128_desc(smem_u32(sB) + kb * n * 128 + k * 32), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&bars[1]);
+        }
+      } else {
+        mbar_arrive(&bars[0]);
+      }
       wait_mode(&bars[1], par, mode & 2);
       par ^= 1u;
       tc_fence_after();
@@ -144,13 +157,13 @@ int main() {
              bytes / h[0], static_cast<double>(h[0]) / (iters * per_wait));
     }
   cudaFuncSetAttribute(roundtrip, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
-  for (int mode = 0; mode < 8; ++mode)
+  for (int mode : {0, 8, 10})
     for (int work : {0, 2})
       for (auto nk : {std::pair<int, int>{128, 2}, {16, 1}}) {
         roundtrip<<<148, 160, 70000>>>(nk.first, nk.second, 2000, work, mode, d);
         cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-        printf("roundtrip mode=%d (issuer-spin=%d epi-spin=%d no-proxy-fence=%d) N=%3d K=%3d tmem_ld_chunks=%d : %.0f cyc/iter\n", mode,
-               mode & 1, (mode >> 1) & 1, (mode >> 2) & 1, nk.first, nk.second * 64, work, h[0] / 2000.0);
+        printf("roundtrip mode=%d (issuer-spin=%d epi-spin=%d no-proxy-fence=%d self-issue=%d) N=%3d K=%3d tmem_ld_chunks=%d : %.0f cyc/iter\n", mode,
+               mode & 1, (mode >> 1) & 1, (mode >> 2) & 1, (mode >> 3) & 1, nk.first, nk.second * 64, work, h[0] / 2000.0);
       }
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
