@@ -152,6 +152,13 @@ int njf_point_features(const float* feat_nchw, const float* ctxt_w2c, const floa
                        int B, int N, int C, int Hf, int Wf, float* xyz_features, float* pixel_aligned_features,
                        void* stream);
 
+/* ---- ray bundle of a view (rendering/geometry.py:117-134 get_pixel_coordinates, :170-203 get_world_rays_with_z,
+ * models/model.py:215-226): k_norm [B][9] normalised intrinsics, c2w [B][16]; coords_xy [B][R][2] normalised pixel
+ * coordinates, or NULL to generate the H x W grid of pixel centres in the reference's order (row-major, x fastest;
+ * R must equal H*W).  origins / dirs [B][R][3]; z [B][R] (camera-space z of the unit direction) may be NULL. */
+int njf_make_rays(const float* k_norm, const float* c2w, const float* coords_xy, int B, int R, int H, int W,
+                  float* origins, float* dirs, float* z, void* stream);
+
 /* ---- PDFSampler alone (rendering/ray_samplers.py:351-451, eval/train u supplied by the caller) */
 int njf_pdf_sample(const float* weights, const float* bins_in, int bins_in_stride, const float* u, int u_stride,
                    int n_rays, int s_in, int n_out, float anneal, int sum_vec_width, float* bins_out,

@@ -84,6 +84,8 @@ def _declare():
     L.njf_transmittance_weights.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.njf_flow_from_encoding.restype = c_int
     L.njf_flow_from_encoding.argtypes = [c_void_p] * 5 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    L.njf_make_rays.restype = c_int
+    L.njf_make_rays.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.njf_debug_field_timing.restype = c_int
     L.njf_debug_field_timing.argtypes = [c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     L._njf_declared = True

@@ -142,10 +142,39 @@ def pdf_fixture():
     print("pdf_sampler", len(cases))
 
 
+def rays_fixture():
+    """Reference ray generation (rendering/geometry.py:117-134 get_pixel_coordinates, :170-203
+    get_world_rays_with_z) for two cameras of the Allegro rig shape on a 9x13 grid and a 400x400 grid corner."""
+    ref_shim.install()
+    from neural_jacobian_field.rendering import geometry as geo  # type: ignore
+
+    K = synth.normalized_intrinsics(**synth.ALLEGRO_INTRINSICS_PX)[None].repeat(2, 1, 1)
+    K[1, 0, 0] *= 1.07   # a second, slightly different camera
+    K[1, 1, 2] += 0.013
+    c2w = torch.stack([synth.relative_target_pose(1), synth.relative_target_pose(3)])
+    out = dict(k_norm=K.numpy(), c2w=c2w.numpy())
+    for tag, (h, w) in (("small", (9, 13)), ("full", (400, 400))):
+        xy, sel = geo.get_pixel_coordinates(h, w)
+        coords = xy.reshape(1, -1, 2).repeat(2, 1, 1)
+        o, d, z = geo.get_world_rays_with_z(coords, K, c2w)
+        o2, d2 = geo.get_world_rays(coords, K, c2w)
+        assert torch.equal(o, o2) and torch.equal(d, d2)
+        keep = slice(None) if tag == "small" else slice(0, 4096)   # keep the fixture small
+        out.update({f"xy_{tag}": xy.numpy() if tag == "small" else xy.reshape(-1, 2)[keep].numpy(),
+                    f"sel_{tag}": sel.numpy() if tag == "small" else sel.reshape(-1, 2)[keep].numpy(),
+                    f"origins_{tag}": o[:, keep].numpy(), f"dirs_{tag}": d[:, keep].numpy(), f"z_{tag}": z[:, keep].numpy()})
+    np.savez_compressed(os.path.join(OUT, "rays.npz"), **out)
+    print("rays", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "rays":
+        rays_fixture()
+        sys.exit(0)
     pdf_fixture()
+    rays_fixture()
     render_fixture("render_transformer", "jacobian_transformer", 8, (16,), 24, wseed=11)
     render_fixture("render_mlp", "jacobian_mlp", 6, (16,), 24, wseed=12)
     render_fixture("render_transformer_2prop_b2", "jacobian_transformer", 8, (16, 12), 16, wseed=13, batch=2,

@@ -246,6 +246,26 @@ def field_heads(w: W, xyz: torch.Tensor, feat, c2w, k_norm, spec: FieldSpec):
     return density_activation(pre), geo, jacobian_head(w, z, enc, spec), z, enc
 
 
+def pixel_coordinates(height: int, width: int):
+    """get_pixel_coordinates (rendering/geometry.py:117-134): normalised xy centres (H,W,2), (row,col) selectors."""
+    row, col = torch.arange(height), torch.arange(width)
+    selector = torch.stack(torch.meshgrid(row, col, indexing="ij"), dim=-1)
+    xy = torch.stack(torch.meshgrid((col + 0.5) / width, (row + 0.5) / height, indexing="xy"), dim=-1)
+    return xy, selector
+
+
+def world_rays_with_z(coords_xy: torch.Tensor, k_norm: torch.Tensor, c2w: torch.Tensor):
+    """get_world_rays_with_z (rendering/geometry.py:170-203; unproject :42-56, transform_cam2world :68-73):
+    coords (B,R,2), k_norm (B,3,3), c2w (B,4,4) -> origins (B,R,3), unit dirs (B,R,3), z (B,R,1)."""
+    hom = torch.cat([coords_xy, torch.ones_like(coords_xy[..., :1])], -1)
+    d = torch.einsum("cij,crj->cri", torch.inverse(k_norm), hom)
+    d = d / d.norm(dim=-1, keepdim=True)
+    z = d[..., -1:]
+    dw = torch.einsum("cij,crj->cri", c2w[:, :3, :3], d)
+    o = c2w[:, None, :3, 3].expand_as(dw)
+    return o.contiguous(), dw.contiguous(), z
+
+
 def positions_of(origins, dirs, starts, ends):
     """RaySamples.get_positions (ray_samplers.py:48-55)."""
     return origins[..., None, :] + dirs[..., None, :] * (starts + ends) / 2

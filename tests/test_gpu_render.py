@@ -324,6 +324,40 @@ def test_chunked_field_pass_is_bit_identical(tmp_path, R, s_prop, s_nerf, max_ti
         assert np.array_equal(outs[0][k], outs[1][k]), k
 
 
+def test_ray_generation_vs_reference():
+    """njf_make_rays (csrc/rays.cu) through njf_b200.geometry against the reference's get_pixel_coordinates /
+    get_world_rays_with_z outputs (tests/golden/rays.npz) and, at the full 400x400 size, against the oracle;
+    the fused grid mode must equal the coordinate mode bit for bit.  Tolerance 1e-6 (unit vectors, fp32)."""
+    from njf_b200 import _lib, geometry as G
+
+    z = np.load(os.path.join(GOLDEN, "rays.npz"))
+    K, c2w = torch.from_numpy(z["k_norm"]).to(DEV), torch.from_numpy(z["c2w"]).to(DEV)
+    xy, sel = G.get_pixel_coordinates(9, 13, device=torch.device(DEV))
+    assert np.array_equal(xy.cpu().numpy(), z["xy_small"]) and np.array_equal(sel.cpu().numpy(), z["sel_small"])
+    coords = xy.reshape(1, -1, 2).repeat(2, 1, 1)
+    o, d, zz = G.get_world_rays_with_z(coords, K, c2w)
+    o2, d2 = G.get_world_rays(coords, K, c2w)
+    og, dg, zg = G.get_world_rays_grid(9, 13, K, c2w, with_z=True)
+    torch.cuda.synchronize()
+    assert torch.equal(o, o2) and torch.equal(d, d2) and torch.equal(o, og) and torch.equal(d, dg) and torch.equal(zz, zg)
+    assert np.array_equal(o.cpu().numpy(), z["origins_small"])
+    np.testing.assert_allclose(d.cpu().numpy(), z["dirs_small"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(zz.cpu().numpy(), z["z_small"], atol=1e-6, rtol=0)
+    # full size: 2 cameras x 400x400 in grid mode vs the CPU oracle (+ the reference's first 4096 rays)
+    og, dg, zg = G.get_world_rays_grid(400, 400, K, c2w, with_z=True)
+    torch.cuda.synchronize()
+    xyf, _ = O.pixel_coordinates(400, 400)
+    oo, do, zo = O.world_rays_with_z(xyf.reshape(1, -1, 2).repeat(2, 1, 1), K.cpu(), c2w.cpu())
+    np.testing.assert_allclose(dg.cpu().numpy(), do.numpy(), atol=1e-6, rtol=0)
+    np.testing.assert_allclose(zg.cpu().numpy(), zo.numpy(), atol=1e-6, rtol=0)
+    np.testing.assert_allclose(dg[:, :4096].cpu().numpy(), z["dirs_full"], atol=1e-6, rtol=0)
+    assert float((dg.norm(dim=-1) - 1).abs().max()) < 1e-6
+    with pytest.raises(_lib.NjfError):
+        G.get_world_rays(coords.cpu(), K.cpu(), c2w.cpu())   # no CPU fallback
+    with pytest.raises(_lib.NjfError):
+        G.get_world_rays(coords[:1], K, c2w)                  # camera count mismatch
+
+
 def test_bad_arguments_fail_loudly():
     from njf_b200 import _lib, api
     from njf_b200.render import render

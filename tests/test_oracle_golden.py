@@ -68,3 +68,21 @@ def test_encodings_known_values():
     s = O.sh4(torch.tensor([[0.5, 0.5, 1.0]]), fp16_round=False)  # direction (0,0,1)
     assert abs(float(s[0, 0]) - 0.2820948) < 1e-6 and abs(float(s[0, 2]) - 0.4886025) < 1e-6
     assert abs(float(s[0, 6]) - (0.9461747 - 0.3153916)) < 1e-6 and abs(float(s[0, 12]) - 0.3731763 * 2.0) < 1e-6
+
+
+def test_ray_generation_matches_reference():
+    """oracle pixel_coordinates / world_rays_with_z against the reference's geometry.get_pixel_coordinates and
+    get_world_rays_with_z (tests/golden/rays.npz, made by oracle/make_golden.py rays)."""
+    z = np.load(os.path.join(GOLDEN, "rays.npz"))
+    K, c2w = torch.from_numpy(z["k_norm"]), torch.from_numpy(z["c2w"])
+    xy, sel = O.pixel_coordinates(9, 13)
+    assert np.array_equal(xy.numpy(), z["xy_small"]) and np.array_equal(sel.numpy(), z["sel_small"])
+    o, d, zz = O.world_rays_with_z(xy.reshape(1, -1, 2).repeat(2, 1, 1), K, c2w)
+    np.testing.assert_allclose(o.numpy(), z["origins_small"], atol=0, rtol=0)
+    np.testing.assert_allclose(d.numpy(), z["dirs_small"], atol=2e-7, rtol=0)
+    np.testing.assert_allclose(zz.numpy(), z["z_small"], atol=2e-7, rtol=0)
+    xyf, self_ = O.pixel_coordinates(400, 400)
+    assert np.array_equal(xyf.reshape(-1, 2)[:4096].numpy(), z["xy_full"])
+    assert np.array_equal(self_.reshape(-1, 2)[:4096].numpy(), z["sel_full"])
+    o, d, zz = O.world_rays_with_z(xyf.reshape(1, -1, 2)[:, :4096].repeat(2, 1, 1), K, c2w)
+    np.testing.assert_allclose(d.numpy(), z["dirs_full"], atol=2e-7, rtol=0)
