@@ -174,6 +174,17 @@ int njf_flow_from_encoding(const float* jbar, const float* p, const float* actio
                            const float* trgt_k_px, int n_rays, int rays_per_view, int action_dim, float* flow,
                            float* pw, void* stream);
 
+/* ---- inverse dynamics on the collapsed encoding (the Adam loop of notebooks/real_world/2_inverse_dynamics.ipynb
+ * over Model.infer_optical_flow, models/model.py:497-525): Gauss-Newton normal equations of
+ *   min_u sum_i w_i | flow_i(u) - target_i |^2 ,  flow_i(u) = proj(p_i + Jbar_i^T u) - proj(p_i)
+ * per view: H [B][A][A] = sum w G^T G, g [B][A] = sum w G^T r, loss [B] = sum w |r|^2 (fp64), G = d flow / d u.
+ * target_flow [N][2] pixels; ray_weight [N] or NULL; workspace: njf_flow_gn_workspace_doubles(B) doubles. */
+int njf_flow_gn_terms(const float* jbar, const float* p, const float* action, const float* trgt_w2c,
+                      const float* trgt_k_px, const float* target_flow, const float* ray_weight, int n_rays,
+                      int rays_per_view, int action_dim, double* workspace, double* H, double* g, double* loss,
+                      void* stream);
+int njf_flow_gn_workspace_doubles(int n_views);
+
 /* ---- self-test of the tcgen05 layer-chain machinery (tests only; weights/bias are HOST pointers) */
 int njf_selftest_chain(const float* w0, const float* w1, const float* w2, const float* w3, const float* bias,
                        const float* a_in, const float* tz_in, float* x_out, float* y_out, int ntiles, int grid,

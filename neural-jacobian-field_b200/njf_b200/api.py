@@ -86,6 +86,10 @@ def _declare():
     L.njf_flow_from_encoding.argtypes = [c_void_p] * 5 + [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.njf_make_rays.restype = c_int
     L.njf_make_rays.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.njf_flow_gn_terms.restype = c_int
+    L.njf_flow_gn_terms.argtypes = [c_void_p] * 7 + [c_int, c_int, c_int] + [c_void_p] * 5
+    L.njf_flow_gn_workspace_doubles.restype = c_int
+    L.njf_flow_gn_workspace_doubles.argtypes = [c_int]
     L.njf_debug_field_timing.restype = c_int
     L.njf_debug_field_timing.argtypes = [c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
     L._njf_declared = True

@@ -14,12 +14,14 @@ from . import _lib, api
 def get_pixel_coordinates(height: int, width: int, device: torch.device = torch.device("cpu")) -> Tuple[Tensor, Tensor]:
     """Normalised (0..1) xy pixel centres (H, W, 2) and (row, col) selectors (H, W, 2), geometry.py:117-134.
     Index bookkeeping only (no kernel): ray order is row-major, x fastest."""
-    row = torch.arange(height, device=device)
-    col = torch.arange(width, device=device)
-    selector = torch.stack(torch.meshgrid(row, col, indexing="ij"), dim=-1)
+    # built on the host and moved: torch's CUDA division by a scalar multiplies by the reciprocal, which differs
+    # from the reference's CPU result (and from the kernel's correctly rounded division) in the last bit
+    row = torch.arange(height)
+    col = torch.arange(width)
+    selector = torch.stack(torch.meshgrid(row, col, indexing="ij"), dim=-1).to(device)
     x = (col + 0.5) / width
     y = (row + 0.5) / height
-    coordinates = torch.stack(torch.meshgrid(x, y, indexing="xy"), dim=-1)
+    coordinates = torch.stack(torch.meshgrid(x, y, indexing="xy"), dim=-1).to(device)
     return coordinates, selector
 
 

@@ -340,6 +340,26 @@ def infer_optical_flow(jac, weights, positions, action, trgt_c2w, trgt_k_px):
     return project_px(pw, trgt_c2w, trgt_k_px) - project_px(p, trgt_c2w, trgt_k_px)
 
 
+def flow_gn_terms(jac, weights, positions, action, trgt_c2w, trgt_k_px, target_flow):
+    """Gauss-Newton normal equations of the notebooks' inverse-dynamics objective
+    sum_i |infer_optical_flow(u)_i - target_i|^2 (2_inverse_dynamics.ipynb cell 26 minimises it with Adam):
+    G = d flow / d u by autograd through the reference formulation; returns H (B,A,A), g (B,A), loss (B) in fp64."""
+    B = jac.shape[0]
+    A = action.shape[-1]
+    Hs, gs, ls = [], [], []
+    for b in range(B):
+        sl = slice(b, b + 1)
+        f = lambda u: infer_optical_flow(jac[sl].double(), weights[sl].double(), positions[sl].double(), u[None],
+                                         trgt_c2w[sl].double(), trgt_k_px[sl].double())[0]
+        u = action[b].double()
+        G = torch.autograd.functional.jacobian(f, u)          # (R, 2, A)
+        r = f(u) - target_flow[b].double()
+        Hs.append(torch.einsum("ria,rib->ab", G, G))
+        gs.append(torch.einsum("ria,ri->a", G, r))
+        ls.append((r ** 2).sum())
+    return torch.stack(Hs), torch.stack(gs), torch.stack(ls)
+
+
 def encoder_resnet34(w: W, image: torch.Tensor, prefix: str = "encoder.model.") -> torch.Tensor:
     """EncoderResnet.forward (models/encoder/encoder_resnet.py:53-86): resnet34 conv1..layer3 (eval BN),
     bilinear upsampling to the conv1 resolution, channel concat -> 512 channels at H/2 x W/2."""

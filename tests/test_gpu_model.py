@@ -91,6 +91,62 @@ def test_model_api_matches_oracle(head, A):
     np.testing.assert_allclose(dho.xyz_features.cpu().numpy(), encf.numpy(), atol=2e-5)
 
 
+@pytest.mark.parametrize("head,A", [("jacobian_transformer", 8), ("jacobian_mlp", 6)])
+def test_inverse_dynamics_gauss_newton(head, A):
+    """the normal equations of the notebooks' inverse-dynamics objective from njf_flow_gn_terms
+    (a) equal an fp64 autograd evaluation of the collapsed formula on the same (jbar, p) to 1e-4 (the kernel's
+    analytic Jacobian is right), (b) agree with the oracle's per-sample reference formulation within the fp16
+    Jacobian tolerance, and (c) Levenberg-Marquardt on them recovers a known action from its own flow."""
+    from njf_b200 import inverse_dynamics as ID
+    from njf_b200.model import CameraInput, RenderingInput, RobotInput
+
+    s_prop, s_nerf = (32,), 32
+    m, sd = _model(head, A, s_prop, s_nerf)
+    sc = _scene(A)
+    cam = CameraInput(sc["img"], sc["ctxt"], sc["K"], sc["trgt"], sc["kpx"])
+    rin = RenderingInput(sc["o"], sc["d"], sc["zn"], sc["zf"])
+    enc = m.encode_image(cam, rin, RobotInput(sc["act"]))
+    g = torch.Generator().manual_seed(3)
+    u_true = (0.3 * torch.randn(1, A, generator=g)).to(DEV)
+    with torch.no_grad():
+        target = m.infer_optical_flow(enc, cam, RobotInput(u_true))
+    u = (0.5 * u_true + 0.05).contiguous()
+    t = ID.gauss_newton_terms(enc, cam, u, target)
+    # (a) fp64 autograd on the collapsed formula
+    w2c = torch.inverse(sc["trgt"]).double()
+    kpx = sc["kpx"].double()
+    jb, pp = enc.jbar.cpu().double(), enc.p.cpu().double()
+
+    def flow64(a):
+        x = pp + torch.einsum("brad,a->brd", jb.reshape(1, -1, A, 3), a)
+        def proj(x_):
+            c = torch.einsum("bij,brj->bri", w2c[:, :3, :3], x_) + w2c[:, None, :3, 3]
+            k = torch.einsum("bij,brj->bri", kpx, c)
+            return k[..., :2] / (k[..., 2:3] + 1e-9)
+        return (proj(x) - proj(pp))[0]
+
+    a64 = u[0].cpu().double()
+    G = torch.autograd.functional.jacobian(flow64, a64)
+    r = flow64(a64) - target[0].cpu().double()
+    H64, g64, l64 = torch.einsum("ria,rib->ab", G, G), torch.einsum("ria,ri->a", G, r), (r ** 2).sum()
+    hs = float(H64.abs().max())
+    np.testing.assert_allclose(t.H[0].cpu().numpy(), H64.numpy(), atol=1e-4 * hs, rtol=1e-4)
+    np.testing.assert_allclose(t.g[0].cpu().numpy(), g64.numpy(), atol=1e-4 * float(g64.abs().max()), rtol=1e-3)
+    np.testing.assert_allclose(float(t.loss[0]), float(l64), rtol=1e-3)
+    # (b) the oracle's reference formulation (per-sample J, weights, positions from the CPU oracle)
+    with torch.no_grad():
+        feat = O.encoder_resnet34(sd, sc["img"])
+        ref = O.render_forward(sd, O.FieldSpec(head, A), feat, sc["ctxt"], sc["K"], sc["trgt"], sc["kpx"], sc["o"], sc["d"],
+                               sc["zn"], sc["zf"], sc["act"], s_prop, s_nerf)
+    Ho, go, lo = O.flow_gn_terms(ref["jacobian"], ref["weights"][..., None], ref["positions"], u.cpu(), sc["trgt"], sc["kpx"],
+                                 target.cpu())
+    np.testing.assert_allclose(t.H[0].cpu().numpy(), Ho[0].numpy(), atol=8e-2 * float(Ho.abs().max()))
+    # (c) recover the action
+    sol, hist = ID.solve_action(enc, cam, target, torch.zeros(1, A), iters=8)
+    assert hist[-1] < 1e-6 * max(hist[0], 1e-12) + 1e-8, hist
+    np.testing.assert_allclose(sol.cpu().numpy(), u_true.cpu().numpy(), atol=2e-3 * float(u_true.abs().max()) + 1e-4)
+
+
 def test_training_mode_is_rejected_loudly():
     m, _ = _model("jacobian_transformer", 8, (16,), 16)
     from njf_b200.model import CameraInput, RenderingInput, RobotInput
