@@ -853,14 +853,24 @@ int launch_field(const NjfField* f, FieldParams& p, cudaStream_t stream) {
     gpc = max_tiles / T;
     if (gpc < 1) gpc = 1;
     if (gpc > NGtot) gpc = NGtot;
-    const size_t tiles = static_cast<size_t>(gpc) * T;
-    const size_t need = tiles * (16 * kRows * sizeof(float4) + kRows * sizeof(float));
-    if (f->xf_scratch_bytes < need) {
+    constexpr size_t kTileBytes = 16 * kRows * sizeof(float4) + kRows * sizeof(float);
+    size_t tiles = static_cast<size_t>(gpc) * T;
+    if (f->xf_scratch_bytes < tiles * kTileBytes) {
       if (f->d_xf_scratch) NJF_CUDA(cudaFree(f->d_xf_scratch));
       f->d_xf_scratch = nullptr;
       f->xf_scratch_bytes = 0;
-      NJF_CUDA(cudaMalloc(&f->d_xf_scratch, need));
-      f->xf_scratch_bytes = need;
+      // little free memory: halve the launch pairs until the hand-over buffer fits (down to one ray group)
+      while (cudaMalloc(&f->d_xf_scratch, tiles * kTileBytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        f->d_xf_scratch = nullptr;
+        if (gpc == 1) NJF_FAIL("out of device memory for the %zu-byte transformer hand-over buffer", tiles * kTileBytes);
+        gpc = (gpc + 1) / 2;
+        tiles = static_cast<size_t>(gpc) * T;
+      }
+      f->xf_scratch_bytes = tiles * kTileBytes;
+    } else {
+      // an existing (possibly smaller-than-wanted but sufficient) buffer: never launch more tiles than it holds
+      tiles = static_cast<size_t>(gpc) * T;
     }
     p.qs = reinterpret_cast<float4*>(f->d_xf_scratch);
     p.wts = f->d_xf_scratch + tiles * 16 * kRows * 4;
