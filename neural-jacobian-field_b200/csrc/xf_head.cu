@@ -10,8 +10,10 @@
 //   * FOUR tile slots per SM (the trunk kernels fit two): slot = 128 rows, ONE thread per row (TMEM lane),
 //     16 KB A tile, 128 TMEM columns (x: fp32 residual stream [0,64), acc [64,128)); residual adds are the
 //     accumulate flag of tcgen05.mma onto x, biases ride in SW32 bias blocks (kStepBias);
-//   * one single-thread MMA issuer warp PER SLOT: the 13 dependent round trips of a tile
-//     (arrive -> mma -> commit -> wake, ~650 cycles each, tools/ubench_tmem.cu) overlap across slots.
+//   * no issuer warps: after a layer's A tile is written the slot's 128 threads meet at a named barrier and its
+//     first thread issues the MMAs (same ~650-cycle round trip as a dedicated issuer thread, tools/ubench_tmem.cu,
+//     but 512 instead of 640 threads: 128 registers per thread and four polling warps fewer); the 13 dependent
+//     round trips of a tile overlap across the four slots.
 // Then J-bar = sum_s w_s J_s per ray (model.py:281-286), optionally the per-sample Jacobians.
 #include "field.h"
 #include "njf_internal.h"
@@ -20,7 +22,7 @@ namespace njf {
 
 constexpr int kXfSlots = 4;
 constexpr int kXfEpiThreads = kXfSlots * kRows;           // 512
-constexpr int kXfThreads = kXfEpiThreads + kXfSlots * 32;  // + one issuer warp per slot
+constexpr int kXfThreads = kXfEpiThreads;  // no issuer warps: the slot's first thread issues after a named barrier
 constexpr uint32_t kXfATile = kRows * 128;                 // 128 rows x 64 fp16
 struct XfSmem {
   static constexpr uint32_t kW = 0;
@@ -33,7 +35,6 @@ struct XfSmem {
 static_assert(kXfMaxBlob % 1024 == 0, "A tiles must stay 1024 B aligned");
 static_assert(XfSmem::kTotal <= 232448, "shared memory budget");
 struct XfBars {
-  uint64_t a_ready[kXfSlots];
   uint64_t acc_ready[kXfSlots];
   uint64_t w_full;
   uint32_t tmem_base;
@@ -60,20 +61,39 @@ struct XfEpi {
 #endif
   uint8_t* a_row;   // this row of the slot's A tile
   uint32_t sw;      // row & 7 (chunk swizzle)
-  uint64_t* a_ready;
   uint64_t* acc_ready;
   uint32_t tm;      // TMEM address: this lane, column 0 of the slot
   uint32_t par;
+  // MMA issue (used by the slot's first thread only)
+  const MmaStep* steps;
+  uint32_t a0, w0, d0;   // smem address of the slot's A tile / of the resident blob, TMEM column 0 of the slot
+  uint64_t ones;
+  uint32_t bar_id;
+  bool issuer;
 };
 __device__ __forceinline__ void xf_store_a(const XfEpi& e, const uint32_t (&pk)[32]) {
 #pragma unroll
   for (int c = 0; c < 8; ++c)
     *reinterpret_cast<uint4*>(e.a_row + ((c ^ e.sw) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
 }
-__device__ __forceinline__ void xf_publish(const XfEpi& e) {
+// A tile of layer `s` written: all 128 threads of the slot meet, the first one issues the layer's MMAs
+// (4 x K=16 + the bias block) and commits to the slot's accumulator barrier
+__device__ __forceinline__ void xf_publish(const XfEpi& e, int s) {
   fence_proxy_async_smem();
   tc_fence_before();
-  mbar_arrive(e.a_ready);
+  named_bar_sync(e.bar_id, kRows);
+  if (e.issuer) {
+    tc_fence_after();
+    const MmaStep st = e.steps[s];
+    const uint32_t idesc = make_idesc_f16(st.n);
+    const uint32_t d = e.d0 + st.d_col;
+    const uint32_t w = e.w0 + st.w_off;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_f16(d, make_sw128_desc(e.a0 + k * 32), make_sw128_desc(w + k * 32), idesc, (st.acc || k > 0) ? 1u : 0u);
+    umma_f16(d, e.ones, make_sw32_desc(w + static_cast<uint32_t>(st.n) * 128u), idesc, 1u);
+    umma_commit(e.acc_ready);
+  }
 }
 __device__ __forceinline__ void xf_wait(XfEpi& e, int ph) {
   XPROF(e, ph);
@@ -177,14 +197,11 @@ __global__ void __launch_bounds__(kXfThreads, 1) xf_kernel(const __grid_constant
   XfBars* bars = reinterpret_cast<XfBars*>(smem + XfSmem::kBars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kXfSlots; ++s) {
-      mbar_init(&bars->a_ready[s], kRows);
-      mbar_init(&bars->acc_ready[s], 1);
-    }
+    for (int s = 0; s < kXfSlots; ++s) mbar_init(&bars->acc_ready[s], 1);
     mbar_init(&bars->w_full, 1);
     mbar_fence_init();
   }
-  if (warp == kXfEpiThreads / 32) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == 0) tmem_alloc(&bars->tmem_base, 512);
   if (threadIdx.x < kRows) {  // ones block: element (row, 0) = 1.0
     uint4* rowp = reinterpret_cast<uint4*>(smem + XfSmem::kOnes + threadIdx.x * 32);
     rowp[0] = make_uint4(0, 0, 0, 0);
@@ -203,36 +220,7 @@ __global__ void __launch_bounds__(kXfThreads, 1) xf_kernel(const __grid_constant
   }
   const int nitems = (p.NG + kXfSlots - 1) / kXfSlots;
 
-  if (warp >= kXfEpiThreads / 32) {
-    // ------------------------------------------------------------------ issuer of slot `slot`
-    if (lane == 0) {
-      const int slot = warp - kXfEpiThreads / 32;
-      const uint32_t a0 = smem_u32(smem + XfSmem::kA + slot * kXfATile);
-      const uint32_t w0 = smem_u32(smem + XfSmem::kW);
-      const uint64_t ones = make_sw32_desc(smem_u32(smem + XfSmem::kOnes));
-      uint32_t apar = 0;
-      mbar_wait(&bars->w_full, 0);
-      for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-        if (kXfSlots * it + slot >= p.NG) continue;
-        for (int tile = 0; tile < p.T; ++tile) {
-          for (int s = 0; s < p.prog.nsteps; ++s) {
-            const MmaStep st = p.prog.steps[s];
-            const uint32_t idesc = make_idesc_f16(st.n);
-            const uint32_t d = tmem + slot * 128 + st.d_col;
-            const uint32_t w = w0 + st.w_off;
-            mbar_wait(&bars->a_ready[slot], apar);
-            apar ^= 1u;
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(d, make_sw128_desc(a0 + k * 32), make_sw128_desc(w + k * 32), idesc, (st.acc || k > 0) ? 1u : 0u);
-            umma_f16(d, ones, make_sw32_desc(w + static_cast<uint32_t>(st.n) * 128u), idesc, 1u);
-            umma_commit(&bars->acc_ready[slot]);
-          }
-        }
-      }
-    }
-  } else {
+  {
     // ------------------------------------------------------------------ one thread per row
     const int slot = warp >> 2, q = warp & 3;
     const int row = q * 32 + lane;
@@ -240,8 +228,15 @@ __global__ void __launch_bounds__(kXfThreads, 1) xf_kernel(const __grid_constant
     uint8_t* a_tile = smem + XfSmem::kA + slot * kXfATile;
     e.a_row = a_tile + row * 128;
     e.sw = row & 7;
-    e.a_ready = &bars->a_ready[slot];
     e.acc_ready = &bars->acc_ready[slot];
+    e.steps = p.prog.steps;
+    e.a0 = smem_u32(a_tile);
+    e.w0 = smem_u32(smem + XfSmem::kW);
+    e.d0 = tmem + slot * 128;
+    e.ones = make_sw32_desc(smem_u32(smem + XfSmem::kOnes));
+    e.bar_id = 1 + slot;
+    e.issuer = (threadIdx.x & (kRows - 1)) == 0;
+    mbar_wait(&bars->w_full, 0);  // the resident weights have landed (once per CTA)
     e.tm = tmem + (static_cast<uint32_t>(q * 32) << 16) + slot * 128;
     e.par = 0;
 #ifdef NJF_PROFILE
@@ -250,7 +245,7 @@ __global__ void __launch_bounds__(kXfThreads, 1) xf_kernel(const __grid_constant
 #endif
     float* part = reinterpret_cast<float*>(smem + XfSmem::kPart) + slot * 4 * 32;
     const int A3 = 3 * p.A;
-    const uint32_t bar_id = 1 + slot;
+    const uint32_t bar_id = e.bar_id;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
       const int lgroup = kXfSlots * it + slot;
       if (lgroup >= p.NG) continue;
@@ -290,7 +285,7 @@ __global__ void __launch_bounds__(kXfThreads, 1) xf_kernel(const __grid_constant
         }
         xf_ln_to_a(e, x);
         tmem_st_wait();
-        xf_publish(e);  // -> M1 (layer 0)
+        xf_publish(e, 0);  // -> M1 (layer 0)
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
           xf_wait(e, l == 0 ? kXLoad : kXLn);
@@ -305,11 +300,11 @@ __global__ void __launch_bounds__(kXfThreads, 1) xf_kernel(const __grid_constant
             case 7: xf_softmax_to_a<7>(e, x); break;
             default: xf_softmax_to_a<8>(e, x); break;
           }
-          xf_publish(e);  // -> M2: x += attention . (V W_out) + b_out
+          xf_publish(e, 4 * l + 1);  // -> M2: x += attention . (V W_out) + b_out
           xf_wait(e, kXSoftmax);
           xf_ld64(e, 0, x);
           xf_ln_to_a(e, x);
-          xf_publish(e);  // -> W1
+          xf_publish(e, 4 * l + 2);  // -> W1
           xf_wait(e, kXLn);
           xf_ld64(e, 64, x);
           {
@@ -321,7 +316,7 @@ __global__ void __launch_bounds__(kXfThreads, 1) xf_kernel(const __grid_constant
             }
             xf_store_a(e, pk);
           }
-          xf_publish(e);  // -> W2: x += W2 . gelu + b2
+          xf_publish(e, 4 * l + 3);  // -> W2: x += W2 . gelu + b2
           xf_wait(e, kXGelu);
           xf_ld64(e, 0, x);
           if (l < 2) {
@@ -332,7 +327,7 @@ __global__ void __launch_bounds__(kXfThreads, 1) xf_kernel(const __grid_constant
             for (int j = 0; j < 32; ++j) pk[j] = pack_f16x2(x[2 * j], x[2 * j + 1]);
             xf_store_a(e, pk);
           }
-          xf_publish(e);  // -> M1 of the next layer / jacobian_head Linear(64, 3A)
+          xf_publish(e, 4 * l + 4);  // -> M1 of the next layer / jacobian_head Linear(64, 3A)
         }
         xf_wait(e, kXLn);
         float J[32];
@@ -408,7 +403,7 @@ __global__ void __launch_bounds__(kXfThreads, 1) xf_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kXfEpiThreads / 32) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace njf
