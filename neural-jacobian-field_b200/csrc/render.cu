@@ -929,7 +929,7 @@ extern "C" int njf_prof_read(unsigned long long* out16, int reset) {
 extern "C" int njf_debug_field_timing(int enable, float* field_kernel_ms, float* xf_kernel_ms) {
   if (field_kernel_ms || xf_kernel_ms) {
     float tf = 0.f, tx = 0.f;
-    for (size_t i = 0; i + 2 < g_field_events_used + 0 && i + 2 < g_field_events.size() + 0; i += 3) {
+    for (size_t i = 0; i + 3 <= g_field_events_used && i + 3 <= g_field_events.size(); i += 3) {
       float a = 0.f, b = 0.f;
       NJF_CUDA(cudaEventSynchronize(g_field_events[i + 2]));
       NJF_CUDA(cudaEventElapsedTime(&a, g_field_events[i], g_field_events[i + 1]));
