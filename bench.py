@@ -22,7 +22,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "neural-jacobian-field_b200"), os.path.join(ROOT, "oracle")):
+ORACLE = os.path.join(ROOT, "oracle")   # test infrastructure: imported ONLY by the cpu-baseline / reference legs
+for _p in (ROOT, os.path.join(ROOT, "neural-jacobian-field_b200")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
@@ -100,17 +101,31 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def scene(view: int, device=None, pin=False):
-    import synth
+def scene(view: int, device=None, pin=False, rays_device=None):
+    """Synthetic view `view`: context image, cameras of the Allegro rig shape, the 400x400 target ray grid.
+    `rays_device`: generate the rays with the library's own kernel on that GPU (njf_b200.geometry); None = the
+    reference-side CPU restatement (oracle/synth.py), used by the reference arm which must not touch our kernels."""
+    from njf_b200 import synth
 
     g = torch.Generator().manual_seed(2 + view)
     img = torch.rand(1, 3, IMG_H, IMG_W, generator=g)
     K = synth.normalized_intrinsics(**synth.ALLEGRO_INTRINSICS_PX)[None]
     kpx = K.clone(); kpx[:, 0] *= IMG_W; kpx[:, 1] *= IMG_H
     ctxt, trgt = torch.eye(4)[None], synth.relative_target_pose(1 + view % 5)[None]
-    o, d = synth.world_rays(synth.pixel_grid(RENDER_H, RENDER_W), K[0], trgt[0])
-    sc = dict(image=img, ctxt_c2w=ctxt, ctxt_k=K, trgt_c2w=trgt, trgt_k_px=kpx, origins=o[None].contiguous(),
-              dirs=d[None].contiguous(), z_near=torch.tensor([0.65]), z_far=torch.tensor([3.2]),
+    if rays_device is not None:
+        from njf_b200 import geometry
+
+        o, d = geometry.get_world_rays_grid(RENDER_H, RENDER_W, K.to(rays_device), trgt.to(rays_device))
+        o, d = o.cpu(), d.cpu()
+    else:
+        if ORACLE not in sys.path:
+            sys.path.insert(0, ORACLE)
+        import synth as osynth
+
+        o, d = osynth.world_rays(osynth.pixel_grid(RENDER_H, RENDER_W), K[0], trgt[0])
+        o, d = o[None], d[None]
+    sc = dict(image=img, ctxt_c2w=ctxt, ctxt_k=K, trgt_c2w=trgt, trgt_k_px=kpx, origins=o.contiguous(),
+              dirs=d.contiguous(), z_near=torch.tensor([0.65]), z_far=torch.tensor([3.2]),
               action=0.1 * torch.randn(1, A, generator=g))
     if pin:
         sc = {k: v.pin_memory() for k, v in sc.items()}
@@ -120,14 +135,13 @@ def scene(view: int, device=None, pin=False):
 
 
 def hot_weights():
-    import synth
+    from njf_b200 import synth
 
     return synth.synth_state_dict(synth.field_shapes(HEAD, A, n_proposal=len(S_PROP)), 11)
 
 
 def build_model(device):
-    import synth
-    from njf_b200 import model as M, modules as mod
+    from njf_b200 import model as M, modules as mod, synth
 
     mlp = mod.MlpCfg()
     cfg = M.ModelCfg(action_dim=A, rendering=M.RenderingCfg(S_PROP, S_NERF), encoder=mod.EncoderResnetCfg(),
@@ -140,15 +154,17 @@ def build_model(device):
     return m.to(device)
 
 
-def oracle_rays_per_s(nrays: int, steps: int, warmup: int, want_outputs=False, device=None, threads=None):
+def oracle_rays_per_s(nrays: int, steps: int, warmup: int, want_outputs=False, device=None, threads=None, rays_device=None):
     """The reference algorithm (oracle port, fp32) on a bounded ray sample: on the host cores (all threads)
     or, with `device`, as eager PyTorch on the GPU (what the reference's own code path does on one GPU)."""
+    if ORACLE not in sys.path:
+        sys.path.insert(0, ORACLE)
     import njf_oracle as O
 
     if threads:
         torch.set_num_threads(threads)
     w = hot_weights()
-    sc = scene(0)
+    sc = scene(0, rays_device=rays_device)
     g = torch.Generator().manual_seed(9)
     feat = torch.randn(1, 512, IMG_H // 2, IMG_W // 2, generator=g).abs() * 0.7
     idx = torch.randperm(RENDER_H * RENDER_W, generator=g)[:nrays]
@@ -251,7 +267,7 @@ def main():
 
     L = api._declare()
     model = build_model(dev)
-    sc = scene(rank, dev)
+    sc = scene(rank, dev, rays_device=dev)
     with torch.no_grad():
         feat = model.encoder(sc["image"]).float().contiguous()   # once, outside the timed region
     fld = model.field()
@@ -335,7 +351,7 @@ def main():
     value = world * R * args.steps / (tot * 1e-3)
 
     # ---- e2e: the public API call (Model.forward) with HOST pinned inputs, encoder + copies inside
-    hs = scene(rank, pin=True)
+    hs = scene(rank, pin=True, rays_device=dev)
     cam = CameraInput(hs["image"], hs["ctxt_c2w"], hs["ctxt_k"], hs["trgt_c2w"], hs["trgt_k_px"])
     rin = RenderingInput(hs["origins"], hs["dirs"], hs["z_near"], hs["z_far"])
     rob = RobotInput(hs["action"])
@@ -399,7 +415,7 @@ def main():
                    "view": "novel target view", "parallelism": f"ray-shard x{world} (one view per GPU, weak)",
                    "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
                    "encoder": "excluded from value (once per image, cuDNN), included in e2e",
-                   "weights": "synthetic seeded (oracle/synth.py), random-init architecture of model_allegro.yaml"},
+                   "weights": "synthetic seeded (njf_b200/synth.py), random-init architecture of model_allegro.yaml"},
         "breakdown_ms": {"hoist": t_hoist, "proposal_kernel": t_prop, "field_pass": t_field, "field_kernel": t_fk, "xf_kernel": t_xf,
                          "finish+gather": ms_step - t_hoist - t_prop - t_field if world == 1 else None},
         "roofline": roof,
@@ -412,7 +428,7 @@ def main():
         # bounded CPU sample of the same workload + quality vs the oracle on those rays
         nrays = 256
         best_host_threads()
-        rps, dt, (ofeat, idx, oref) = oracle_rays_per_s(nrays, 1, 0, want_outputs=True)
+        rps, dt, (ofeat, idx, oref) = oracle_rays_per_s(nrays, 1, 0, want_outputs=True, rays_device=dev)
         from njf_b200.render import render
         m2 = fld.hoist(ofeat.to(dev))
         res = render(fld, m2, Hf, Wf, cams, sc["origins"][:, idx.to(dev)].contiguous(), sc["dirs"][:, idx.to(dev)].contiguous(),

@@ -2,7 +2,7 @@
 (imported from /root/reference through oracle/ref_shim.py) on seeded synthetic inputs.
 
 Run in the build container only:   python oracle/make_golden.py
-Weights are not stored: they are re-created from ``oracle/synth.py`` (seed + state-dict key).
+Weights are not stored: they are re-created from ``njf_b200/synth.py`` (seed + state-dict key; re-exported by ``oracle/synth.py``).
 """
 from __future__ import annotations
 

@@ -16,9 +16,7 @@ import __graft_entry__ as ge
 
 def main():
     ge.build()
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import synth
-    from njf_b200 import inverse_dynamics as ID, model as M, modules as mod
+    from njf_b200 import geometry, inverse_dynamics as ID, model as M, modules as mod, synth
 
     dev = torch.device("cuda", 0)
     A, N, s_prop, s_nerf = 6, 10_000, (256,), 256
@@ -34,9 +32,9 @@ def main():
     K = synth.normalized_intrinsics(**synth.ALLEGRO_INTRINSICS_PX)[None]
     kpx = K.clone(); kpx[:, 0] *= 640; kpx[:, 1] *= 480
     ctxt, trgt = torch.eye(4)[None], synth.relative_target_pose(1)[None]
-    o, d = synth.world_rays(torch.rand(N, 2, generator=g), K[0], trgt[0])
+    o, d = geometry.get_world_rays(torch.rand(1, N, 2, generator=g).to(dev), K.to(dev), trgt.to(dev))
     cam = M.CameraInput(img.to(dev), ctxt.to(dev), K.to(dev), trgt.to(dev), kpx.to(dev))
-    rin = M.RenderingInput(o[None].to(dev), d[None].to(dev), torch.tensor([0.65], device=dev), torch.tensor([3.2], device=dev))
+    rin = M.RenderingInput(o, d, torch.tensor([0.65], device=dev), torch.tensor([3.2], device=dev))
     u_true = (0.02 * torch.randn(1, A, generator=g)).to(dev)   # random-weight field: keep the flow in the tens of pixels
 
     def timed(fn, n):

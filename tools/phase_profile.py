@@ -23,7 +23,7 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     model = bench.build_model(dev)
-    sc = bench.scene(0, dev)
+    sc = bench.scene(0, dev, rays_device=dev)
     with torch.no_grad():
         feat = model.encoder(sc["image"]).float().contiguous()
     fld = model.field()
