@@ -105,3 +105,28 @@ def test_gelu_fit():
     g = np.maximum(v, 0) - np.float32(0.5) * (np.abs(v) * np.exp2(-q))
     ref = 0.5 * v.astype(np.float64) * (1 + erf(v.astype(np.float64) / np.sqrt(2)))
     assert np.abs(g - ref).max() < 5e-7
+
+
+def test_product_path_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing in the shipped package may import it, and bench.py reaches it
+    only through oracle_rays_per_s (cpu-baseline / reference legs) and the reference-arm ray generation."""
+    import ast
+
+    pkg = os.path.join(ROOT, "neural-jacobian-field_b200", "njf_b200")
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n.split(".")[0] in ("njf_oracle", "ref_shim", "make_golden") for n in names), (fn, names)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    for fn_node in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        uses = [n for n in ast.walk(fn_node) if isinstance(n, ast.Import) and any(a.name in ("njf_oracle", "synth") for a in n.names)]
+        if uses:
+            assert fn_node.name in ("oracle_rays_per_s", "scene"), fn_node.name
