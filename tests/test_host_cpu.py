@@ -130,3 +130,39 @@ def test_product_path_never_imports_the_oracle():
         uses = [n for n in ast.walk(fn_node) if isinstance(n, ast.Import) and any(a.name in ("njf_oracle", "synth") for a in n.names)]
         if uses:
             assert fn_node.name in ("oracle_rays_per_s", "scene"), fn_node.name
+
+
+def test_levenberg_marquardt_driver_cpu():
+    """The LM driver of njf_b200.inverse_dynamics on a CPU stand-in for the normal-equation kernel: a batch of
+    small non-linear least-squares problems (perspective-like residuals) built with torch autograd."""
+    from njf_b200.inverse_dynamics import levenberg_marquardt
+
+    g = torch.Generator().manual_seed(0)
+    B, N, A = 3, 40, 5
+    M = torch.randn(B, N, 2, A, generator=g, dtype=torch.float64)
+    c = 3.0 + torch.rand(B, N, 1, generator=g, dtype=torch.float64)
+    q = 0.1 * torch.randn(B, N, A, generator=g, dtype=torch.float64)
+    u_true = 0.3 * torch.randn(B, A, generator=g, dtype=torch.float64)
+
+    def f(u):  # (B,A) -> (B,N,2): linear map divided by a depth-like affine term
+        return torch.einsum("bnia,ba->bni", M, u) / (c + torch.einsum("bna,ba->bn", q, u)[..., None])
+
+    target = f(u_true)
+
+    def terms(u):
+        Hs, gs, ls = [], [], []
+        for b in range(B):
+            fb = lambda ub: (torch.einsum("nia,a->ni", M[b], ub) / (c[b] + (q[b] @ ub)[:, None]))
+            G = torch.autograd.functional.jacobian(fb, u[b])          # (N,2,A)
+            r = fb(u[b]) - target[b]
+            Hs.append(torch.einsum("nia,nib->ab", G, G)); gs.append(torch.einsum("nia,ni->a", G, r)); ls.append((r ** 2).sum())
+        return torch.stack(Hs), torch.stack(gs), torch.stack(ls)
+
+    u, hist = levenberg_marquardt(terms, torch.zeros(B, A), iters=10)
+    assert hist.shape == (11, B)
+    assert bool((hist[1:] <= hist[:-1] + 1e-18).all())                # accepted cost never increases
+    assert float(hist[-1].max()) < 1e-16 * max(float(hist[0].max()), 1.0) + 1e-20
+    assert float((u - u_true).abs().max()) < 1e-8
+    # a prior pulls towards the start and is honoured in the reported cost
+    u2, hist2 = levenberg_marquardt(terms, torch.zeros(B, A), iters=10, prior_weight=1e3)
+    assert float(u2.abs().max()) < float(u.abs().max())
