@@ -61,6 +61,7 @@ def main():
 
     t_adam = timed(adam_step, 100)
     t_gn = timed(lambda: ID.gauss_newton_terms(enc, cam, act.detach(), target), 100)
+    ID.solve_action(enc, cam, target, torch.zeros(1, A), iters=2)   # first call initialises cuSOLVER
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     sol, hist = ID.solve_action(enc, cam, target, torch.zeros(1, A), iters=10)
