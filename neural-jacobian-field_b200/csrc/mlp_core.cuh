@@ -81,7 +81,7 @@ struct CtaCtx {
   uint32_t tmem_base;
 };
 
-// all 320 threads
+// all threads of the CTA
 __device__ __forceinline__ CtaCtx cta_setup(uint8_t* smem_raw) {
   CtaCtx c;
   // align inside the shared window with pointer arithmetic only (keeps the shared address space

@@ -1,11 +1,13 @@
 // The render kernels of libnjf_b200.so (sm_100a):
-//   proposal_kernel : uniform/PDF bins -> positions -> gather + posenc -> ResnetFC (tcgen05) ->
-//                     sigma -> transmittance weights -> PDF resampling  (one proposal level)
-//   field_kernel    : final bins -> gather + posenc -> density trunk, colour head, Jacobian head
-//                     (cross-attention or MLP) -> transmittance weights -> alpha compositing
+//   proposal_kernel : spacing bins -> positions -> gather + posenc -> ResnetFC (tcgen05) -> delta * sigma
+//   pdf_kernel      : transmittance weights + PDF resampling of one proposal level, one warp per ray
+//   field_kernel    : final bins -> gather + posenc -> query embedding (cross-attention head: handed to
+//                     xf_kernel, xf_head.cu) -> density trunk, colour head (and the MLP Jacobian trunk) ->
+//                     transmittance weights -> alpha compositing
 //   finish_kernel   : call-global depth clip, J.u flow, projection to the target camera
-//   hoist_kernel    : lin_z / query 1x1 "convolutions" applied once per image (fp32 SIMT GEMM)
-// plus the standalone sampler kernels.  See DESIGN.md for the data layout and rooflines.
+//   hoist_kernel    : fp32 SIMT variant of the hoist GEMM (A/B checks only; the product path is hoist_tc.cu)
+// plus the standalone sampler / point-query kernels and the host launchers of the C ABI.
+// See DESIGN.md for the data layout and rooflines.
 #include "render.cuh"
 #include "njf_internal.h"
 #include <cstdlib>
