@@ -166,3 +166,19 @@ def test_levenberg_marquardt_driver_cpu():
     # a prior pulls towards the start and is honoured in the reported cost
     u2, hist2 = levenberg_marquardt(terms, torch.zeros(B, A), iters=10, prior_weight=1e3)
     assert float(u2.abs().max()) < float(u.abs().max())
+
+
+def test_joint_sensitivity_matches_reference():
+    """njf_b200.visualization against outputs of the reference's inference/jacobian_color_map.py
+    (tests/golden/joint_sensitivity.npz; generated with matplotlib / cv2 stubbed)."""
+    import numpy as np
+    from njf_b200 import visualization as V
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "joint_sensitivity.npz"))
+    J, E, cm = torch.from_numpy(z["J"]), torch.from_numpy(z["E"]), torch.from_numpy(z["cm"])
+    np.testing.assert_allclose(V.compute_joint_sensitivity(J, None, 0).numpy(), z["s0"], atol=1e-6)
+    np.testing.assert_allclose(V.compute_joint_sensitivity(J, E[0], 1).numpy(), z["s1"], atol=1e-6)
+    np.testing.assert_allclose(V.compute_joint_sensitivity(J, E[:, None, None, None], 0).numpy(), z["s2"], atol=1e-6)
+    img = V.visualize_joint_sensitivity(torch.from_numpy(z["s0"]), cm)
+    assert img.dtype == np.uint8 and int(np.abs(img.astype(int) - z["img0"].astype(int)).max()) <= 1
+    assert np.allclose(np.array(V.JACOBIAN_COLORMAP["model_allegro"]).T, z["cm"])
