@@ -167,14 +167,49 @@ def rays_fixture():
     print("rays", {k: v.shape for k, v in out.items()})
 
 
+def joint_sensitivity_fixture():
+    """Reference inference/jacobian_color_map.py:53-109 (compute_joint_sensitivity, visualize_joint_sensitivity).
+    The module imports matplotlib / cv2 at the top without using them in these functions: empty stand-ins."""
+    import types
+
+    ref_shim.install()
+    for name in ("matplotlib", "matplotlib.pyplot", "cv2"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["matplotlib"], "pyplot"):
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    from neural_jacobian_field.inference import jacobian_color_map as ref  # type: ignore
+
+    g = torch.Generator().manual_seed(0)
+    J = torch.randn(2, 5, 7, 24, generator=g)
+    Q, _ = torch.linalg.qr(torch.randn(2, 3, 3, generator=g))
+    E = torch.eye(4)[None].repeat(2, 1, 1)
+    E[:, :3, :3] = Q
+    E[:, :3, 3] = torch.randn(2, 3, generator=g)
+    s0 = ref.compute_joint_sensitivity(J, None, 0)
+    s1 = ref.compute_joint_sensitivity(J, E[0], 1)
+    s2 = ref.compute_joint_sensitivity(J, E[:, None, None, None], 0)
+    cm = torch.tensor(ref.JACOBIAN_COLORMAP["model_allegro"]).T
+    np.savez_compressed(os.path.join(OUT, "joint_sensitivity.npz"), J=J.numpy(), E=E.numpy(), s0=s0.numpy(), s1=s1.numpy(),
+                        s2=s2.numpy(), img0=ref.visualize_joint_sensitivity(s0, cm), cm=cm.numpy())
+    print("joint_sensitivity")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     if len(sys.argv) > 1 and sys.argv[1] == "rays":
         rays_fixture()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "joint_sensitivity":
+        joint_sensitivity_fixture()
+        sys.exit(0)
     pdf_fixture()
     rays_fixture()
+    joint_sensitivity_fixture()
     render_fixture("render_transformer", "jacobian_transformer", 8, (16,), 24, wseed=11)
     render_fixture("render_mlp", "jacobian_mlp", 6, (16,), 24, wseed=12)
     render_fixture("render_transformer_2prop_b2", "jacobian_transformer", 8, (16, 12), 16, wseed=13, batch=2,
