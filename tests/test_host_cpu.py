@@ -182,3 +182,35 @@ def test_joint_sensitivity_matches_reference():
     img = V.visualize_joint_sensitivity(torch.from_numpy(z["s0"]), cm)
     assert img.dtype == np.uint8 and int(np.abs(img.astype(int) - z["img0"].astype(int)).max()) <= 1
     assert np.allclose(np.array(V.JACOBIAN_COLORMAP["model_allegro"]).T, z["cm"])
+
+
+def test_c_abi_argument_errors_without_a_gpu():
+    """Argument validation of the C ABI happens before any CUDA call: every bad call returns non-zero and leaves a
+    message in njf_last_error() (the Python layer turns it into NjfError) -- checked here without a device."""
+    import ctypes
+
+    from njf_b200 import _lib, api
+
+    L = api._declare()
+    err = lambda: L.njf_last_error().decode()
+    # unsupported encoder width / head / action_dim are rejected by njf_field_create before it touches the device
+    h = ctypes.c_void_p()
+    arr = (api.NjfTensor * 1)()
+    for desc, frag in ((api.NjfFieldDesc(api.HEADS["jacobian_transformer"], 8, 1, 256, 1), "encoder_dim"),
+                       (api.NjfFieldDesc(api.HEADS["jacobian_transformer"], 9, 1, 512, 1), "action_dim"),
+                       (api.NjfFieldDesc(7, 8, 1, 512, 1), "head"),
+                       (api.NjfFieldDesc(api.HEADS["jacobian_mlp"], 6, 9, 512, 1), "n_proposal")):
+        assert L.njf_field_create(ctypes.byref(desc), arr, 0, ctypes.byref(h)) != 0
+        assert frag in err(), err()
+    # a missing tensor is named
+    desc = api.NjfFieldDesc(api.HEADS["jacobian_mlp"], 6, 1, 512, 1)
+    assert L.njf_field_create(ctypes.byref(desc), arr, 0, ctypes.byref(h)) != 0 and "missing tensor" in err()
+    with pytest.raises(_lib.NjfError):
+        _lib.check(L.njf_field_create(ctypes.byref(desc), arr, 0, ctypes.byref(h)))
+    with pytest.raises(_lib.NjfError):
+        api.Field("flow_mlp", 8, 1, {})                       # ablation decoder: no kernel, fails loudly
+    # null / inconsistent arguments of the stand-alone entry points
+    assert L.njf_make_rays(None, None, None, 1, 4, 2, 2, None, None, None, None) != 0 and "null" in err()
+    assert L.njf_pdf_sample(None, None, 0, None, 0, 1, 8, 8, 1.0, 8, None, None, None) != 0
+    assert L.njf_flow_gn_terms(None, None, None, None, None, None, None, 10, 10, 6, None, None, None, None, None) != 0
+    assert L.njf_flow_gn_workspace_doubles(3) > 0
