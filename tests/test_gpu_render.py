@@ -227,10 +227,12 @@ def test_compute_density_point_queries():
     np.testing.assert_allclose(p_d.cpu().numpy(), z.numpy(), atol=1e-5, rtol=1e-5)
 
 
-@pytest.mark.parametrize("R,s_prop,s_nerf", [(1, (37,), 53), (7, (24,), 8), (129, (130,), 129), (33, (512,), 300)])
+@pytest.mark.parametrize("R,s_prop,s_nerf", [(1, (37,), 53), (7, (24,), 8), (129, (130,), 129), (33, (512,), 300),
+                                             (5, (96,), 96), (11, (160,), 32)])
 def test_ragged_sizes_vs_oracle(R, s_prop, s_nerf):
     """Ragged shapes: a single ray, ray counts that do not fill a tile, sample counts that are not
-    powers of two / not multiples of the tile, and rays longer than one tile (S > 128)."""
+    powers of two / not multiples of the tile, rays longer than one tile (S > 128), and multiples of 32 that leave
+    padding rows in the tile (96) or pack several rays per tile (32) -- the per-warp fast paths of the scans."""
     from njf_b200 import api
     from njf_b200.render import render
 
