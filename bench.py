@@ -405,7 +405,10 @@ def main():
                      "executes fewer FLOPs (hoist + fold) and gathers from L2-resident fp16 maps, so fractions may exceed 1")
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        roof["traffic"] = json.load(open(tp)).get(dom)
+        t = json.load(open(tp)).get(dom)   # ncu --set full capture of this build (profiles/ncu_*_summary.json)
+        if t:
+            roof["traffic"] = t["bytes_per_launch"]          # dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch
+            roof["traffic_detail"] = t
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
