@@ -298,6 +298,9 @@ def main():
         setattr(a, k, api.dptr(t))
     a.level_bins[0] = api.dptr(lb)
     a.minmax = api.dptr(minmax)
+    ws = torch.empty(fld.workspace_bytes(1, R, S_PROP, S_NERF), dtype=torch.uint8, device=dev)   # caller-owned scratch
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    a.packed = api.dptr(packed)
     gathered = torch.empty(world * packed.numel(), **f32) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -314,8 +317,7 @@ def main():
         _lib.check(L.njf_field_pass(h, ctypes.byref(cams), ctypes.byref(a), api.dptr(lb), S_NERF + 1, st()))
         if e: e[3].record()
         _lib.check(L.njf_finish_pass(h, ctypes.byref(cams), ctypes.byref(a), st()))
-        if world > 1:
-            torch.cat([outs[k][0] for k in ("rgb", "depth", "flow", "jbar", "p", "pw")], dim=1, out=packed)
+        if world > 1:   # finish_kernel wrote the packed per-ray struct: one collective, no torch.cat
             dist.all_gather_into_tensor(gathered, packed.view(-1))
         if e:
             e[4].record()

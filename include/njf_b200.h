@@ -11,7 +11,10 @@
  * Conventions: plain pointers and sizes only; all tensors fp32, contiguous, row-major; pointers
  * are DEVICE pointers unless a parameter says "host"; every call enqueues on `stream`
  * (a cudaStream_t passed as void*) and returns 0 on success, non-zero on failure with a message
- * in njf_last_error().  Nothing is allocated behind the caller's back except inside NjfField.
+ * in njf_last_error().  Nothing is allocated behind the caller's back: NjfField owns only the packed
+ * weights it is created with; every pass writes into caller-provided outputs and a caller-provided
+ * `workspace` (njf_workspace_bytes), so a frame can be captured into a CUDA graph and two streams can
+ * render from one NjfField concurrently as long as each uses its own workspace.
  * There is no CPU fallback anywhere in this library.
  */
 #ifndef NJF_B200_H_
@@ -45,8 +48,13 @@ typedef struct NjfFieldDesc {
   int action_dim;    /* A: transformer head A <= 8, MLP head A <= 10 */
   int n_proposal;    /* number of proposal networks, 1..NJF_MAX_LEVELS */
   int encoder_dim;   /* must be 512 (EncoderResnet.get_output_dim, models/encoder/encoder_resnet.py:88) */
-  int sh_fp16_round; /* 1: round the SH-16 direction encoding through fp16 like tiny-cuda-nn does */
+  int sh_fp16_round; /* 1: round the SH-16 direction encoding through fp16 like tiny-cuda-nn does (the encoding is an
+                        fp16 tensor-core operand of the colour head here, so it is rounded either way) */
+  int sh_convention; /* NJF_SH_TCNN (default, what SHEncoding(implementation="tcnn") computes: signs of tiny-cuda-nn,
+                        input re-mapped x*2-1) or NJF_SH_NERFSTUDIO_TORCH (nerfstudio's torch fallback
+                        components_from_spherical_harmonics: its sign set, evaluated on the [0,1] input as passed) */
 } NjfFieldDesc;
+enum { NJF_SH_TCNN = 0, NJF_SH_NERFSTUDIO_TORCH = 1 };
 
 typedef struct NjfTensor {
   const char* name;  /* reference state-dict key without the "model." prefix, e.g.
@@ -129,7 +137,21 @@ typedef struct NjfRenderArgs {
   int32_t* level_inds[NJF_MAX_LEVELS]; /* [B][R][n_l+1] searchsorted results */
   float* minmax;                  /* REQUIRED workspace: 2 floats; after njf_field_pass = (min, max) of steps over the call
                                      (all-reduce it across ranks before njf_finish_pass when one call is ray-sharded) */
+  /* caller-owned scratch ("caller allocates outputs and a workspace"): holds delta*sigma between
+     proposal_kernel and pdf_kernel (when prop_weights[l] is NULL) and the fp16 query-embedding hand-over between
+     field_kernel and xf_kernel (cross-attention head).  Any size >= njf_workspace_min_bytes works: a pass whose
+     intermediates do not fit runs as several launch groups over ray ranges (bit-identical results);
+     njf_workspace_bytes returns the size at which no pass is split more than needed to keep the hand-over
+     <= 256 MiB.  16-byte aligned. */
+  void* workspace;
+  size_t workspace_bytes;
+  float* packed;                  /* optional [B][R][12+3A]: rgb3 | depth1 | flow2 | jbar3A | p3 | pw3 per ray, written by
+                                     njf_finish_pass (one buffer for the multi-GPU gather) */
 } NjfRenderArgs;
+
+/* workspace sizing for a (B, R, sample-count) render with this field */
+size_t njf_workspace_bytes(const NjfField* f, int B, int R, int n_levels, const int* s_prop, int s_nerf);
+size_t njf_workspace_min_bytes(const NjfField* f, int n_levels, const int* s_prop, int s_nerf);
 
 int njf_render_forward(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* args, void* stream);
 
@@ -144,13 +166,20 @@ int njf_finish_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderAr
  * world-space points (no rays).  points [B][N][3]; sigma [B][N], geo [B][N][15], jac [B][N][3A]. */
 int njf_query_points(const NjfField* f, const float* ctxt_w2c, const float* ctxt_k, const void* maps, int Hf,
                      int Wf, const float* points, int B, int N, float* sigma, float* geo, float* jac,
-                     void* stream);
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* workspace for njf_query_points (cross-attention head hand-over; 0 for the MLP head) */
+size_t njf_query_workspace_bytes(const NjfField* f, int B, int N);
 /* by-products returned by the reference's DensityHeadOutput: positional encoding (63) of the
  * context-camera point and the bilinear gather of the RAW encoder features (NCHW fp32, C channels);
  * either output may be NULL.  (pixel_aligned_features.py:11-35, action_decoder_jacobian.py:97-104) */
 int njf_point_features(const float* feat_nchw, const float* ctxt_w2c, const float* ctxt_k, const float* points,
                        int B, int N, int C, int Hf, int Wf, float* xyz_features, float* pixel_aligned_features,
                        void* stream);
+
+/* ---- inverse of n 4x4 poses (torch.inverse in rendering/geometry.py:59-65 transform_world2cam and :206-215):
+ * Gauss-Jordan with partial pivoting in fp64, rounded to fp32 -- on the device, so that a frame needs no host
+ * LAPACK call and no host->device copy of the inverted matrices.  in/out [n][16]. */
+int njf_invert_poses(const float* c2w, float* w2c, int n, void* stream);
 
 /* ---- ray bundle of a view (rendering/geometry.py:117-134 get_pixel_coordinates, :170-203 get_world_rays_with_z,
  * models/model.py:215-226): k_norm [B][9] normalised intrinsics, c2w [B][16]; coords_xy [B][R][2] normalised pixel

@@ -142,8 +142,15 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
   Builder b;
   for (int i = 0; i < n_tensors; ++i) b.t[tensors[i].name] = {tensors[i].data, tensors[i].numel};
 
-  auto* f = new NjfField();   // value-initialised: all tables start at zero
+  // owned until success: every failure path below frees the device buffers already allocated
+  struct Guard {
+    NjfField* f;
+    ~Guard() { if (f) njf_field_destroy(f); }
+  } guard{new NjfField()};   // value-initialised: all tables start at zero
+  NjfField* f = guard.f;
   f->desc = *desc;
+  if (desc->sh_convention != NJF_SH_TCNN && desc->sh_convention != NJF_SH_NERFSTUDIO_TORCH)
+    NJF_FAIL("unknown sh_convention %d", desc->sh_convention);
   // hoist channel order: proposal nets (384 each), then the main map (dens 384 + head part)
   for (int i = 0; i < desc->n_proposal; ++i) {
     const std::string p = "proposal_networks." + std::to_string(i) + ".density_head";
@@ -258,15 +265,10 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
     trunk_lin_in(b, fp, "decoder.jacobian_head");
     trunk_blocks(b, fp, "decoder.jacobian_head", 3 * A, 32);
   }
-  if (!b.err.empty()) {
-    delete f;
-    NJF_FAIL("njf_field_create: %s", b.err.c_str());
-  }
+  if (!b.err.empty()) NJF_FAIL("njf_field_create: %s", b.err.c_str());
   f->ch_total = desc->n_proposal * f->ch_prop + f->ch_main;
-  if (static_cast<int>(b.hoist_b.size()) != f->ch_total) {
-    delete f;
+  if (static_cast<int>(b.hoist_b.size()) != f->ch_total)
     NJF_FAIL("internal: hoist rows %zu != %d", b.hoist_b.size(), f->ch_total);
-  }
   NJF_CUDA(cudaMalloc(&f->d_blob, b.blob.size()));
   NJF_CUDA(cudaMalloc(&f->d_hoist_w, b.hoist_w.size() * sizeof(float)));
   NJF_CUDA(cudaMalloc(&f->d_hoist_b, b.hoist_b.size() * sizeof(float)));
@@ -282,6 +284,7 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
   if (njf_hoist_build(f, b.hoist_w, b.hoist_b)) return 1;
   for (int i = 0; i < desc->n_proposal; ++i) f->prop_blob[i] = f->d_blob;
   f->field_blob = f->d_blob;
+  guard.f = nullptr;
   *out = f;
   return 0;
 }
@@ -290,8 +293,6 @@ extern "C" void njf_field_destroy(NjfField* f) {
   if (!f) return;
   cudaFree(f->d_blob);
   cudaFree(f->d_hoist_img);
-  cudaFree(f->d_scratch);
-  cudaFree(f->d_xf_scratch);
   cudaFree(f->d_xf_blob);
   cudaFree(f->d_hoist_w);
   cudaFree(f->d_hoist_b);

@@ -22,7 +22,7 @@ struct XfParams {
   int A;
   // tiling of the pass: identical to field_kernel's (render.cuh PassGeom)
   int NR, S, G, T, NG, group0;
-  const float4* qs;    // [tile][16 chunks][128 rows] float4: the 64-wide query embedding of every row
+  const uint4* qs;     // [tile][8 chunks][128 rows] x 8 fp16: the 64-wide query embedding of every row
   const float* wts;    // [tile][128 rows] transmittance weight of the sample (0 for padding rows)
   float* jbar;         // [NR][3A] or null
   float* jac_out;      // [NR*S][3A] or null
@@ -36,10 +36,6 @@ struct NjfField {
   struct HoistJobHost { int map, c0, N; uint32_t w_off; int bias_off; };
   NjfFieldDesc desc;
   uint8_t* d_hoist_img = nullptr;          // tcgen05 weight images of the hoist GEMM (hoist_tc.cu)
-  mutable float* d_scratch = nullptr;      // grow-only per-field scratch (proposal weights between the
-  mutable size_t scratch_bytes = 0;        // proposal kernel and the PDF kernel); one stream at a time
-  mutable float* d_xf_scratch = nullptr;   // grow-only: query stream + sample weights between field_kernel
-  mutable size_t xf_scratch_bytes = 0;     // and xf_kernel (transformer head)
   njf::Program head_prog;                  // transformer head: steps of xf_kernel
   uint8_t* d_xf_blob = nullptr;
   uint32_t xf_bytes = 0;

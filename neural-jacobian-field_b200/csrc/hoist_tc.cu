@@ -11,6 +11,7 @@
 // columns) stay in TMEM until the bias + fp16 epilogue.
 #include "field.h"
 #include "njf_internal.h"
+#include <atomic>
 
 namespace njf {
 
@@ -192,11 +193,13 @@ int njf_hoist_build(NjfField* f, const std::vector<float>& w, const std::vector<
 
 int njf_hoist_launch(const NjfField* f, const float* feat_nchw, int B, int Hf, int Wf, void* maps_out,
                      cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static std::atomic<bool> attr[64];  // the opt-in applies to the current device only
+  if (dev >= 0 && dev < 64 && !attr[dev].load(std::memory_order_acquire)) {
     NJF_CUDA(cudaFuncSetAttribute(hoist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kHoistSmem)));
-    attr = true;
+    attr[dev].store(true, std::memory_order_release);
   }
   HoistParams p{};
   p.feat = feat_nchw;

@@ -306,6 +306,28 @@ __device__ __forceinline__ void epi_relu_to_a(const EpiCtx& e, int tcol, int c0)
   a_store32(e, c0, p);
 }
 
+// 64 accumulator columns [tcol, tcol+64) -> ReLU -> fp16 -> A tile columns [c0, c0+64): the second TMEM load is
+// issued before the first half is converted and stored, so its latency hides behind that work
+__device__ __forceinline__ void epi_relu_to_a64(const EpiCtx& e, int tcol, int c0) {
+  uint32_t r0[32], r1[32];
+  tmem_ld32(e.tmem + tcol, r0);
+  tmem_ld_wait();
+  tmem_ld32(e.tmem + tcol + 32, r1);
+  {
+    uint32_t p[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p[j] = pack_relu_f16x2(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+    a_store32(e, c0, p);
+  }
+  tmem_ld_wait();
+  {
+    uint32_t p[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p[j] = pack_relu_f16x2(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+    a_store32(e, c0 + 32, p);
+  }
+}
+
 // x[c0..c0+32) (+= tz_staging[row][c0..], written back to TMEM so later accumulating MMAs see it)
 // -> ReLU -> fp16 -> A tile.  Biases are accumulated by the tensor core (kStepBias).
 template <bool kHasTz>

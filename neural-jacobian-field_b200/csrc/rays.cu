@@ -79,3 +79,64 @@ extern "C" int njf_make_rays(const float* k_norm, const float* c2w, const float*
   NJF_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---- inverse of 4x4 poses: Gauss-Jordan with partial pivoting in fp64, one thread per matrix, rounded to fp32
+// (rendering/geometry.py:59-65 transform_world2cam and :206-215 call torch.inverse on the fp32 pose)
+namespace njf {
+__global__ void invert_poses_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      a[r][c] = static_cast<double>(in[i * 16 + r * 4 + c]);
+      a[r][4 + c] = (r == c) ? 1.0 : 0.0;
+    }
+#pragma unroll
+  for (int col = 0; col < 4; ++col) {
+    int piv = col;
+    double best = fabs(a[col][col]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r > col && fabs(a[r][col]) > best) {
+        best = fabs(a[r][col]);
+        piv = r;
+      }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r == piv && piv != col) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const double t = a[col][c];
+          a[col][c] = a[r][c];
+          a[r][c] = t;
+        }
+      }
+    const double inv = 1.0 / a[col][col];  // singular pose -> inf/nan, like torch.inverse raising / returning garbage
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[col][c] *= inv;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (r != col) {
+        const double fct = a[r][col];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[r][c] -= fct * a[col][c];
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[i * 16 + r * 4 + c] = static_cast<float>(a[r][4 + c]);
+}
+}  // namespace njf
+
+extern "C" int njf_invert_poses(const float* c2w, float* w2c, int n, void* stream_) {
+  using namespace njf;
+  if (!c2w || !w2c) NJF_FAIL("njf_invert_poses: null argument");
+  if (n < 1) return 0;
+  invert_poses_kernel<<<(n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream_)>>>(c2w, w2c, n);
+  NJF_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -10,6 +10,7 @@
 // See DESIGN.md for the data layout and rooflines.
 #include "render.cuh"
 #include "njf_internal.h"
+#include <atomic>
 #include <cstdlib>
 
 namespace njf {
@@ -100,8 +101,10 @@ struct ProposalParams {
   float anneal;
   int sum_vec;
   float* bins_out;       // [NR][n_out+1]
-  float* weights_out;    // [NR][S]: input of the PDF step, which runs as its own kernel afterwards (one warp
-                         // per ray, fully parallel -- in here a single warp per tile would do it while seven wait)
+  float* weights_out;    // [rays of this launch][S]: input of the PDF step, which runs as its own kernel afterwards
+                         // (one warp per ray, fully parallel -- in here a single warp per tile would do it while
+                         // seven wait); row 0 belongs to ray `w_ray0`
+  int w_ray0;
   int32_t* inds_out;     // optional [NR][n_out+1]
 };
 
@@ -129,8 +132,9 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
     SlotScratch* sc = slot_scratch(c, e.slot);
     const int lane = threadIdx.x & 31;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-      const int group = 2 * it + e.slot;
-      if (group >= g.NG) continue;
+      const int lgroup = 2 * it + e.slot;  // launch-local ray group
+      if (lgroup >= g.NG) continue;
+      const int group = g.group0 + lgroup;
       for (int tile = 0; tile < g.T; ++tile) {
         RowState rs;
         PROF(e, kPOther);
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
         }
         // delta*sigma goes out; the per-ray kernel that follows does the transmittance scan
         // (RaySamples.get_weights) and the PDF resampling with one warp per ray
-        if (e.half == 0 && rs.ray >= 0) p.weights_out[static_cast<size_t>(rs.ray) * g.S + rs.s] = dd;
+        if (e.half == 0 && rs.ray >= 0) p.weights_out[static_cast<size_t>(rs.ray - p.w_ray0) * g.S + rs.s] = dd;
         PROF(e, kPWeights);
       }
     }
@@ -175,13 +179,14 @@ struct FieldParams {
   PassGeom g;
   int head_kind;   // NJF_HEAD_*
   int A;
+  int sh_conv;     // NJF_SH_*
   // per-ray outputs
   float* rgb; float* depth; float* jbar; float* p;
   // per-sample outputs
   float* steps; float* weights; float* sigma; float* jac_out; float* positions; float* rgb_samples;
   float* geo_out;    // [NR*S][15] density-head geometry features (point queries)
   // transformer head: hand-over to xf_kernel (indexed by the launch-local tile number)
-  float4* qs;        // [tile][16][128] query embedding
+  uint4* qs;         // [tile][8 chunks][128 rows] x 8 fp16: query embedding
   float* wts;        // [tile][128] sample weights (0 for padding rows)
   uint32_t* minmax;  // [2] ordered-uint encoded min / max of steps
 };
@@ -196,9 +201,10 @@ __device__ __forceinline__ void ld_acc32(const EpiCtx& e, float (&v)[32]) {
 }
 // Query embedding of the cross-attention head (action_decoder_jacobian.py:423-430):
 //   q0 = W_q . [enc | xyz] + b_q (tensor core, q_enc step) + hoisted W_q[:, 63:] . feat
-// Each of the row's two threads owns 32 of the 64 values and streams them to the `qs` scratch that
-// xf_kernel consumes ([tile][16 chunks of 4][128 rows] float4: warp stores are 512 contiguous bytes).
-__device__ __forceinline__ void store_query_stream(const EpiCtx& e, float4* qs_tile) {
+// Each of the row's two threads owns 32 of the 64 values and streams them, rounded to fp16 (they feed a
+// LayerNorm and fp16 tensor-core operands next), to the `qs` hand-over that xf_kernel consumes
+// ([tile][8 chunks of 8 values][128 rows] uint4: warp stores are 512 contiguous bytes; 128 B per sample).
+__device__ __forceinline__ void store_query_stream(const EpiCtx& e, uint4* qs_tile) {
   float x[32];
   ld_acc32(e, x);
 #pragma unroll
@@ -212,34 +218,43 @@ __device__ __forceinline__ void store_query_stream(const EpiCtx& e, float4* qs_t
       x[8 * j + 2 * t + 1] += f.y;
     }
   }
-  float4* dst = qs_tile + (8 * e.half) * kRows + e.row;
+  uint4* dst = qs_tile + (4 * e.half) * kRows + e.row;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) __stcs(dst + j * kRows, make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
+  for (int j = 0; j < 4; ++j)
+    __stcs(dst + j * kRows, make_uint4(pack_f16x2(x[8 * j], x[8 * j + 1]), pack_f16x2(x[8 * j + 2], x[8 * j + 3]),
+                                       pack_f16x2(x[8 * j + 4], x[8 * j + 5]), pack_f16x2(x[8 * j + 6], x[8 * j + 7])));
 }
 
-// SH degree 4 (tiny-cuda-nn convention) of the unit direction (action_decoder_jacobian.py:194-199)
-__device__ __forceinline__ void sh16(float dx, float dy, float dz, float (&o)[16]) {
-  // get_normalized_directions then tcnn's internal x*2-1
-  const float x = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(dx, 1.f), 0.5f), 2.f), 1.f);
-  const float y = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(dy, 1.f), 0.5f), 2.f), 1.f);
-  const float z = __fsub_rn(__fmul_rn(__fmul_rn(__fadd_rn(dz, 1.f), 0.5f), 2.f), 1.f);
+// SH degree 4 of the unit direction (action_decoder_jacobian.py:194-199): the colour head's directional encoding.
+//  conv = NJF_SH_TCNN            : tiny-cuda-nn's SphericalHarmonics (input d01 re-mapped x*2-1, tcnn's signs)
+//  conv = NJF_SH_NERFSTUDIO_TORCH: nerfstudio's torch fallback (components_from_spherical_harmonics evaluated on
+//                                  the [0,1] input as passed, all-positive leading signs)
+__device__ __forceinline__ void sh16(float dx, float dy, float dz, int conv, float (&o)[16]) {
+  // get_normalized_directions: (d + 1) / 2
+  const float hx = __fmul_rn(__fadd_rn(dx, 1.f), 0.5f), hy = __fmul_rn(__fadd_rn(dy, 1.f), 0.5f),
+              hz = __fmul_rn(__fadd_rn(dz, 1.f), 0.5f);
+  const bool tc = conv == NJF_SH_TCNN;
+  const float x = tc ? __fsub_rn(__fmul_rn(hx, 2.f), 1.f) : hx;
+  const float y = tc ? __fsub_rn(__fmul_rn(hy, 2.f), 1.f) : hy;
+  const float z = tc ? __fsub_rn(__fmul_rn(hz, 2.f), 1.f) : hz;
+  const float sg = tc ? -1.f : 1.f;  // tcnn flips the sign of the odd-in-(x,y) terms below
   const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
   o[0] = 0.28209479177387814f;
-  o[1] = -0.48860251190291987f * y;
+  o[1] = sg * 0.48860251190291987f * y;
   o[2] = 0.48860251190291987f * z;
-  o[3] = -0.48860251190291987f * x;
+  o[3] = sg * 0.48860251190291987f * x;
   o[4] = 1.0925484305920792f * xy;
-  o[5] = -1.0925484305920792f * yz;
+  o[5] = sg * 1.0925484305920792f * yz;
   o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
-  o[7] = -1.0925484305920792f * xz;
+  o[7] = sg * 1.0925484305920792f * xz;
   o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-  o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+  o[9] = sg * 0.59004358992664352f * y * (3.0f * x2 - y2);
   o[10] = 2.8906114426405538f * xy * z;
-  o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+  o[11] = sg * 0.45704579946446572f * y * (5.0f * z2 - 1.0f);
   o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
-  o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+  o[13] = sg * 0.45704579946446572f * x * (5.0f * z2 - 1.0f);
   o[14] = 1.4453057213202769f * z * (x2 - y2);
-  o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+  o[15] = sg * 0.59004358992664352f * x * (x2 - 3.0f * y2);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constant__ FieldParams p) {
@@ -298,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         if (p.head_kind == NJF_HEAD_TRANSFORMER) {
           gather_segment<64>(e, g, sc->taps, 384);
           epi_wait_acc(e);
-          if (p.qs) store_query_stream(e, p.qs + tidx * 16 * kRows);
+          if (p.qs) store_query_stream(e, p.qs + tidx * 8 * kRows);
           PROF(e, kPHead);
         }
         gather_segment<128>(e, g, sc->taps, 0);
@@ -335,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           a_store16(e, 0, pk);
         } else {
           float sh[16];
-          sh16(dv[0], dv[1], dv[2], sh);
+          sh16(dv[0], dv[1], dv[2], p.sh_conv, sh);
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 7; ++j) pk[j] = pack_f16x2(sh[1 + 2 * j], sh[2 + 2 * j]);
@@ -550,6 +565,8 @@ struct FinishParams {
   const float* p;
   float* pw;
   float* flow;
+  const float* rgb;
+  float* packed;         // optional [NR][12 + 3A]: rgb3 | depth1 | flow2 | jbar3A | p3 | pw3
 };
 __device__ __forceinline__ void project_uv(const float* W, const float* K, float x, float y, float z, float& u,
                                            float& v) {
@@ -567,9 +584,19 @@ __global__ void finish_kernel(const FinishParams q) {
   const int ray = blockIdx.x * blockDim.x + threadIdx.x;
   if (ray >= q.NR) return;
   const int b = ray / q.R;
-  if (q.depth && q.minmax) {
-    const float lo = q.minmax[0], hi = q.minmax[1];
-    q.depth[ray] = fminf(fmaxf(q.depth[ray], lo), hi);
+  const int A3 = 3 * q.A;
+  float* pk = q.packed ? q.packed + static_cast<size_t>(ray) * (12 + A3) : nullptr;
+  float dep = 0.f;
+  if (q.depth) {
+    dep = q.depth[ray];
+    if (q.minmax) {
+      dep = fminf(fmaxf(dep, q.minmax[0]), q.minmax[1]);
+      q.depth[ray] = dep;
+    }
+  }
+  if (pk) {
+    if (q.rgb) { pk[0] = q.rgb[ray * 3]; pk[1] = q.rgb[ray * 3 + 1]; pk[2] = q.rgb[ray * 3 + 2]; }
+    pk[3] = dep;
   }
   if (!q.p || !q.jbar) return;
   const float px = q.p[ray * 3], py = q.p[ray * 3 + 1], pz = q.p[ray * 3 + 2];
@@ -577,7 +604,11 @@ __global__ void finish_kernel(const FinishParams q) {
   for (int a = 0; a < q.A; ++a) {
     const float ua = __ldg(q.action + b * q.A + a);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) f[d] = fmaf(q.jbar[static_cast<size_t>(ray) * 3 * q.A + a * 3 + d], ua, f[d]);
+    for (int d = 0; d < 3; ++d) {
+      const float jv = q.jbar[static_cast<size_t>(ray) * A3 + a * 3 + d];
+      f[d] = fmaf(jv, ua, f[d]);
+      if (pk) pk[6 + a * 3 + d] = jv;
+    }
   }
   const float wx = px + f[0], wy = py + f[1], wz = pz + f[2];
   if (q.pw) {
@@ -585,12 +616,22 @@ __global__ void finish_kernel(const FinishParams q) {
     q.pw[ray * 3 + 1] = wy;
     q.pw[ray * 3 + 2] = wz;
   }
-  if (q.flow) {
+  float fu = 0.f, fv = 0.f;
+  if (q.flow || pk) {
     float u0, v0, u1, v1;
     project_uv(q.trgt_w2c + b * 16, q.trgt_k + b * 9, px, py, pz, u0, v0);
     project_uv(q.trgt_w2c + b * 16, q.trgt_k + b * 9, wx, wy, wz, u1, v1);
-    q.flow[ray * 2] = u1 - u0;
-    q.flow[ray * 2 + 1] = v1 - v0;
+    fu = u1 - u0;
+    fv = v1 - v0;
+  }
+  if (q.flow) {
+    q.flow[ray * 2] = fu;
+    q.flow[ray * 2 + 1] = fv;
+  }
+  if (pk) {
+    pk[4] = fu; pk[5] = fv;
+    pk[6 + A3] = px; pk[7 + A3] = py; pk[8 + A3] = pz;
+    pk[9 + A3] = wx; pk[10 + A3] = wy; pk[11 + A3] = wz;
   }
 }
 
@@ -754,15 +795,24 @@ using namespace njf;
 
 namespace {
 
-int g_num_sms = 0;
+// per-device state: SM count and the >48 KB dynamic shared memory opt-in (cudaFuncSetAttribute applies to the
+// CURRENT device only, so a process that renders on several GPUs must opt in on each of them)
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  static std::atomic<int> sms[kMaxDevices];
+  const int dev = current_device();
+  int n = sms[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    sms[dev].store(n, std::memory_order_relaxed);
   }
-  return g_num_sms;
+  return n;
 }
 
 int make_geom(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a, int S, const float* bins,
@@ -816,6 +866,9 @@ int check_args(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a
   if (a->B < 1 || a->R < 1) NJF_FAIL("B=%d R=%d: nothing to render", a->B, a->R);
   if (a->n_levels != f->desc.n_proposal) NJF_FAIL("n_levels %d != field n_proposal %d", a->n_levels, f->desc.n_proposal);
   if (!a->origins || !a->dirs || !a->z_near || !a->z_far || !a->maps) NJF_FAIL("missing ray / map input");
+  if (a->Hf < 1 || a->Wf < 1 || a->Hf > 16384 || a->Wf > 16384) NJF_FAIL("feature map %dx%d out of range", a->Hf, a->Wf);
+  if (a->s_nerf < 1 || a->s_nerf > 512) NJF_FAIL("num_nerf_samples %d unsupported (1..512)", a->s_nerf);
+  if (static_cast<long long>(a->B) * a->R > 0x7fffffffLL / 512) NJF_FAIL("B*R = %lld rays: render in groups", static_cast<long long>(a->B) * a->R);
   if (static_cast<size_t>(a->B) * a->Hf * a->Wf * 768 * 2 >= (1ull << 32))
     NJF_FAIL("hoisted maps of %d views of %dx%d exceed the 4 GiB tap-offset range; render the views in groups", a->B, a->Hf, a->Wf);
   return 0;
@@ -823,23 +876,45 @@ int check_args(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a
 
 template <class K>
 int set_smem(K kernel) {
-  static bool done = false;
-  if (!done) {
+  static std::atomic<bool> done[kMaxDevices];  // one flag per (kernel instantiation, device)
+  const int dev = current_device();
+  if (!done[dev].load(std::memory_order_acquire)) {
     NJF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes)));
-    done = true;
+    done[dev].store(true, std::memory_order_release);
   }
   return 0;
 }
 
-// field_kernel (+ xf_kernel for the cross-attention head) over all ray groups of the pass.  The
-// transformer hand-over buffers (32.5 KB per 128-row tile) live in a grow-only scratch owned by the
-// field; passes with more than kXfMaxTiles tiles run as several launch pairs over ray-group ranges.
-constexpr int kXfMaxTiles = 160 * 1024;
+// field_kernel (+ xf_kernel for the cross-attention head) over all ray groups of the pass.  The transformer
+// hand-over (16.5 KB per 128-row tile: fp16 query embedding + fp32 sample weights) lives in the CALLER's
+// workspace; a pass with more tiles than the workspace holds runs as several launch pairs over ray-group
+// ranges that re-use the same bytes (so a small workspace stays L2-resident and never reaches HBM).
+constexpr size_t kXfTileBytes = 8 * kRows * sizeof(uint4) + kRows * sizeof(float);
+constexpr size_t kXfDefaultCap = 256ull << 20;  // njf_workspace_bytes: hand-over capped at 256 MiB
 // optional per-kernel timing of the field pass (njf_debug_field_timing): CUDA events on the launching stream
 bool g_time_field = false;
 std::vector<cudaEvent_t> g_field_events;  // triples (before field_kernel, between, after xf_kernel) per launch pair
 size_t g_field_events_used = 0;
-int launch_field(const NjfField* f, FieldParams& p, cudaStream_t stream) {
+
+// ray groups per launch pair for a hand-over region of `bytes`: whole rounds of all SMs (4 xf slots x SMs groups,
+// which is also a whole number of field_kernel slot pairs) so that no launch ends with a partly filled wave
+int xf_groups_per_launch(size_t bytes, int T, int NGtot) {
+  static const long env_tiles = [] {  // NJF_XF_MAX_TILES: smaller launch pairs (tests of the chunked path, L2 studies)
+    const char* v = getenv("NJF_XF_MAX_TILES");
+    return v ? atol(v) : 0L;
+  }();
+  size_t tiles = bytes / kXfTileBytes;
+  if (env_tiles > 0 && static_cast<size_t>(env_tiles) < tiles)  // never below one ray group if the workspace holds one
+    tiles = (static_cast<size_t>(env_tiles) < static_cast<size_t>(T) && tiles >= static_cast<size_t>(T))
+                ? static_cast<size_t>(T) : static_cast<size_t>(env_tiles);
+  long gpc = static_cast<long>(tiles / T);
+  if (gpc >= NGtot) return NGtot;
+  const long quantum = 4L * num_sms();
+  if (gpc > quantum) gpc -= gpc % quantum;
+  return static_cast<int>(gpc);
+}
+
+int launch_field(const NjfField* f, FieldParams& p, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (set_smem(field_kernel)) return 1;
   const int NGtot = p.g.NG, T = p.g.T;
   const bool xf = f->desc.head == NJF_HEAD_TRANSFORMER && (p.jbar || p.jac_out);
@@ -847,35 +922,15 @@ int launch_field(const NjfField* f, FieldParams& p, cudaStream_t stream) {
   float* jac = p.jac_out;
   int gpc = NGtot;  // groups per launch
   if (xf) {
-    static const int max_tiles = [] {  // NJF_XF_MAX_TILES: smaller launch pairs (tests of the chunked path)
-      const char* v = getenv("NJF_XF_MAX_TILES");
-      const int n = v ? atoi(v) : 0;
-      return n > 0 ? n : kXfMaxTiles;
-    }();
-    gpc = max_tiles / T;
-    if (gpc < 1) gpc = 1;
-    if (gpc > NGtot) gpc = NGtot;
-    constexpr size_t kTileBytes = 16 * kRows * sizeof(float4) + kRows * sizeof(float);
-    size_t tiles = static_cast<size_t>(gpc) * T;
-    if (f->xf_scratch_bytes < tiles * kTileBytes) {
-      if (f->d_xf_scratch) NJF_CUDA(cudaFree(f->d_xf_scratch));
-      f->d_xf_scratch = nullptr;
-      f->xf_scratch_bytes = 0;
-      // little free memory: halve the launch pairs until the hand-over buffer fits (down to one ray group)
-      while (cudaMalloc(&f->d_xf_scratch, tiles * kTileBytes) != cudaSuccess) {
-        (void)cudaGetLastError();
-        f->d_xf_scratch = nullptr;
-        if (gpc == 1) NJF_FAIL("out of device memory for the %zu-byte transformer hand-over buffer", tiles * kTileBytes);
-        gpc = (gpc + 1) / 2;
-        tiles = static_cast<size_t>(gpc) * T;
-      }
-      f->xf_scratch_bytes = tiles * kTileBytes;
-    } else {
-      // an existing (possibly smaller-than-wanted but sufficient) buffer: never launch more tiles than it holds
-      tiles = static_cast<size_t>(gpc) * T;
-    }
-    p.qs = reinterpret_cast<float4*>(f->d_xf_scratch);
-    p.wts = f->d_xf_scratch + tiles * 16 * kRows * 4;
+    if (!ws) NJF_FAIL("cross-attention head: NjfRenderArgs.workspace required (njf_workspace_bytes)");
+    if (reinterpret_cast<uintptr_t>(ws) & 15) NJF_FAIL("workspace must be 16-byte aligned");
+    gpc = xf_groups_per_launch(ws_bytes, T, NGtot);
+    if (gpc < 1)
+      NJF_FAIL("workspace of %zu bytes cannot hold one ray group of the query hand-over (%zu bytes)", ws_bytes,
+               static_cast<size_t>(T) * kXfTileBytes);
+    const size_t tiles = static_cast<size_t>(gpc) * T;
+    p.qs = static_cast<uint4*>(ws);
+    p.wts = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + tiles * 8 * kRows * sizeof(uint4));
   }
   if (f->desc.head == NJF_HEAD_TRANSFORMER) {
     p.jbar = nullptr;
@@ -914,6 +969,13 @@ int launch_field(const NjfField* f, FieldParams& p, cudaStream_t stream) {
   return 0;
 }
 
+// tile geometry of a pass with S samples per ray
+void tile_geom(int S, int NR, int& G, int& T, int& NG) {
+  G = S <= kRows ? kRows / S : 1;
+  T = S <= kRows ? 1 : (S + kRows - 1) / kRows;
+  NG = (NR + G - 1) / G;
+}
+
 }  // namespace
 
 #ifdef NJF_PROFILE
@@ -945,6 +1007,58 @@ extern "C" int njf_debug_field_timing(int enable, float* field_kernel_ms, float*
   g_field_events_used = 0;
   g_time_field = enable != 0;
   return 0;
+}
+
+extern "C" size_t njf_workspace_min_bytes(const NjfField* f, int n_levels, const int* s_prop, int s_nerf) {
+  if (!f || !s_prop) return 0;
+  size_t need = 16;
+  int G, T, NG;
+  for (int l = 0; l < n_levels && l < NJF_MAX_LEVELS; ++l) {
+    tile_geom(s_prop[l], 1, G, T, NG);
+    const size_t b = static_cast<size_t>(G) * s_prop[l] * sizeof(float);  // one ray group of delta*sigma
+    if (b > need) need = b;
+  }
+  if (f->desc.head == NJF_HEAD_TRANSFORMER) {
+    tile_geom(s_nerf, 1, G, T, NG);
+    const size_t b = static_cast<size_t>(T) * kXfTileBytes;  // one ray group of the query hand-over
+    if (b > need) need = b;
+  }
+  return (need + 255) & ~static_cast<size_t>(255);
+}
+
+extern "C" size_t njf_workspace_bytes(const NjfField* f, int B, int R, int n_levels, const int* s_prop, int s_nerf) {
+  if (!f || !s_prop || B < 1 || R < 1) return 0;
+  const int NR = B * R;
+  size_t need = njf_workspace_min_bytes(f, n_levels, s_prop, s_nerf);
+  int G, T, NG;
+  for (int l = 0; l < n_levels && l < NJF_MAX_LEVELS; ++l) {
+    size_t b = static_cast<size_t>(NR) * s_prop[l] * sizeof(float);
+    if (b > kXfDefaultCap) b = kXfDefaultCap;
+    if (b > need) need = b;
+  }
+  if (f->desc.head == NJF_HEAD_TRANSFORMER) {
+    tile_geom(s_nerf, NR, G, T, NG);
+    size_t b = static_cast<size_t>(NG) * T * kXfTileBytes;
+    if (b > kXfDefaultCap) {
+      // whole rounds of all SMs per launch pair (xf_groups_per_launch), at most the cap
+      const size_t round = static_cast<size_t>(4) * num_sms() * T * kXfTileBytes;
+      b = (kXfDefaultCap / round) * round;
+      if (b == 0) b = round;
+    }
+    if (b > need) need = b;
+  }
+  return (need + 255) & ~static_cast<size_t>(255);
+}
+
+extern "C" size_t njf_query_workspace_bytes(const NjfField* f, int B, int N) {
+  if (!f || f->desc.head != NJF_HEAD_TRANSFORMER || B < 1 || N < 1) return 256;
+  size_t tiles = (static_cast<size_t>(B) * N + kRows - 1) / kRows;
+  size_t b = tiles * kXfTileBytes;
+  if (b > kXfDefaultCap) {
+    const size_t round = static_cast<size_t>(4) * num_sms() * kXfTileBytes;
+    b = (kXfDefaultCap / round) * round;
+  }
+  return (b + 255) & ~static_cast<size_t>(255);
 }
 
 extern "C" size_t njf_hoisted_bytes(const NjfField* f, int B, int Hf, int Wf) {
@@ -990,29 +1104,53 @@ extern "C" int njf_proposal_pass(const NjfField* f, const NjfCameras* cams, cons
   p.bins_out = a->level_bins[level];
   p.weights_out = a->prop_weights[level];
   p.inds_out = a->level_inds[level];
+  // delta*sigma travels from proposal_kernel to pdf_kernel through the caller's prop_weights output or, when that
+  // is NULL, through the caller's workspace; a workspace smaller than [NR][S] floats splits the level into
+  // launch pairs over ray ranges
+  const int NGtot = p.g.NG, G = p.g.G, S = p.g.S, NR = p.g.NR;
+  int gpc = NGtot;
+  float* scratch = nullptr;
   if (!p.weights_out) {
-    // transmittance weights travel through a grow-only scratch buffer owned by the field
-    const size_t need = static_cast<size_t>(p.g.NR) * p.g.S * sizeof(float);
-    if (f->scratch_bytes < need) {
-      if (f->d_scratch) NJF_CUDA(cudaFree(f->d_scratch));
-      f->d_scratch = nullptr;
-      f->scratch_bytes = 0;
-      NJF_CUDA(cudaMalloc(&f->d_scratch, need));
-      f->scratch_bytes = need;
+    if (!a->workspace) NJF_FAIL("njf_proposal_pass: prop_weights[%d] or NjfRenderArgs.workspace required", level);
+    if (reinterpret_cast<uintptr_t>(a->workspace) & 15) NJF_FAIL("workspace must be 16-byte aligned");
+    scratch = static_cast<float*>(a->workspace);
+    const size_t rays_fit = a->workspace_bytes / (static_cast<size_t>(S) * sizeof(float));
+    long g = static_cast<long>(rays_fit / G);
+    if (g < 1) NJF_FAIL("workspace of %zu bytes cannot hold one ray group of proposal level %d", a->workspace_bytes, level);
+    if (g < NGtot) {
+      const long quantum = 2L * num_sms();
+      if (g > quantum) g -= g % quantum;
+      gpc = static_cast<int>(g);
     }
-    p.weights_out = f->d_scratch;
   }
   if (set_smem(proposal_kernel)) return 1;
-  const int nitems = (p.g.NG + 1) / 2;
-  const int grid = nitems < num_sms() ? nitems : num_sms();
-  proposal_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
-  NJF_CUDA(cudaGetLastError());
-  {
-    const int wpb = 4;
-    const size_t smem = static_cast<size_t>(wpb) * (2 * p.g.S + 8) * sizeof(float);
-    pdf_kernel<<<(p.g.NR + wpb - 1) / wpb, wpb * 32, smem, stream>>>(
-        p.weights_out, /*from_dd=*/1, /*store_weights=*/a->prop_weights[level] != nullptr, bins_in, bins_in_stride, p.u,
-        p.u_stride, p.g.NR, p.g.S, p.n_out, p.anneal, p.sum_vec, p.bins_out, p.inds_out);
+  // pdf_kernel: one warp per ray; 4 warps per block while their scan buffers fit the default 48 KB
+  const int wpb = (static_cast<size_t>(4) * (2 * S + 8) * sizeof(float) <= 48 * 1024) ? 4 : 1;
+  const size_t pdf_smem = static_cast<size_t>(wpb) * (2 * S + 8) * sizeof(float);
+  const int nb = p.n_out + 1;
+  for (int g0 = 0; g0 < NGtot; g0 += gpc) {
+    p.g.group0 = g0;
+    p.g.NG = (NGtot - g0 < gpc) ? NGtot - g0 : gpc;
+    const int ray0 = g0 * G;
+    const int nrays = (NR - ray0 < p.g.NG * G) ? NR - ray0 : p.g.NG * G;
+    float* wbuf;
+    if (scratch) {
+      p.weights_out = scratch;
+      p.w_ray0 = ray0;
+      wbuf = scratch;
+    } else {
+      p.w_ray0 = 0;
+      wbuf = a->prop_weights[level] + static_cast<size_t>(ray0) * S;
+    }
+    const int nitems = (p.g.NG + 1) / 2;
+    const int grid = nitems < num_sms() ? nitems : num_sms();
+    proposal_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+    NJF_CUDA(cudaGetLastError());
+    pdf_kernel<<<(nrays + wpb - 1) / wpb, wpb * 32, pdf_smem, stream>>>(
+        wbuf, /*from_dd=*/1, /*store_weights=*/a->prop_weights[level] != nullptr,
+        bins_in + static_cast<size_t>(ray0) * bins_in_stride, bins_in_stride, p.u + static_cast<size_t>(ray0) * p.u_stride,
+        p.u_stride, nrays, S, p.n_out, p.anneal, p.sum_vec, p.bins_out + static_cast<size_t>(ray0) * nb,
+        p.inds_out ? p.inds_out + static_cast<size_t>(ray0) * nb : nullptr);
     NJF_CUDA(cudaGetLastError());
   }
   return 0;
@@ -1031,6 +1169,7 @@ extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const N
   if (make_geom(f, cams, a, a->s_nerf, bins, bins_stride, map_of(f, a, -1), f->ch_main, p.g)) return 1;
   p.head_kind = f->desc.head;
   p.A = f->desc.action_dim;
+  p.sh_conv = f->desc.sh_convention;
   p.rgb = a->rgb;
   p.depth = a->depth;
   p.jbar = a->jbar;
@@ -1043,7 +1182,7 @@ extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const N
   p.rgb_samples = a->rgb_samples;
   p.minmax = reinterpret_cast<uint32_t*>(a->minmax);
   init_minmax_kernel<<<1, 1, 0, stream>>>(p.minmax);
-  if (launch_field(f, p, stream)) return 1;
+  if (launch_field(f, p, a->workspace, a->workspace_bytes, stream)) return 1;
   decode_minmax_kernel<<<1, 1, 0, stream>>>(p.minmax);
   NJF_CUDA(cudaGetLastError());
   return 0;
@@ -1051,7 +1190,7 @@ extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const N
 
 extern "C" int njf_query_points(const NjfField* f, const float* ctxt_w2c, const float* ctxt_k, const void* maps,
                                 int Hf, int Wf, const float* points, int B, int N, float* sigma, float* geo,
-                                float* jac, void* stream_) {
+                                float* jac, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!f || !ctxt_w2c || !ctxt_k || !maps || !points) NJF_FAIL("njf_query_points: null argument");
   if (B < 1 || N < 1) NJF_FAIL("njf_query_points: B=%d N=%d", B, N);
   if (static_cast<size_t>(B) * Hf * Wf * 768 * 2 >= (1ull << 32)) NJF_FAIL("njf_query_points: maps too large");
@@ -1074,7 +1213,7 @@ extern "C" int njf_query_points(const NjfField* f, const float* ctxt_w2c, const 
   p.sigma = sigma;
   p.geo_out = geo;
   p.jac_out = jac;
-  return launch_field(f, p, stream);
+  return launch_field(f, p, workspace, workspace_bytes, stream);
 }
 
 extern "C" int njf_point_features(const float* feat_nchw, const float* ctxt_w2c, const float* ctxt_k,
@@ -1106,7 +1245,10 @@ extern "C" int njf_finish_pass(const NjfField* f, const NjfCameras* cams, const 
   q.p = a->p;
   q.pw = a->pw;
   q.flow = a->flow;
-  if ((q.flow || q.pw) && (!q.jbar || !q.p || !q.action || !q.trgt_w2c || !q.trgt_k))
+  q.rgb = a->rgb;
+  q.packed = a->packed;
+  if (q.packed && (!q.jbar || !q.p || !q.rgb || !q.depth)) NJF_FAIL("packed output needs rgb, depth, jbar and p");
+  if ((q.flow || q.pw || q.packed) && (!q.jbar || !q.p || !q.action || !q.trgt_w2c || !q.trgt_k))
     NJF_FAIL("flow / pw outputs need jbar, p, action and the target camera");
   finish_kernel<<<(q.NR + 255) / 256, 256, 0, stream>>>(q);
   NJF_CUDA(cudaGetLastError());
@@ -1131,10 +1273,11 @@ extern "C" int njf_pdf_sample(const float* weights, const float* bins_in, int bi
                               int u_stride, int n_rays, int s_in, int n_out, float anneal, int sum_vec_width,
                               float* bins_out, int32_t* inds_out, void* stream_) {
   if (!weights || !bins_in || !u || !bins_out) NJF_FAIL("njf_pdf_sample: null argument");
-  if (s_in < 1 || s_in > 4096 || n_out < 1) NJF_FAIL("njf_pdf_sample: bad sizes");
+  if (s_in < 1 || s_in > 4096 || n_out < 1) NJF_FAIL("njf_pdf_sample: bad sizes (1 <= s_in <= 4096, n_out >= 1)");
+  if (n_rays < 0) NJF_FAIL("njf_pdf_sample: negative ray count");
   if (n_rays == 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int wpb = 4;
+  const int wpb = (static_cast<size_t>(4) * (2 * s_in + 8) * sizeof(float) <= 48 * 1024) ? 4 : 1;  // s_in <= 4096: <= 32.8 KB
   const size_t smem = static_cast<size_t>(wpb) * (2 * s_in + 8) * sizeof(float);
   pdf_kernel<<<(n_rays + wpb - 1) / wpb, wpb * 32, smem, stream>>>(const_cast<float*>(weights), 0, 0, bins_in,
                                                                  bins_in_stride, u, u_stride, n_rays, s_in, n_out,
@@ -1149,7 +1292,7 @@ extern "C" int njf_transmittance_weights(const float* deltas, const float* sigma
   if (s < 1 || s > 4096) NJF_FAIL("njf_transmittance_weights: bad sizes");
   if (n_rays == 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int wpb = 4;
+  const int wpb = (static_cast<size_t>(4) * 2 * s * sizeof(float) <= 48 * 1024) ? 4 : 1;  // s <= 4096: <= 32 KB
   tw_kernel<<<(n_rays + wpb - 1) / wpb, wpb * 32, static_cast<size_t>(wpb) * 2 * s * sizeof(float), stream>>>(
       deltas, sigma, n_rays, s, weights_out);
   NJF_CUDA(cudaGetLastError());

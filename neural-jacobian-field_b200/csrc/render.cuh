@@ -218,20 +218,24 @@ __device__ __forceinline__ void write_taps(TapEntry* tab, int row, const RowStat
 // (8 B / lane).  The four taps are blended in packed fp16 (HFMA2; the map, the weights and the
 // staged result are fp16 anyway -- 4 instead of 1 fp16 roundings).
 // The staging buffer is read by the row's two epilogue threads: pair barriers fence both ways.
+// gather_rows: rows [j_begin, j_end) of the warp's 16 rows, NO barriers -- the caller fences the staging buffer
+// with pair_bar (before the first rows of a segment: the partner warp has finished reading the previous
+// segment; after the last rows: the writes are visible to the row's two epilogue threads).  Splitting a segment
+// over several calls lets the trunk driver spread the L2-latency-bound loads over BOTH MMA wait windows of a
+// residual block (fc_0 and fc_1) instead of stacking them behind one.
 template <int NCH>
-__device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0) {
-  PROF(e, kPOther);
+__device__ __forceinline__ void gather_rows(EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0, int j_begin,
+                                            int j_end) {
   static_assert(NCH == 128 || NCH == 64, "segment width");
-  pair_bar(e);  // the partner warp has finished reading the previous segment
-  PROF(e, kPBar);
-  if (g.debug & 1) { pair_bar(e); return; }
+  PROF(e, kPOther);
+  if (g.debug & 1) return;
   const int lane = threadIdx.x & 31;
   const int wrow0 = e.q * 32 + e.half * 16;
   const bool active = (NCH == 128) || lane < 16;
   const uint8_t* mp = reinterpret_cast<const uint8_t*>(g.map + ch0) + lane * 8;
   constexpr int U = 4;
 #pragma unroll 1
-  for (int j0 = 0; j0 < 16; j0 += U) {
+  for (int j0 = j_begin; j0 < j_end; j0 += U) {
     uint2 t[U][4];
     uint4 w[U];
 #pragma unroll
@@ -267,6 +271,15 @@ __device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, con
     }
   }
   PROF(e, kPGather);
+}
+
+// a whole segment at once, fenced both ways
+template <int NCH>
+__device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0) {
+  PROF(e, kPOther);
+  pair_bar(e);  // the partner warp has finished reading the previous segment
+  PROF(e, kPBar);
+  gather_rows<NCH>(e, g, taps, ch0, 0, 16);
   pair_bar(e);
   PROF(e, kPBar);
 }
@@ -282,18 +295,28 @@ __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom&
   epi_publish(e);  // -> fc_0 (block 0)
 #pragma unroll 1
   for (int k = 0; k < 5; ++k) {
-    // overlap: gather the next hoisted segment while the tensor pipe runs fc_0
-    if (k < 2) gather_segment<128>(e, g, taps, seg_ch0 + 128 * (k + 1));
+    // the next hoisted segment is gathered in two halves: one while the tensor pipe runs fc_0, one while it
+    // runs fc_1 -- each half's load latency hides behind one MMA round trip
+    if (k < 2) {
+      pair_bar(e);  // both warps of the row quarter have consumed segment k (the x update above)
+      PROF(e, kPBar);
+      gather_rows<128>(e, g, taps, seg_ch0 + 128 * (k + 1), 0, 8);
+    }
     PROF(e, kPEpi);
     epi_wait_acc(e);
-    for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_relu_to_a(e, 128 + c0, c0);
+    epi_relu_to_a64(e, 128 + e.col0, e.col0);
     epi_publish(e);  // -> fc_1 (block k), accumulates onto x
+    if (k < 2) {
+      gather_rows<128>(e, g, taps, seg_ch0 + 128 * (k + 1), 8, 16);
+      pair_bar(e);  // segment k+1 complete and visible to the row's two threads
+      PROF(e, kPBar);
+    }
     PROF(e, kPEpi);
     epi_wait_acc(e);
     if (k < 2) {
       for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<true>(e, c0);
     } else {
-      for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<false>(e, c0);
+      epi_relu_to_a64(e, e.col0, e.col0);  // no hoisted segment after block 2: x -> ReLU -> A tile
     }
     epi_publish(e);  // -> fc_0 (block k+1) or lin_out
   }

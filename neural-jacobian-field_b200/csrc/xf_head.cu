@@ -17,6 +17,7 @@
 // Then J-bar = sum_s w_s J_s per ray (model.py:281-286), optionally the per-sample Jacobians.
 #include "field.h"
 #include "njf_internal.h"
+#include <atomic>
 
 namespace njf {
 
@@ -266,13 +267,19 @@ __global__ void __launch_bounds__(kXfThreads, 1) xf_kernel(const __grid_constant
         const int ray = (lr < 0) ? -1 : group * p.G + lr;
         const bool valid = ray >= 0 && ray < p.NR;
         const size_t tidx = static_cast<size_t>(lgroup) * p.T + tile;
-        const float4* qp = p.qs + tidx * 16 * kRows + row;
+        const uint4* qp = p.qs + tidx * 8 * kRows + row;
         const float w = __ldcs(p.wts + tidx * kRows + row);
         float x[64];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 v = __ldcs(qp + j * kRows);
-          x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+        for (int j = 0; j < 8; ++j) {
+          const uint4 v = __ldcs(qp + j * kRows);
+          const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = __half22float2(h[t]);
+            x[8 * j + 2 * t] = f.x;
+            x[8 * j + 2 * t + 1] = f.y;
+          }
         }
         {  // the residual stream lives in TMEM; accumulating MMAs (M2, W2) add onto it
           uint32_t r[32];
@@ -423,18 +430,19 @@ extern "C" int njf_xf_prof_read(unsigned long long* out8, int reset) {
 #endif
 
 int njf_xf_launch(const NjfField* f, const XfParams& params, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static std::atomic<bool> attr[64];  // the opt-in applies to the current device only
+  if (dev >= 0 && dev < 64 && !attr[dev].load(std::memory_order_acquire)) {
     NJF_CUDA(cudaFuncSetAttribute(xf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(XfSmem::kTotal)));
-    attr = true;
+    attr[dev].store(true, std::memory_order_release);
   }
   XfParams p = params;
   p.prog = f->head_prog;
   p.blob = f->d_xf_blob;
   p.blob_bytes = f->xf_bytes;
   p.A = f->desc.action_dim;
-  int sms = 0, dev = 0;
-  cudaGetDevice(&dev);
+  int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
   const int nitems = (p.NG + kXfSlots - 1) / kXfSlots;

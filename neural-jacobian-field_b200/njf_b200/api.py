@@ -16,11 +16,12 @@ from . import _lib
 NJF_MAX_LEVELS = 4
 HEAD_TRANSFORMER, HEAD_MLP = 0, 1
 HEADS = {"jacobian_transformer": HEAD_TRANSFORMER, "jacobian_mlp": HEAD_MLP}
+SH_CONVENTIONS = {"tcnn": 0, "nerfstudio_torch": 1}
 
 
 class NjfFieldDesc(Structure):
     _fields_ = [("head", c_int), ("action_dim", c_int), ("n_proposal", c_int), ("encoder_dim", c_int),
-                ("sh_fp16_round", c_int)]
+                ("sh_fp16_round", c_int), ("sh_convention", c_int)]
 
 
 class NjfTensor(Structure):
@@ -48,6 +49,7 @@ class NjfRenderArgs(Structure):
         ("prop_weights", c_void_p * NJF_MAX_LEVELS), ("level_bins", c_void_p * NJF_MAX_LEVELS),
         ("level_inds", c_void_p * NJF_MAX_LEVELS),
         ("minmax", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_size_t), ("packed", c_void_p),
     ]
 
 
@@ -74,7 +76,15 @@ def _declare():
     L.njf_field_pass.argtypes = [c_void_p, POINTER(NjfCameras), POINTER(NjfRenderArgs), c_void_p, c_int, c_void_p]
     L.njf_query_points.restype = c_int
     L.njf_query_points.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
-                                   c_void_p, c_void_p, c_void_p, c_void_p]
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.njf_query_workspace_bytes.restype = c_size_t
+    L.njf_query_workspace_bytes.argtypes = [c_void_p, c_int, c_int]
+    L.njf_workspace_bytes.restype = c_size_t
+    L.njf_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_int), c_int]
+    L.njf_workspace_min_bytes.restype = c_size_t
+    L.njf_workspace_min_bytes.argtypes = [c_void_p, c_int, POINTER(c_int), c_int]
+    L.njf_invert_poses.restype = c_int
+    L.njf_invert_poses.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     L.njf_point_features.restype = c_int
     L.njf_point_features.argtypes = [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_void_p, c_void_p]
     L.njf_pdf_sample.restype = c_int
@@ -117,12 +127,15 @@ class Field:
     """Owner of an ``NjfField*`` (packed decoder + proposal-network weights on the current device)."""
 
     def __init__(self, head: str, action_dim: int, n_proposal: int, weights: Dict[str, torch.Tensor],
-                 sh_fp16_round: bool = True, encoder_dim: int = 512):
+                 sh_fp16_round: bool = True, encoder_dim: int = 512, sh_convention: str = "tcnn"):
         if head not in HEADS:
             raise _lib.NjfError(f"decoder '{head}' has no B200 kernel (supported: {sorted(HEADS)})")
+        if sh_convention not in SH_CONVENTIONS:
+            raise _lib.NjfError(f"sh_convention '{sh_convention}' unknown (supported: {sorted(SH_CONVENTIONS)})")
         L = _declare()
         self.head, self.action_dim, self.n_proposal = head, int(action_dim), int(n_proposal)
-        desc = NjfFieldDesc(HEADS[head], int(action_dim), int(n_proposal), int(encoder_dim), int(bool(sh_fp16_round)))
+        desc = NjfFieldDesc(HEADS[head], int(action_dim), int(n_proposal), int(encoder_dim), int(bool(sh_fp16_round)),
+                            SH_CONVENTIONS[sh_convention])
         keep = []
         arr = (NjfTensor * len(weights))()
         for i, (k, v) in enumerate(weights.items()):
@@ -133,15 +146,41 @@ class Field:
         _lib.check(L.njf_field_create(ctypes.byref(desc), arr, len(weights), ctypes.byref(h)))
         self._h = h
         self.device = torch.device("cuda", torch.cuda.current_device())
+        self._ws: Dict[int, torch.Tensor] = {}   # caller-owned workspaces, one per stream (grow-only)
 
     @property
     def handle(self) -> c_void_p:
         return self._h
 
+    def _check_device(self, t: torch.Tensor, what: str) -> None:
+        if t.device != self.device:
+            raise _lib.NjfError(f"{what} lives on {t.device}, the field was packed on {self.device}")
+
+    def workspace_bytes(self, B: int, R: int, s_prop: Sequence[int], s_nerf: int) -> int:
+        L = _declare()
+        arr = (c_int * NJF_MAX_LEVELS)(*[int(s) for s in s_prop])
+        return int(L.njf_workspace_bytes(self._h, int(B), int(R), len(s_prop), arr, int(s_nerf)))
+
+    def workspace_min_bytes(self, s_prop: Sequence[int], s_nerf: int) -> int:
+        L = _declare()
+        arr = (c_int * NJF_MAX_LEVELS)(*[int(s) for s in s_prop])
+        return int(L.njf_workspace_min_bytes(self._h, len(s_prop), arr, int(s_nerf)))
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        """The library allocates nothing inside a pass; this is the host mirror's scratch for the CURRENT stream
+        (one buffer per stream, so two streams can render from one field concurrently), grown on demand."""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
     def hoist(self, feat_nchw: torch.Tensor) -> torch.Tensor:
         """(B,512,Hf,Wf) fp32 encoder output -> opaque fp16 hoisted maps (uint8 buffer)."""
         L = _declare()
         assert feat_nchw.is_cuda and feat_nchw.dtype == torch.float32
+        self._check_device(feat_nchw, "feature map")
         feat_nchw = feat_nchw.contiguous()
         B, C, Hf, Wf = feat_nchw.shape
         if C != 512:
@@ -161,17 +200,48 @@ class Field:
 
 
 def make_cameras(ctxt_c2w, ctxt_k, trgt_c2w, trgt_k_px, device):
-    """The reference inverts the 4x4 poses with torch.inverse inside the path (geometry.py:59-65);
-    the 4x4 inversions stay on the host side (fp32, CPU LAPACK like the CPU reference)."""
+    """The reference inverts the 4x4 poses with torch.inverse inside the path (geometry.py:59-65).
+    Host inputs: inverted on the host (fp32, CPU LAPACK like the CPU reference); the host copies also let the
+    kernels carry the per-view constants in their parameter block.  CUDA inputs: inverted on the device by
+    njf_invert_poses -- no host round trip, no synchronisation (what a CUDA-graphed frame uses)."""
+    if ctxt_c2w.is_cuda:
+        L = _declare()
+        f = lambda t: t.detach().to(device, torch.float32).contiguous()
+        cc, ck = f(ctxt_c2w), f(ctxt_k)
+        cw = torch.empty_like(cc)
+        _lib.check(L.njf_invert_poses(dptr(cc), dptr(cw), cc.shape[0], stream_ptr()))
+        tw = tk = None
+        tc = None
+        if trgt_c2w is not None:
+            tc = f(trgt_c2w)
+            tw = torch.empty_like(tc)
+            _lib.check(L.njf_invert_poses(dptr(tc), dptr(tw), tc.shape[0], stream_ptr()))
+            tk = f(trgt_k_px)
+        cams = NjfCameras(dptr(cw), dptr(ck), dptr(tw), dptr(tk), None, None)
+        return cams, (cw, ck, tw, tk, cc, tc)
     f = lambda t: t.detach().to("cpu", torch.float32)
     cw_h = torch.inverse(f(ctxt_c2w)).contiguous()
     ck_h = f(ctxt_k).contiguous()
-    cw = cw_h.to(device)
-    tw = torch.inverse(f(trgt_c2w)).contiguous().to(device) if trgt_c2w is not None else None
-    ck = ck_h.to(device)
-    tk = f(trgt_k_px).contiguous().to(device) if trgt_k_px is not None else None
+    cw = cw_h.to(device, non_blocking=True)
+    tw = torch.inverse(f(trgt_c2w)).contiguous().to(device, non_blocking=True) if trgt_c2w is not None else None
+    ck = ck_h.to(device, non_blocking=True)
+    tk = f(trgt_k_px).contiguous().to(device, non_blocking=True) if trgt_k_px is not None else None
     cams = NjfCameras(dptr(cw), dptr(ck), dptr(tw), dptr(tk), cw_h.data_ptr(), ck_h.data_ptr())
     return cams, (cw, ck, tw, tk, cw_h, ck_h)
+
+
+def query_points(fld: "Field", w2c, k_norm, maps, Hf, Wf, points, want_jac=True):
+    """njf_query_points: density head (+ Jacobian head) at explicit world points (B,N,3)."""
+    L = _declare()
+    B, N = points.shape[:2]
+    A = fld.action_dim
+    o = dict(device=points.device, dtype=torch.float32)
+    sigma, geo = torch.empty(B, N, 1, **o), torch.empty(B, N, 15, **o)
+    jac = torch.empty(B, N, 3 * A, **o) if want_jac else None
+    ws = fld.workspace(int(L.njf_query_workspace_bytes(fld.handle, B, N)))
+    _lib.check(L.njf_query_points(fld.handle, dptr(w2c), dptr(k_norm), dptr(maps), int(Hf), int(Wf), dptr(points), B, N,
+                                  dptr(sigma), dptr(geo), dptr(jac), ws.data_ptr(), ws.numel(), stream_ptr()))
+    return sigma, geo, jac
 
 
 def eval_tables(s_prop: Sequence[int], s_nerf: int, device):

@@ -392,12 +392,9 @@ class Model(nn.Module):
         feats = pixel_encoding.features.to(dev).float().contiguous()
         C, Hf, Wf = feats.shape[1:]
         o = dict(device=dev, dtype=torch.float32)
-        sigma, geo, jac = torch.empty(B, N, 1, **o), torch.empty(B, N, 15, **o), torch.empty(B, N, 3 * A, **o)
         xyzf, pixf = torch.empty(B, N, 63, **o), torch.empty(B, N, C, **o)
         with torch.cuda.device(dev):
-            _lib.check(L.njf_query_points(self.field().handle, api.dptr(w2c), api.dptr(kn), api.dptr(pixel_encoding.hoisted),
-                                          Hf, Wf, api.dptr(pts), B, N, api.dptr(sigma), api.dptr(geo), api.dptr(jac),
-                                          api.stream_ptr()))
+            sigma, geo, jac = api.query_points(self.field(), w2c, kn, pixel_encoding.hoisted, Hf, Wf, pts)
             _lib.check(L.njf_point_features(api.dptr(feats), api.dptr(w2c), api.dptr(kn), api.dptr(pts), B, N, C, Hf, Wf,
                                             api.dptr(xyzf), api.dptr(pixf), api.stream_ptr()))
         out = DensityHeadOutput(density=sigma, density_features=geo, xyz_features=xyzf, pixel_aligned_features=pixf)

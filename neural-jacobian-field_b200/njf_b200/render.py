@@ -28,6 +28,8 @@ class RenderResult:
     level_bins: List[torch.Tensor] = dc_field(default_factory=list)     # per level (B,R,n_l+1) spacing bins
     level_inds: List[torch.Tensor] = dc_field(default_factory=list)     # per level (B,R,n_l+1) int32
     bins0: Optional[torch.Tensor] = None
+    minmax: Optional[torch.Tensor] = None         # (2,) call-global (min, max) of steps (the depth clip range)
+    packed: Optional[torch.Tensor] = None         # (B,R,12+3A) rgb|depth|flow|jbar|p|pw (multi-GPU gather buffer)
 
 
 def render(fld: api.Field, maps: torch.Tensor, Hf: int, Wf: int, cams: api.NjfCameras, origins: torch.Tensor,
@@ -36,13 +38,21 @@ def render(fld: api.Field, maps: torch.Tensor, Hf: int, Wf: int, cams: api.NjfCa
            sampler_outputs: bool = False, bins0: Optional[torch.Tensor] = None,
            us: Optional[Sequence[torch.Tensor]] = None, anneal: float = 1.0,
            sum_vec_width: Optional[int] = None, final_bins: Optional[torch.Tensor] = None,
-           host_near_far: Optional[Sequence[torch.Tensor]] = None) -> RenderResult:
+           host_near_far: Optional[Sequence[torch.Tensor]] = None, packed: bool = False,
+           workspace: Optional[torch.Tensor] = None, minmax_hook=None) -> RenderResult:
     """One fused render of B x R rays.  All tensors live on the field's CUDA device.
 
     ``final_bins`` (B,R,s_nerf+1): skip the proposal levels and render the field at the given
-    spacing-domain bins (stage-wise parity tests / externally supplied samples)."""
+    spacing-domain bins (stage-wise parity tests / externally supplied samples).
+    ``workspace``: caller-owned uint8 scratch (any size >= fld.workspace_min_bytes); default = the field's
+    per-stream buffer of fld.workspace_bytes(...).
+    ``minmax_hook(minmax)``: called between the field pass and the finish pass with the (2,) device tensor of the
+    call's (min, max) sample distance -- a ray-sharded render all-reduces it there so that every shard applies
+    the reference's call-global depth clip (models/model.py:277); forces the staged entry points."""
     L = api._declare()
     dev = origins.device
+    fld._check_device(origins, "ray origins")
+    fld._check_device(maps, "hoisted maps")
     B, R = origins.shape[:2]
     A = fld.action_dim
     f32 = dict(device=dev, dtype=torch.float32)
@@ -90,7 +100,12 @@ def render(fld: api.Field, maps: torch.Tensor, Hf: int, Wf: int, cams: api.NjfCa
             a.level_inds[lvl] = api.dptr(li)
     minmax = torch.empty(2, **f32)
     a.minmax = api.dptr(minmax)
-    keep.append(minmax)
+    res.minmax = minmax
+    if workspace is None:
+        workspace = fld.workspace(fld.workspace_bytes(B, R, s_prop, s_nerf))
+    assert workspace.is_cuda and workspace.dtype == torch.uint8 and workspace.is_contiguous()
+    a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    keep.append(workspace)
     res.rgb = torch.empty(B, R, 3, **f32)
     res.depth = torch.empty(B, R, 1, **f32)
     res.flow = torch.empty(B, R, 2, **f32)
@@ -99,6 +114,9 @@ def render(fld: api.Field, maps: torch.Tensor, Hf: int, Wf: int, cams: api.NjfCa
     res.pw = torch.empty(B, R, 3, **f32)
     a.rgb, a.depth, a.flow = api.dptr(res.rgb), api.dptr(res.depth), api.dptr(res.flow)
     a.jbar, a.p, a.pw = api.dptr(res.jbar), api.dptr(res.p), api.dptr(res.pw)
+    if packed:
+        res.packed = torch.empty(B, R, 12 + 3 * A, **f32)
+        a.packed = api.dptr(res.packed)
     if vis or per_sample:
         res.steps = torch.empty(B, R, s_nerf, **f32)
         res.weights = torch.empty(B, R, s_nerf, **f32)
@@ -112,13 +130,24 @@ def render(fld: api.Field, maps: torch.Tensor, Hf: int, Wf: int, cams: api.NjfCa
         a.positions, a.rgb_samples = api.dptr(res.positions), api.dptr(res.rgb_samples)
     st = api.stream_ptr()
     h = fld.handle
-    if final_bins is None:
+    if final_bins is None and minmax_hook is None:
         _lib.check(L.njf_render_forward(h, ctypes.byref(cams), ctypes.byref(a), st))
+    elif final_bins is None:
+        bins, stride = bins0, a.bins0_stride
+        for lvl in range(len(s_prop)):
+            _lib.check(L.njf_proposal_pass(h, ctypes.byref(cams), ctypes.byref(a), lvl, api.dptr(bins), stride, st))
+            bins = res.level_bins[lvl]
+            stride = bins.shape[-1]
+        _lib.check(L.njf_field_pass(h, ctypes.byref(cams), ctypes.byref(a), api.dptr(bins), stride, st))
+        minmax_hook(minmax)
+        _lib.check(L.njf_finish_pass(h, ctypes.byref(cams), ctypes.byref(a), st))
     else:
         fb = final_bins.contiguous().float()
         keep.append(fb)
         stride = 0 if fb.dim() == 1 else fb.shape[-1]
         _lib.check(L.njf_field_pass(h, ctypes.byref(cams), ctypes.byref(a), api.dptr(fb), stride, st))
+        if minmax_hook is not None:
+            minmax_hook(minmax)
         _lib.check(L.njf_finish_pass(h, ctypes.byref(cams), ctypes.byref(a), st))
     res._keep = keep  # inputs stay alive until the caller is done with the (async) result
     return res

@@ -39,6 +39,7 @@ class FieldSpec:
     dim_head: int = 64
     depth: int = 3
     sh_fp16_round: bool = True
+    sh_convention: str = "tcnn"   # or "nerfstudio_torch" (nerfstudio's torch fallback)
 
 
 # ----------------------------------------------------------------------------- encodings
@@ -56,9 +57,23 @@ _SH = (0.28209479177387814, 0.48860251190291987, 1.0925484305920792, 0.946174695
        0.45704579946446572, 0.3731763325901154, 1.4453057213202769)
 
 
-def sh4(d01: torch.Tensor, fp16_round: bool = True) -> torch.Tensor:
+def sh4(d01: torch.Tensor, fp16_round: bool = True, convention: str = "tcnn") -> torch.Tensor:
     """tiny-cuda-nn SphericalHarmonics degree 4 of (2*d01 - 1), output through fp16
-    (SHEncoding(levels=4, implementation="tcnn"), action_decoder_jacobian.py:194-199, :284)."""
+    (SHEncoding(levels=4, implementation="tcnn"), action_decoder_jacobian.py:194-199, :284).
+    convention="nerfstudio_torch": what nerfstudio's SHEncoding computes when it falls back to its torch
+    implementation (components_from_spherical_harmonics, restated from the published source): the direction tensor
+    is used AS PASSED (here the [0,1]-normalised one) and every component carries a positive leading sign."""
+    if convention == "nerfstudio_torch":
+        x, y, z = d01.unbind(-1)
+        xx, yy, zz = x * x, y * y, z * z
+        c = _SH
+        o = torch.stack([
+            torch.full_like(x, c[0]), c[1] * y, c[1] * z, c[1] * x,
+            c[2] * x * y, c[2] * y * z, c[3] * zz - c[4], c[2] * x * z, c[5] * (xx - yy),
+            c[6] * y * (3 * xx - yy), c[7] * x * y * z, c[8] * y * (5 * zz - 1),
+            c[9] * z * (5 * zz - 3), c[8] * x * (5 * zz - 1), c[10] * z * (xx - yy),
+            c[6] * x * (xx - 3 * yy)], -1)
+        return o.half().float() if fp16_round else o
     d = d01 * 2.0 - 1.0
     x, y, z = d.unbind(-1)
     xy, xz, yz, x2, y2, z2 = x * y, x * z, y * z, x * x, y * y, z * z
@@ -192,6 +207,23 @@ def uniform_bins(n_rays_shape: Sequence[int], s: int) -> torch.Tensor:
     return torch.linspace(0.0, 1.0, s + 1)[None, ...].repeat(*n_rays_shape, 1)
 
 
+def stratified_bins(t_rand: torch.Tensor, s: int) -> torch.Tensor:
+    """Train-mode SpacedSampler bins (ray_samplers.py:214-233): t_rand (...,s+1) or (...,1) uniform [0,1)."""
+    bins = torch.linspace(0.0, 1.0, s + 1).to(t_rand.device)[None, ...]
+    centers = (bins[..., 1:] + bins[..., :-1]) / 2.0
+    upper = torch.cat([centers, bins[..., -1:]], -1)
+    lower = torch.cat([bins[..., :1], centers], -1)
+    return lower + (upper - lower) * t_rand
+
+
+def stratified_u(rand: torch.Tensor, n_samples: int) -> torch.Tensor:
+    """Train-mode PDFSampler positions (ray_samplers.py:389-401): rand (...,n_samples+1) or (...,1)."""
+    nb = n_samples + 1
+    u = torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb, device=rand.device)
+    u = u.expand((*rand.shape[:-1], nb))
+    return (u + rand / nb).contiguous()
+
+
 def transmittance_weights(deltas: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
     """RaySamples.get_weights (ray_samplers.py:77-101). deltas, sigma (...,S,1)."""
     dd = torch.where(deltas > 0, deltas * sigma, torch.zeros_like(sigma))
@@ -279,14 +311,17 @@ def project_px(p: torch.Tensor, c2w: torch.Tensor, k_px: torch.Tensor) -> torch.
 
 def render_forward(w: W, spec: FieldSpec, feat: torch.Tensor, ctxt_c2w, ctxt_k, trgt_c2w, trgt_k_px,
                    origins, dirs, z_near, z_far, action, s_prop: Sequence[int], s_nerf: int,
-                   anneal: float = 1.0) -> Dict[str, torch.Tensor]:
-    """Model.forward in eval mode with compute_vis_features=True (models/model.py:316-396),
-    encoder output ``feat`` (B,512,Hf,Wf) given.  origins/dirs (B,R,3); z_near/z_far (B,);
-    action (B,A).  Returns composites and the per-sample intermediates used by the tests."""
+                   anneal: float = 1.0, bins0: Optional[torch.Tensor] = None,
+                   us: Optional[Sequence[torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """Model.forward with compute_vis_features=True (models/model.py:316-396), encoder output ``feat``
+    (B,512,Hf,Wf) given.  origins/dirs (B,R,3); z_near/z_far (B,); action (B,A).  Eval mode by default; train mode =
+    the caller passes the stratified level-0 bins (``stratified_bins``) and per-level PDF positions
+    (``stratified_u``) drawn from its own torch.rand tensors, plus the proposal-weight ``anneal``.
+    Returns composites and the per-sample intermediates used by the tests."""
     B, R = origins.shape[:2]
     near = torch.ones_like(origins[..., :1]) * z_near[:, None, None]   # model.py:215-226
     far = torch.ones_like(origins[..., :1]) * z_far[:, None, None]
-    bins = uniform_bins((B, R), s_prop[0]).to(origins.device)
+    bins = uniform_bins((B, R), s_prop[0]).to(origins.device) if bins0 is None else bins0
     out: Dict[str, torch.Tensor] = {}
     prop_w: List[torch.Tensor] = []
     prop_bins: List[torch.Tensor] = [bins]
@@ -295,7 +330,8 @@ def render_forward(w: W, spec: FieldSpec, feat: torch.Tensor, ctxt_c2w, ctxt_k, 
         is_prop = lvl < len(s_prop)
         if lvl > 0:
             n = s_prop[lvl] if is_prop else s_nerf
-            bins, inds = pdf_resample(torch.pow(prop_w[-1], anneal)[..., 0], bins, n)
+            bins, inds = pdf_resample(torch.pow(prop_w[-1], anneal)[..., 0], bins, n,
+                                      u=None if us is None else us[lvl - 1])
             bins = bins.detach()
             prop_bins.append(bins)
             out[f"inds_{lvl}"] = inds
@@ -313,7 +349,7 @@ def render_forward(w: W, spec: FieldSpec, feat: torch.Tensor, ctxt_c2w, ctxt_k, 
     # flow = J u (action_decoder_jacobian.py:135-143): J laid out (action_dim, spatial_dim)
     flow = torch.einsum("brsad,ba->brsd", jac.reshape(B, R, S, spec.action_dim, 3), action)
     d01 = (dirs[..., None, :].expand(pos.shape) + 1.0) / 2.0           # :24-30
-    rgb = color_head(w, geo, sh4(d01, spec.sh_fp16_round))
+    rgb = color_head(w, geo, sh4(d01, spec.sh_fp16_round, spec.sh_convention))
     weights = transmittance_weights(ends - starts, sigma)               # model.py:351
     steps = (starts + ends) / 2
     depth = torch.sum(weights * steps, dim=-2) / (torch.sum(weights, -2) + 1e-10)   # :271-279
@@ -328,6 +364,9 @@ def render_forward(w: W, spec: FieldSpec, feat: torch.Tensor, ctxt_c2w, ctxt_k, 
         sigma=sigma, jacobian=jac, rgb_samples=rgb, positions=pos, final_bins=bins,
         proposal_weights=prop_w[-1].squeeze(-1) if prop_w else torch.zeros(0, device=origins.device),
     )
+    for i, (pw_, pb_) in enumerate(zip(prop_w, prop_bins)):   # ModelTrainingOutput (model.py:377-382)
+        out[f"prop_weights_{i}"] = pw_.squeeze(-1)
+        out[f"prop_bins_{i}"] = pb_
     return out
 
 

@@ -215,8 +215,7 @@ def test_compute_density_point_queries():
     pd = pts.to(DEV).contiguous()
     fd = feat.to(DEV).contiguous()
     Hf, Wf = feat.shape[-2:]
-    _lib.check(L.njf_query_points(fld.handle, api.dptr(w2c), api.dptr(kn), api.dptr(maps), Hf, Wf, api.dptr(pd), B, N,
-                                  api.dptr(s_d), api.dptr(g_d), api.dptr(j_d), api.stream_ptr()))
+    s_d, g_d, j_d = api.query_points(fld, w2c, kn, maps, Hf, Wf, pd)
     _lib.check(L.njf_point_features(api.dptr(fd), api.dptr(w2c), api.dptr(kn), api.dptr(pd), B, N, 512, Hf, Wf,
                                     api.dptr(x_d), api.dptr(p_d), api.stream_ptr()))
     torch.cuda.synchronize()
