@@ -78,6 +78,10 @@ void njf_field_destroy(NjfField* f);
 size_t njf_hoisted_bytes(const NjfField* f, int B, int Hf, int Wf);
 int njf_hoist_features(const NjfField* f, const float* feat_nchw, int B, int Hf, int Wf, void* maps_out,
                        void* stream);
+/* the same for views [view0, view0 + B_local) of a B_total-view map buffer (njf_hoisted_bytes(f, B_total, ...)):
+ * a rank of a ray-sharded multi-view call encodes and hoists only the views its ray range touches */
+int njf_hoist_features_views(const NjfField* f, const float* feat_nchw, int B_local, int view0, int B_total, int Hf,
+                             int Wf, void* maps_out, void* stream);
 
 /* ---- cameras ---------------------------------------------------------------------------------- */
 typedef struct NjfCameras {
@@ -147,6 +151,13 @@ typedef struct NjfRenderArgs {
   size_t workspace_bytes;
   float* packed;                  /* optional [B][R][12+3A]: rgb3 | depth1 | flow2 | jbar3A | p3 | pw3 per ray, written by
                                      njf_finish_pass (one buffer for the multi-GPU gather) */
+  /* ray-sharded call ("flatten (view, ray) and split contiguously by rank"): when n_rays > 0 this call
+     renders only rays [ray_offset, ray_offset + n_rays) of the flattened B x R index space.  origins / dirs /
+     bins0 / u (per-ray strides) and every per-ray / per-sample output then hold n_rays entries; the per-view
+     inputs (cameras, z_near, z_far, action, maps) stay arrays over all B views (maps of views the range does not
+     touch are never read).  n_rays == 0: the whole B x R call. */
+  int ray_offset;
+  int n_rays;
 } NjfRenderArgs;
 
 /* workspace sizing for a (B, R, sample-count) render with this field */
@@ -202,6 +213,33 @@ int njf_transmittance_weights(const float* deltas, const float* sigma, int n_ray
 int njf_flow_from_encoding(const float* jbar, const float* p, const float* action, const float* trgt_w2c,
                            const float* trgt_k_px, int n_rays, int rays_per_view, int action_dim, float* flow,
                            float* pw, void* stream);
+
+/* ---- action-phase training: backward of the cross-attention Jacobian head.
+ * models/model_wrapper.py:75-85 freezes everything but the Jacobian head and :148-163 puts an MSE on the optical
+ * flow, so the gradient path is  flow -> pw = p + Jbar^T u -> Jbar = sum_s w_s J_s -> J_s = head(q0_s) -> W_q, b_q.
+ *
+ * njf_flow_backward: backward of njf_finish_pass / njf_flow_from_encoding (models/model.py:288-314, 497-525):
+ *   g_flow [N][2] (+ optional g_pw_in [N][3]) -> g_jbar [N][3A] (nullable), g_action [B][A] (nullable, zeroed here).
+ * njf_xf_backward: given the hand-over region a train-mode njf_field_pass left in ITS workspace (single launch
+ *   group: workspace >= all tiles; fp16 query embedding + sample weights per 128-row tile) and g_jbar, recomputes
+ *   the three attention / feed-forward layers in fp32 and back-propagates.  `folded` / `g_folded`
+ *   (njf_xf_folded_floats() floats, fp32, natural-base softmax) hold, per layer,
+ *   [M1 64x64 | m1b | M2 | b_out | W1 | w1b | W2 | b2] and then [W_head 64x64 (rows >= 3A zero) | b_head 64], i.e.
+ *   the matrices field.cu folds from the state dict (transformer.py:14-21, 63-82): rows of M1 / columns of M2 are
+ *   indexed h*8 + a.  g_folded is ACCUMULATED into.  g_q0 [n_tiles*128][64] receives d loss / d q0 per row.
+ * njf_query_backward: q0 = W_q [enc63 | feat512] + b_q (action_decoder_jacobian.py:423-430): g_bq [64],
+ *   g_wq_enc [64][64] (columns 0..62 = d W_q[:, :63]), both accumulated, and g_map [B][Hf*Wf][64] (accumulated;
+ *   the adjoint of the bilinear gather), from which d W_q[:, 63:] = sum_pixels g_map^T . features. */
+int njf_xf_folded_floats(void);
+size_t njf_xf_backward_workspace_bytes(int n_tiles);
+int njf_xf_backward(const float* folded, int action_dim, const void* handover, int n_tiles, int n_rays, int s_nerf,
+                    const float* g_jbar, float* g_folded, float* g_q0, void* workspace, size_t workspace_bytes,
+                    void* stream);
+int njf_query_backward(const NjfCameras* cams, const NjfRenderArgs* args, const float* final_bins, int bins_stride,
+                       const float* g_q0, int n_tiles, float* g_wq_enc, float* g_bq, float* g_map, void* stream);
+int njf_flow_backward(const float* g_flow, const float* g_pw_in, const float* jbar, const float* p, const float* action,
+                      const float* trgt_w2c, const float* trgt_k_px, int n_rays, int rays_per_view, int action_dim,
+                      float* g_jbar, float* g_action, void* stream);
 
 /* ---- inverse dynamics on the collapsed encoding (the Adam loop of notebooks/real_world/2_inverse_dynamics.ipynb
  * over Model.infer_optical_flow, models/model.py:497-525): Gauss-Newton normal equations of

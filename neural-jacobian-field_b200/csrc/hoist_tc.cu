@@ -192,7 +192,7 @@ int njf_hoist_build(NjfField* f, const std::vector<float>& w, const std::vector<
 }
 
 int njf_hoist_launch(const NjfField* f, const float* feat_nchw, int B, int Hf, int Wf, void* maps_out,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int view0, int B_total) {
   int dev = 0;
   cudaGetDevice(&dev);
   static std::atomic<bool> attr[64];  // the opt-in applies to the current device only
@@ -201,6 +201,7 @@ int njf_hoist_launch(const NjfField* f, const float* feat_nchw, int B, int Hf, i
                                   static_cast<int>(kHoistSmem)));
     attr[dev].store(true, std::memory_order_release);
   }
+  if (B_total < 0) B_total = B;
   HoistParams p{};
   p.feat = feat_nchw;
   p.wimg = f->d_hoist_img;
@@ -208,9 +209,10 @@ int njf_hoist_launch(const NjfField* f, const float* feat_nchw, int B, int Hf, i
   p.HW = Hf * Wf;
   __half* base = static_cast<__half*>(maps_out);
   std::vector<__half*> map_ptr;
-  for (int m = 0; m <= f->desc.n_proposal; ++m) {
-    map_ptr.push_back(base);
-    base += static_cast<size_t>(B) * p.HW * ((m < f->desc.n_proposal) ? f->ch_prop : f->ch_main);
+  for (int m = 0; m <= f->desc.n_proposal; ++m) {  // maps are [level][B_total views][pixel][channel]; write views view0..
+    const size_t ch = (m < f->desc.n_proposal) ? f->ch_prop : f->ch_main;
+    map_ptr.push_back(base + static_cast<size_t>(view0) * p.HW * ch);
+    base += static_cast<size_t>(B_total) * p.HW * ch;
   }
   int nj = 0;
   for (const auto& j : f->hoist_jobs) {

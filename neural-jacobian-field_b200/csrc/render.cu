@@ -556,6 +556,7 @@ __global__ void decode_minmax_kernel(uint32_t* mm) {
 // depth clip + optical flow (model.py:271-279, 288-314; geometry.py:206-215)
 struct FinishParams {
   int NR, R, A;
+  int ray0;
   const float* action;    // [B][A]
   const float* trgt_w2c;  // [B][16]
   const float* trgt_k;    // [B][9] pixel units
@@ -583,7 +584,7 @@ __device__ __forceinline__ void project_uv(const float* W, const float* K, float
 __global__ void finish_kernel(const FinishParams q) {
   const int ray = blockIdx.x * blockDim.x + threadIdx.x;
   if (ray >= q.NR) return;
-  const int b = ray / q.R;
+  const int b = (ray + q.ray0) / q.R;
   const int A3 = 3 * q.A;
   float* pk = q.packed ? q.packed + static_cast<size_t>(ray) * (12 + A3) : nullptr;
   float dep = 0.f;
@@ -818,7 +819,8 @@ int num_sms() {
 int make_geom(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a, int S, const float* bins,
               int bins_stride, const __half* map, int CH, PassGeom& g) {
   if (S < 1 || S > 512) NJF_FAIL("samples per ray %d unsupported (1..512)", S);
-  g.NR = a->B * a->R;
+  g.NR = a->n_rays > 0 ? a->n_rays : a->B * a->R;
+  g.ray0 = a->n_rays > 0 ? a->ray_offset : 0;
   g.R = a->R;
   g.S = S;
   g.G = S <= kRows ? kRows / S : 1;
@@ -864,6 +866,9 @@ const __half* map_of(const NjfField* f, const NjfRenderArgs* a, int level /* -1 
 int check_args(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a) {
   if (!f || !cams || !a) NJF_FAIL("null argument");
   if (a->B < 1 || a->R < 1) NJF_FAIL("B=%d R=%d: nothing to render", a->B, a->R);
+  if (a->n_rays < 0 || a->ray_offset < 0 ||
+      (a->n_rays > 0 && static_cast<long long>(a->ray_offset) + a->n_rays > static_cast<long long>(a->B) * a->R))
+    NJF_FAIL("ray range [%d, %d + %d) outside the %d x %d call", a->ray_offset, a->ray_offset, a->n_rays, a->B, a->R);
   if (a->n_levels != f->desc.n_proposal) NJF_FAIL("n_levels %d != field n_proposal %d", a->n_levels, f->desc.n_proposal);
   if (!a->origins || !a->dirs || !a->z_near || !a->z_far || !a->maps) NJF_FAIL("missing ray / map input");
   if (a->Hf < 1 || a->Wf < 1 || a->Hf > 16384 || a->Wf > 16384) NJF_FAIL("feature map %dx%d out of range", a->Hf, a->Wf);
@@ -1085,6 +1090,13 @@ extern "C" int njf_hoist_features(const NjfField* f, const float* feat_nchw, int
   return 0;
 }
 
+extern "C" int njf_hoist_features_views(const NjfField* f, const float* feat_nchw, int B_local, int view0, int B_total,
+                                        int Hf, int Wf, void* maps_out, void* stream_) {
+  if (!f || !feat_nchw || !maps_out) NJF_FAIL("njf_hoist_features_views: null argument");
+  if (B_local < 1 || view0 < 0 || view0 + B_local > B_total) NJF_FAIL("njf_hoist_features_views: views [%d, %d) outside %d", view0, view0 + B_local, B_total);
+  return njf_hoist_launch(f, feat_nchw, B_local, Hf, Wf, maps_out, static_cast<cudaStream_t>(stream_), view0, B_total);
+}
+
 extern "C" int njf_proposal_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a, int level,
                                  const float* bins_in, int bins_in_stride, void* stream_) {
   if (check_args(f, cams, a)) return 1;
@@ -1233,7 +1245,8 @@ extern "C" int njf_finish_pass(const NjfField* f, const NjfCameras* cams, const 
   if (check_args(f, cams, a)) return 1;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   FinishParams q{};
-  q.NR = a->B * a->R;
+  q.NR = a->n_rays > 0 ? a->n_rays : a->B * a->R;
+  q.ray0 = a->n_rays > 0 ? a->ray_offset : 0;
   q.R = a->R;
   q.A = f->desc.action_dim;
   q.action = a->action;

@@ -8,7 +8,8 @@ namespace njf {
 
 // ----------------------------------------------------------------------------- pass geometry
 struct PassGeom {
-  int NR;   // total rays (B*R)
+  int NR;   // rays of this call (B*R, or the length of a ray-sharded range)
+  int ray0; // index of the call's first ray in the flattened (view, ray) space (ray-sharded calls), else 0
   int R;    // rays per view
   int S;    // samples per ray in this pass
   int G;    // rays per 128-row tile (S <= 128) else 1
@@ -71,7 +72,7 @@ __device__ __forceinline__ void row_setup(const PassGeom& g, int group, int tile
     return;
   }
   rs.ray = ray;
-  const int b = ray / g.R;
+  const int b = (ray + g.ray0) / g.R;
   const bool cv = b < g.n_const_views;
   const float* vc = g.view_const[cv ? b : 0];
   if (g.points) {  // explicit world-space points instead of (ray, bin) samples

@@ -50,6 +50,7 @@ class NjfRenderArgs(Structure):
         ("level_inds", c_void_p * NJF_MAX_LEVELS),
         ("minmax", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t), ("packed", c_void_p),
+        ("ray_offset", c_int), ("n_rays", c_int),
     ]
 
 
@@ -65,6 +66,8 @@ def _declare():
     L.njf_hoisted_bytes.argtypes = [c_void_p, c_int, c_int, c_int]
     L.njf_hoist_features.restype = c_int
     L.njf_hoist_features.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    L.njf_hoist_features_views.restype = c_int
+    L.njf_hoist_features_views.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     for name in ("njf_render_forward", "njf_finish_pass"):
         fn = getattr(L, name)
         fn.restype = c_int
@@ -188,6 +191,24 @@ class Field:
         nbytes = L.njf_hoisted_bytes(self._h, B, Hf, Wf)
         maps = torch.empty(nbytes, dtype=torch.uint8, device=feat_nchw.device)
         _lib.check(L.njf_hoist_features(self._h, feat_nchw.data_ptr(), B, Hf, Wf, maps.data_ptr(), stream_ptr()))
+        return maps
+
+    def hoist_views(self, feat_nchw: torch.Tensor, view0: int, n_views_total: int,
+                    maps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Hoist the given views into slots [view0, view0 + B_local) of a map buffer laid out for ``n_views_total``
+        views (allocated here if ``maps`` is None): what a rank of a ray-sharded multi-view call does for the views
+        its ray range touches."""
+        L = _declare()
+        assert feat_nchw.is_cuda and feat_nchw.dtype == torch.float32
+        self._check_device(feat_nchw, "feature map")
+        feat_nchw = feat_nchw.contiguous()
+        Bl, C, Hf, Wf = feat_nchw.shape
+        if C != 512:
+            raise _lib.NjfError(f"feature map has {C} channels, kernels are built for 512")
+        if maps is None:
+            maps = torch.empty(L.njf_hoisted_bytes(self._h, n_views_total, Hf, Wf), dtype=torch.uint8, device=feat_nchw.device)
+        _lib.check(L.njf_hoist_features_views(self._h, feat_nchw.data_ptr(), Bl, int(view0), int(n_views_total), Hf, Wf,
+                                              maps.data_ptr(), stream_ptr()))
         return maps
 
     def __del__(self):

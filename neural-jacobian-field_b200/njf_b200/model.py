@@ -87,9 +87,12 @@ class ModelStandardOutput:
 
 @dataclass
 class SampleBins:
-    """What the training losses read from the reference's RaySamples (spacing-domain bin edges)."""
+    """What the training losses read from the reference's RaySamples (rendering/ray_samplers.py:28-46):
+    spacing-domain and euclidean bin edges of one sampling level."""
     spacing_starts: Tensor  # (B,R,S,1)
     spacing_ends: Tensor    # (B,R,S,1)
+    starts: Optional[Tensor] = None  # (B,R,S,1) euclidean
+    ends: Optional[Tensor] = None    # (B,R,S,1)
 
 
 @dataclass
@@ -184,27 +187,82 @@ class _FlowFromEncoding(torch.autograd.Function):
         act = action.detach().contiguous().float()
         _lib.check(L.njf_flow_from_encoding(api.dptr(jbar), api.dptr(p), api.dptr(act), api.dptr(w2c), api.dptr(kpx),
                                             B * R, R, A, api.dptr(flow), api.dptr(pw), api.stream_ptr()))
-        ctx.save_for_backward(jbar, pw, w2c, kpx)
+        ctx.save_for_backward(jbar, p, act, w2c, kpx)
         ctx.A = A
         return flow
 
     @staticmethod
     def backward(ctx, g):
-        jbar, pw, w2c, kpx = ctx.saved_tensors
-        B, R = pw.shape[:2]
-        # uv = (K c)_{0,1} / ((K c)_2 + 1e-9), c = W[:3,:3] x + W[:3,3];  d uv / d x, then x = p + J^T u
-        c = torch.einsum("bij,brj->bri", w2c[:, :3, :3], pw) + w2c[:, None, :3, 3]
-        k = torch.einsum("bij,brj->bri", kpx, c)
-        z = k[..., 2:3] + 1e-9
-        dk = torch.zeros(B, R, 2, 3, device=pw.device)
-        dk[..., 0, 0] = 1.0 / z[..., 0]
-        dk[..., 1, 1] = 1.0 / z[..., 0]
-        dk[..., 0, 2] = -k[..., 0] / (z[..., 0] ** 2)
-        dk[..., 1, 2] = -k[..., 1] / (z[..., 0] ** 2)
-        dx = torch.einsum("brij,bjk,bkl->bril", dk, kpx, w2c[:, :3, :3])          # (B,R,2,3)
-        J = jbar.reshape(B, R, ctx.A, 3)
-        ga = torch.einsum("bri,bril,bral->ba", g, dx, J)
+        # d flow / d action through proj(p + Jbar^T u): njf_flow_backward (csrc/xf_backward.cu), one thread per ray
+        from . import train as T
+
+        L = T._declare()
+        jbar, p, act, w2c, kpx = ctx.saved_tensors
+        B, R = p.shape[:2]
+        ga = torch.empty(B, ctx.A, device=p.device, dtype=torch.float32)
+        _lib.check(L.njf_flow_backward(api.dptr(g.contiguous().float()), None, api.dptr(jbar), api.dptr(p), api.dptr(act),
+                                       api.dptr(w2c), api.dptr(kpx), B * R, R, ctx.A, None, api.dptr(ga),
+                                       api.stream_ptr()))
         return ga, None, None, None, None
+
+
+class _FrameGraph:
+    """Encoder + hoist + pose inversion + proposal / field / finish passes of ONE frame shape captured into a CUDA
+    graph (SURVEY.md 7.2 "CUDA-graph the whole frame", 8f-3): a frame is the host->device copies of its inputs into
+    static buffers plus one graph launch.  Possible because the library allocates nothing inside a pass and reads the
+    cameras through device pointers here (no per-view constants baked into kernel parameters)."""
+
+    NAMES = ("image", "ctxt_c2w", "ctxt_k", "trgt_c2w", "trgt_k", "origins", "dirs", "z_near", "z_far", "action")
+
+    def __init__(self, model: "Model", fld: api.Field, cam: CameraInput, rin: RenderingInput, rob: RobotInput, vis: bool):
+        dev = model._device()
+        self.dev = dev
+        r = model.cfg.rendering
+        self.s_prop, self.s_nerf = tuple(r.num_proposal_samples), int(r.num_nerf_samples)
+        src = self._sources(cam, rin, rob)
+        self.inp = {k: torch.empty(tuple(t.shape), dtype=torch.float32, device=dev) for k, t in zip(self.NAMES, src)}
+        B, R = rin.origins.shape[:2]
+        with torch.cuda.device(dev):
+            self.bins0, self.us = api.eval_tables(self.s_prop, self.s_nerf, dev)
+            self.ws = torch.empty(fld.workspace_bytes(B, R, self.s_prop, self.s_nerf), dtype=torch.uint8, device=dev)
+            self._copy_in(src)
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(2):   # warm-up: cuDNN algorithm choice, function attributes, allocator
+                    self._body(model, fld, vis)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self.res = self._body(model, fld, vis)
+
+    @staticmethod
+    def _sources(cam, rin, rob):
+        return (cam.input_image, cam.ctxt_extrinsics, cam.ctxt_intrinsics, cam.trgt_extrinsics, cam.trgt_intrinsics,
+                rin.origins, rin.directions, rin.z_near, rin.z_far, rob.robot_action)
+
+    def _copy_in(self, src):
+        for k, t in zip(self.NAMES, src):
+            self.inp[k].copy_(t.detach(), non_blocking=True)
+
+    def _body(self, model, fld, vis) -> RenderResult:
+        i = self.inp
+        feats = model.encoder.forward(i["image"]).float().contiguous()
+        maps = fld.hoist(feats)
+        cams, keep = api.make_cameras(i["ctxt_c2w"], i["ctxt_k"], i["trgt_c2w"], i["trgt_k"], self.dev)
+        Hf, Wf = feats.shape[-2:]
+        res = render(fld, maps, Hf, Wf, cams, i["origins"], i["dirs"], i["z_near"], i["z_far"], i["action"], self.s_prop,
+                     self.s_nerf, vis=vis, bins0=self.bins0, us=self.us, anneal=model._anneal, workspace=self.ws)
+        res._cams = (keep, feats, maps)
+        return res
+
+    def run(self, cam, rin, rob) -> RenderResult:
+        with torch.cuda.device(self.dev):
+            self._copy_in(self._sources(cam, rin, rob))
+            self.graph.replay()
+        return self.res   # static buffers: overwritten by the next replay of this shape
 
 
 class Model(nn.Module):
@@ -225,6 +283,10 @@ class Model(nn.Module):
         self._field: Optional[api.Field] = None
         self._field_key = None
         self.sh_fp16_round = True  # tiny-cuda-nn's SH encoding returns fp16
+        self.sh_convention = "tcnn"  # or "nerfstudio_torch" (what nerfstudio computes without tiny-cuda-nn)
+        self.cuda_graph = False    # eval-mode forward of a fixed shape as ONE CUDA-graph launch (encoder + hoist + render)
+        self._graphs: Dict[tuple, "_FrameGraph"] = {}
+        self.jitter_generator: Optional[torch.Generator] = None   # train-mode stratified jitter (None = torch's global CUDA RNG)
 
     # ------------------------------------------------------------------ training-schedule hooks (model.py:201-213)
     def step_before_iter(self, step):
@@ -241,25 +303,47 @@ class Model(nn.Module):
             self._steps_since_update += 1
 
     # ------------------------------------------------------------------ packed-weight cache
+    def _mode(self) -> str:
+        return getattr(self.decoder, "mode", "regular")
+
+    def _head_and_dim(self) -> Tuple[str, int]:
+        """Kernel head and action dimension for the decoder's current mode.  mode "arm"
+        (action_decoder_jacobian.py:306-313, 331, 400-407, 439) swaps the Jacobian head for ``jacobian_head_arm``,
+        a ResnetFC with 3 * arm_action_dim outputs: that is the MLP-head kernel on the arm head's weights."""
+        if self._mode() == "arm":
+            if not getattr(self.decoder.cfg, "use_arm_model", False):
+                raise _lib.NjfError("decoder mode 'arm' needs cfg.use_arm_model=True (jacobian_head_arm)")
+            return "jacobian_mlp", int(self.decoder.cfg.arm_action_dim)
+        return self.cfg.action_decoder.name, int(self.cfg.action_dim)
+
     def _hot_state(self) -> Dict[str, Tensor]:
+        arm = self._mode() == "arm"
         sd = {}
         for k, v in self.state_dict().items():
-            if k.startswith("decoder.") or k.startswith("proposal_networks."):
-                if "jacobian_head_arm" in k:
-                    continue
+            if not (k.startswith("decoder.") or k.startswith("proposal_networks.")):
+                continue
+            if arm:
+                if k.startswith("decoder.jacobian_head_arm."):
+                    sd["decoder.jacobian_head." + k[len("decoder.jacobian_head_arm."):]] = v
+                elif "jacobian" not in k:
+                    sd[k] = v
+            elif "jacobian_head_arm" not in k:
                 sd[k] = v
         return sd
 
     def field(self) -> api.Field:
-        """Packed weights for the kernels; re-packed whenever a hot-path parameter changed."""
+        """Packed weights for the kernels; re-packed whenever a hot-path parameter or a packing option changed."""
         dev = self._device()
         params = [p for n, p in self.named_parameters() if not n.startswith("encoder.")]
-        key = (dev, tuple((p.data_ptr(), p._version) for p in params))
+        key = (dev, self._mode(), bool(self.sh_fp16_round), self.sh_convention,
+               tuple((p.data_ptr(), p._version) for p in params))
         if self._field is None or self._field_key != key:
+            head, A = self._head_and_dim()
             with torch.cuda.device(dev):
-                self._field = api.Field(self.cfg.action_decoder.name, self.cfg.action_dim, len(self.proposal_networks),
-                                        self._hot_state(), sh_fp16_round=self.sh_fp16_round)
+                self._field = api.Field(head, A, len(self.proposal_networks), self._hot_state(),
+                                        sh_fp16_round=self.sh_fp16_round, sh_convention=self.sh_convention)
             self._field_key = key
+            self._graphs.clear()
         return self._field
 
     def _device(self) -> torch.device:
@@ -270,12 +354,13 @@ class Model(nn.Module):
         return dev
 
     def _check_mode(self):
-        if getattr(self.decoder, "mode", "regular") != "regular":
-            raise NotImplementedError("only decoder mode 'regular' is implemented")
-        if self.training:
-            raise NotImplementedError(
-                "njf_b200.Model: training-mode forward (stratified jitter + autograd through the render) is the "
-                "next row of the scope table (SURVEY.md section 8f); call model.eval() for inference")
+        if self._mode() not in ("regular", "arm"):
+            raise NotImplementedError(f"decoder mode '{self._mode()}' unknown")
+
+    def _trainable_outside_head(self) -> List[str]:
+        pat = self.decoder.action_param_glob_pattern
+        return [n for n, p in self.named_parameters()
+                if p.requires_grad and not (n.startswith("decoder.") and pat in n[len("decoder."):])]
 
     # ------------------------------------------------------------------ encoding
     def _encode(self, camera_input: CameraInput, robot_input: RobotInput) -> PixelEncoding:
@@ -298,13 +383,13 @@ class Model(nn.Module):
                                       camera_input.trgt_intrinsics, dev)
         mv = lambda t: t.detach().to(dev, torch.float32, non_blocking=True)
         Hf, Wf = pe.features.shape[-2:]
+        host_nf = ((rendering_input.z_near, rendering_input.z_far)
+                   if rendering_input.z_near.device.type == "cpu" and not pe.extrinsics.is_cuda else None)
         with torch.cuda.device(dev):
             res = render(self.field(), pe.hoisted, Hf, Wf, cams, mv(rendering_input.origins),
                          mv(rendering_input.directions), mv(rendering_input.z_near), mv(rendering_input.z_far),
                          mv(robot_input.robot_action), tuple(r.num_proposal_samples), r.num_nerf_samples,
-                         anneal=self._anneal,
-                         host_near_far=((rendering_input.z_near, rendering_input.z_far)
-                                        if rendering_input.z_near.device.type == "cpu" else None), **kw)
+                         anneal=self._anneal, host_near_far=host_nf, **kw)
         res._cams = keep
         return res
 
@@ -312,18 +397,114 @@ class Model(nn.Module):
     def forward(self, camera_input: CameraInput, rendering_input: RenderingInput, robot_input: RobotInput,
                 compute_vis_features: bool = False) -> ModelOutput:
         self._check_mode()
+        if self.training:
+            return self._forward_train(camera_input, rendering_input, robot_input, compute_vis_features)
         out_dev = rendering_input.origins.device
-        pe = self._encode(camera_input, robot_input)
-        res = self._render(pe, camera_input, rendering_input, robot_input, vis=compute_vis_features)
+        if self.cuda_graph:
+            res = self._graph_frame(camera_input, rendering_input, robot_input, compute_vis_features)
+            if out_dev.type == "cuda":   # the graph's outputs are static buffers: hand CUDA callers their own copy
+                res = RenderResult(**{k: (v.clone() if isinstance(v, Tensor) else v) for k, v in vars(res).items()
+                                      if k in RenderResult.__dataclass_fields__})
+        else:
+            pe = self._encode(camera_input, robot_input)
+            res = self._render(pe, camera_input, rendering_input, robot_input, vis=compute_vis_features)
+        return self._model_output(res, out_dev, compute_vis_features, None)
+
+    @staticmethod
+    def _model_output(res, out_dev, compute_vis_features, training_output) -> ModelOutput:
         back = (lambda t: t) if out_dev.type == "cuda" else (lambda t: t.to(out_dev))
         out = ModelOutput(
             standard_output=ModelStandardOutput(rgb=back(res.rgb), depth=back(res.depth), optical_flow=back(res.flow)),
-            training_output=None, vis_output=None)
+            training_output=training_output, vis_output=None)
         if compute_vis_features:
             out.vis_output = ModelVisOutput(action_features=back(res.jbar), steps=back(res.steps),
                                             weights=back(res.weights), ray_positions=back(res.p),
                                             ray_positions_warped=back(res.pw))
         return out
+
+    # ------------------------------------------------------------------ train-mode forward (model.py:316-396 with
+    # self.training: stratified jitter, ray_samplers.py:219-233 / 389-401; ModelTrainingOutput, model.py:377-382)
+    def _forward_train(self, camera_input, rendering_input, robot_input, compute_vis_features) -> ModelOutput:
+        from . import train as T
+
+        dev = self._device()
+        r = self.cfg.rendering
+        s_prop, s_nerf = tuple(r.num_proposal_samples), int(r.num_nerf_samples)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if need_grad:
+            outside = self._trainable_outside_head()
+            if outside:
+                raise NotImplementedError(
+                    "njf_b200.Model trains the ACTION phase only (everything but the Jacobian head frozen, "
+                    "models/model_wrapper.py:75-85): call model.decoder.freeze_non_action_parameters() and freeze the "
+                    "encoder / proposal networks, or run under torch.no_grad().  Perception-phase gradients (density, "
+                    f"colour, proposal networks, encoder) have no backward kernels yet; trainable outside the head: {outside[:4]} ...")
+            if self.cfg.action_decoder.name != "jacobian_transformer" or self._mode() != "regular":
+                raise NotImplementedError("backward kernels exist for the cross-attention Jacobian head "
+                                          "('jacobian_transformer', mode 'regular') only")
+        out_dev = rendering_input.origins.device
+        pe = self._encode(camera_input, robot_input)
+        mv = lambda t: t.detach().to(dev, torch.float32, non_blocking=True).contiguous()
+        o, d = mv(rendering_input.origins), mv(rendering_input.directions)
+        zn, zf = mv(rendering_input.z_near), mv(rendering_input.z_far)
+        B, R = o.shape[:2]
+        # RNG stays in torch: seed torch / set `jitter_generator` to reproduce a step
+        bins0, us = T.stratified_tables(s_prop, s_nerf, B, R, r.single_jitter, dev,
+                                        generator=getattr(self, "jitter_generator", None))
+        action = robot_input.robot_action.to(dev, torch.float32)
+        cams, keep = api.make_cameras(pe.extrinsics, pe.intrinsics, camera_input.trgt_extrinsics,
+                                      camera_input.trgt_intrinsics, dev)
+        Hf, Wf = pe.features.shape[-2:]
+        with torch.cuda.device(dev):
+            if need_grad:
+                holder: list = []
+                folded = T.fold_head(self.decoder, self.cfg.action_dim)
+                wq = self.decoder.jacobian_query_mlp
+                flow, pw, jbar, _, _, _ = T._RenderJacobianHead.apply(
+                    folded, wq.weight, wq.bias, action, self.field(), pe.hoisted, pe.features, cams, keep, o, d, zn, zf,
+                    s_prop, s_nerf, bins0, us, self._anneal, holder)
+                res = holder[0]
+                res_flow, res_pw, res_jbar = flow, pw, jbar
+            else:
+                res = render(self.field(), pe.hoisted, Hf, Wf, cams, o, d, zn, zf, action.detach().contiguous(), s_prop,
+                             s_nerf, vis=True, sampler_outputs=True, bins0=bins0, us=us, anneal=self._anneal)
+                res_flow, res_pw, res_jbar = res.flow, res.pw, res.jbar
+        res._cams = keep
+        # ModelTrainingOutput: weights and sample bins of every proposal level and of the final level
+        near, far = zn[:, None, None], zf[:, None, None]
+        euclid = lambda b: b * far + (1 - b) * near                       # ray_samplers.py:242-245
+        level_bins = [bins0] + list(res.level_bins)                        # spacing-domain edges per level
+        weights_list, samples_list = [], []
+        for lvl, b in enumerate(level_bins):
+            w = res.prop_weights[lvl] if lvl < len(s_prop) else res.weights
+            e = euclid(b)
+            weights_list.append(w[..., None])
+            samples_list.append(SampleBins(spacing_starts=b[..., :-1, None], spacing_ends=b[..., 1:, None],
+                                           starts=e[..., :-1, None], ends=e[..., 1:, None]))
+        back = (lambda t: t) if out_dev.type == "cuda" else (lambda t: t.to(out_dev))
+        out = ModelOutput(
+            standard_output=ModelStandardOutput(rgb=back(res.rgb), depth=back(res.depth), optical_flow=back(res_flow)),
+            training_output=ModelTrainingOutput(weights_list=[back(w) for w in weights_list], ray_samples_list=samples_list),
+            vis_output=None)
+        if compute_vis_features:
+            out.vis_output = ModelVisOutput(action_features=back(res_jbar), steps=back(res.steps),
+                                            weights=back(res.weights), ray_positions=back(res.p),
+                                            ray_positions_warped=back(res_pw))
+        return out
+
+    # ------------------------------------------------------------------ one CUDA-graph launch per frame
+    def _graph_frame(self, camera_input, rendering_input, robot_input, vis: bool) -> RenderResult:
+        dev = self._device()
+        fld = self.field()
+        B, R = rendering_input.origins.shape[:2]
+        key = (tuple(camera_input.input_image.shape), B, R, bool(vis), float(self._anneal),
+               tuple((p.data_ptr(), p._version) for p in self.encoder.parameters()))
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 4:
+                self._graphs.clear()
+            g = self._graphs[key] = _FrameGraph(self, fld, camera_input, rendering_input, robot_input, vis)
+        return g.run(camera_input, rendering_input, robot_input)
 
     # ------------------------------------------------------------------ inverse-dynamics helpers (model.py:458-525)
     def encode_image(self, camera_input, rendering_input, robot_input) -> ModelInferenceEncoding:

@@ -171,8 +171,12 @@ class ActionDecoderJacobian(nn.Module):
     action_param_glob_pattern = "jacobian"
 
     def switch_mode(self, mode: Literal["regular", "arm"]):
-        if mode != "regular":
-            raise NotImplementedError("njf_b200: only mode='regular' has a fused kernel")
+        """action_decoder_jacobian.py:89-90.  "arm" renders with ``jacobian_head_arm`` (a ResnetFC Jacobian head of
+        3 * arm_action_dim outputs): njf_b200.Model packs that head for the MLP-head kernel."""
+        if mode not in ("regular", "arm"):
+            raise ValueError(f"unknown decoder mode '{mode}'")
+        if mode == "arm" and not getattr(self.cfg, "use_arm_model", False):
+            raise ValueError("mode 'arm' needs cfg.use_arm_model=True")
         self.mode = mode
 
     def freeze_non_action_parameters(self) -> int:
@@ -251,6 +255,11 @@ class EncoderResnet(nn.Module):
 
     def forward(self, rgb: torch.Tensor) -> torch.Tensor:
         m = self.model
+        if rgb.is_cuda:   # NHWC storage: the layout cuDNN's tensor-core convolutions run in natively (values unchanged)
+            if not getattr(self, "_channels_last", False):
+                m.to(memory_format=torch.channels_last)
+                self._channels_last = True
+            rgb = rgb.contiguous(memory_format=torch.channels_last)
         x = m.relu(m.bn1(m.conv1(rgb)))
         lat = [x]
         x = m.layer1(m.maxpool(x)); lat.append(x)
@@ -266,8 +275,18 @@ class EncoderResnet(nn.Module):
 # ----------------------------------------------------------------------------- registries
 ENCODERS = {"resnet": EncoderResnet}
 DENSITY_DECODERS = {"density_mlp": DensityDecoderMlp}
-ACTION_DECODERS = {"jacobian_mlp": ActionDecoderJacobianMLP, "jacobian_transformer": ActionDecoderJacobianTransformer}
-# "flow_mlp" (ablation decoder, models/decoder/action_decoder_flow.py) is out of scope: no shipped config selects it.
+class ActionDecoderFlowMlp(nn.Module):
+    """Registry slot of the reference's ablation decoder (models/decoder/action_decoder_flow.py:64-286: a direct
+    scene-flow MLP conditioned on the action, no Jacobian).  No shipped config selects it and it has no B200 kernel
+    ("keep registry slot only"): constructing it fails loudly."""
+
+    def __init__(self, cfg=None, action_dim: int = 0, encoder_dim: int = 0):
+        raise NotImplementedError("action decoder 'flow_mlp' (ablation baseline) has no B200 kernel; "
+                                  "use 'jacobian_mlp' or 'jacobian_transformer'")
+
+
+ACTION_DECODERS = {"jacobian_mlp": ActionDecoderJacobianMLP, "jacobian_transformer": ActionDecoderJacobianTransformer,
+                   "flow_mlp": ActionDecoderFlowMlp}
 
 EncoderCfg = EncoderResnetCfg
 DensityDecoderCfg = DensityDecoderMlpCfg

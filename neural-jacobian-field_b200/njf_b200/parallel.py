@@ -52,6 +52,30 @@ def allreduce_minmax(minmax: torch.Tensor, group=None) -> torch.Tensor:
     return minmax
 
 
+def shard_views(start: int, stop: int, rays_per_view: int) -> Tuple[int, int]:
+    """Views [v0, v1) touched by the flattened ray range [start, stop)."""
+    return start // rays_per_view, (stop - 1) // rays_per_view + 1
+
+
+def render_sharded(fld, maps, Hf: int, Wf: int, cams, origins: torch.Tensor, dirs: torch.Tensor, z_near, z_far, action,
+                   s_prop, s_nerf: int, n_views: int, rays_per_view: int, rank: int, world: int, group=None,
+                   gather: bool = True, **kw):
+    """One rank's part of a ray-sharded B-view call (BASELINE config 4): rays [start, stop) of the
+    flattened (view, ray) space, the reference's call-global depth clip reproduced by all-reducing (min, max) of
+    the sample steps between njf_field_pass and njf_finish_pass, and the packed per-ray struct that
+    njf_finish_pass writes gathered with ONE collective.  ``origins`` / ``dirs``: this rank's (n, 3) rays;
+    cameras / z_near / z_far / action / ``maps``: all ``n_views`` views (only the views the range touches are read).
+    Returns (RenderResult of the shard, gathered (n_views * rays_per_view, 12 + 3A) frame or None)."""
+    from .render import render
+
+    start, stop = ray_shard(n_views * rays_per_view, rank, world)
+    assert origins.shape[0] == stop - start, "origins must hold exactly this rank's rays"
+    res = render(fld, maps, Hf, Wf, cams, origins[None], dirs[None], z_near, z_far, action, s_prop, s_nerf, packed=True,
+                 minmax_hook=lambda mm: allreduce_minmax(mm, group), ray_range=(n_views, rays_per_view, start), **kw)
+    frame = gather_rendered(res.packed[0], n_views * rays_per_view, group) if gather else None
+    return res, frame
+
+
 def gather_rendered(packed: torch.Tensor, n_rays_total: int, group=None) -> torch.Tensor:
     """All-gather the per-rank packed ray buffers into the full (n_rays_total, C) frame buffer.
     Shards may differ by one ray, so ranks pad to the largest shard for the single collective."""

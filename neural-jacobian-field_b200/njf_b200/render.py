@@ -39,7 +39,8 @@ def render(fld: api.Field, maps: torch.Tensor, Hf: int, Wf: int, cams: api.NjfCa
            us: Optional[Sequence[torch.Tensor]] = None, anneal: float = 1.0,
            sum_vec_width: Optional[int] = None, final_bins: Optional[torch.Tensor] = None,
            host_near_far: Optional[Sequence[torch.Tensor]] = None, packed: bool = False,
-           workspace: Optional[torch.Tensor] = None, minmax_hook=None) -> RenderResult:
+           workspace: Optional[torch.Tensor] = None, minmax_hook=None,
+           ray_range: Optional[Sequence[int]] = None) -> RenderResult:
     """One fused render of B x R rays.  All tensors live on the field's CUDA device.
 
     ``final_bins`` (B,R,s_nerf+1): skip the proposal levels and render the field at the given
@@ -48,12 +49,20 @@ def render(fld: api.Field, maps: torch.Tensor, Hf: int, Wf: int, cams: api.NjfCa
     per-stream buffer of fld.workspace_bytes(...).
     ``minmax_hook(minmax)``: called between the field pass and the finish pass with the (2,) device tensor of the
     call's (min, max) sample distance -- a ray-sharded render all-reduces it there so that every shard applies
-    the reference's call-global depth clip (models/model.py:277); forces the staged entry points."""
+    the reference's call-global depth clip (models/model.py:277); forces the staged entry points.
+    ``ray_range = (n_views, rays_per_view, ray_offset)``: a ray-sharded call -- ``origins`` / ``dirs`` are
+    (1, n, 3) and hold rays [ray_offset, ray_offset + n) of the flattened (view, ray) space of an
+    n_views x rays_per_view call; cameras, z_near, z_far, action and ``maps`` cover all n_views views."""
     L = api._declare()
     dev = origins.device
     fld._check_device(origins, "ray origins")
     fld._check_device(maps, "hoisted maps")
     B, R = origins.shape[:2]
+    Bv, Rv = B, R            # views / rays per view as the kernels see them
+    if ray_range is not None:
+        Bv, Rv, ray_offset = (int(v) for v in ray_range)
+        if B != 1:
+            raise _lib.NjfError("a ray-sharded call takes origins / dirs of shape (1, n, 3)")
     A = fld.action_dim
     f32 = dict(device=dev, dtype=torch.float32)
     origins, dirs = origins.contiguous().float(), dirs.contiguous().float()
@@ -61,13 +70,16 @@ def render(fld: api.Field, maps: torch.Tensor, Hf: int, Wf: int, cams: api.NjfCa
     action = action.contiguous().float()
     if len(s_prop) != fld.n_proposal:
         raise _lib.NjfError(f"{len(s_prop)} proposal levels requested, field has {fld.n_proposal}")
-    tab_bins0, tab_us = api.eval_tables(s_prop, s_nerf, dev)
+    if bins0 is None or us is None:   # eval mode: the reference's own linspace tables (host -> device copy)
+        tab_bins0, tab_us = api.eval_tables(s_prop, s_nerf, dev)
     bins0 = tab_bins0 if bins0 is None else bins0.contiguous().float()
     us = tab_us if us is None else [u.contiguous().float() for u in us]
 
     res = RenderResult(bins0=bins0)
     a = api.NjfRenderArgs()
-    a.B, a.R, a.n_levels, a.s_nerf = B, R, len(s_prop), int(s_nerf)
+    a.B, a.R, a.n_levels, a.s_nerf = Bv, Rv, len(s_prop), int(s_nerf)
+    if ray_range is not None:
+        a.ray_offset, a.n_rays = ray_offset, R
     for i, s in enumerate(s_prop):
         a.s_prop[i] = int(s)
     a.origins, a.dirs = api.dptr(origins), api.dptr(dirs)

@@ -24,7 +24,7 @@ from test_gpu_render import DEV, _check_composites, _check_samples, _field_and_m
 
 pytestmark = pytest.mark.gpu
 
-INDEX_MISMATCH_BOUND = 0.02   # measured 0.3-1.1 % on these cases (profiles/parity_r02.json); bound = measured + margin
+INDEX_MISMATCH_BOUND = 0.01   # measured on a B200: cfg3 0.20 %, cfg2 0.14 %, cfg5 0.50 % (profiles/parity_r02.json); bound = measured + margin
 
 
 def _scene(B, Hf, Wf, A, seed, near=0.65, far=3.2):
@@ -202,7 +202,8 @@ def test_train_mode_sampler_inputs_vs_oracle(s_prop, s_nerf, single_jitter):
                    sampler_outputs=True, bins0=bins0.to(DEV), us=[u.to(DEV) for u in us], anneal=anneal)
     for lvl in range(len(s_prop)):
         np.testing.assert_allclose(full.prop_weights[lvl].cpu().numpy(), ref[f"prop_weights_{lvl}"], atol=2e-3, rtol=0)
-        np.testing.assert_allclose(full.level_bins[lvl].cpu().numpy(), ref[f"prop_bins_{lvl + 1}"], atol=3e-3, rtol=0)
+        nxt = ref[f"prop_bins_{lvl + 1}"] if lvl + 1 < len(s_prop) else ref["final_bins"]
+        np.testing.assert_allclose(full.level_bins[lvl].cpu().numpy(), nxt, atol=3e-3, rtol=0)
     _check_composites(full, ref, 2.55, loose=2.5)
     assert np.mean(_index_mismatch(full, ref, len(s_prop))) < 2 * INDEX_MISMATCH_BOUND   # annealed weights: flatter CDF
 
