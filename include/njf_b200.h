@@ -261,6 +261,8 @@ int njf_selftest_chain(const float* w0, const float* w1, const float* w2, const 
  * the launching stream; a later call returns the accumulated milliseconds of field_kernel and of xf_kernel (the
  * cross-attention head; 0 for the MLP head) since the previous call and resets the counters.  Either pointer may be NULL. */
 int njf_debug_field_timing(int enable, float* field_kernel_ms, float* xf_kernel_ms);
+/* number of kernels the library has launched since the last reset (bench.py's gpu_launches) */
+long long njf_debug_launch_count(int reset);
 
 #ifdef __cplusplus
 }

@@ -226,6 +226,7 @@ int njf_hoist_launch(const NjfField* f, const float* feat_nchw, int B, int Hf, i
   }
   dim3 grid((p.HW + 127) / 128, nj, B);
   hoist_tc_kernel<<<grid, 128, kHoistSmem, stream>>>(p);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }

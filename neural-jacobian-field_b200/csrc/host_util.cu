@@ -1,6 +1,7 @@
 // Host-side utilities of libnjf_b200.so: error string, fp16 conversion, weight-image packer.
 #include <cuda_fp16.h>
 
+#include <atomic>
 #include <cstring>
 
 #include "njf_internal.h"
@@ -12,6 +13,9 @@ std::string& last_error() {
   static thread_local std::string s;
   return s;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 uint16_t f32_to_f16_bits(float f) {
   const __half h = __float2half_rn(f);
@@ -44,3 +48,9 @@ void pack_sw32_bias_f16(const float* bias, int n_real, int n_pad, uint8_t* out) 
 
 extern "C" const char* njf_last_error(void) { return njf::last_error().c_str(); }
 extern "C" int njf_version(void) { return 100; }
+
+extern "C" long long njf_debug_launch_count(int reset) {
+  const long long v = njf::g_launches.load(std::memory_order_relaxed);
+  if (reset) njf::g_launches.store(0, std::memory_order_relaxed);
+  return v;
+}

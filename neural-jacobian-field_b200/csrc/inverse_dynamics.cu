@@ -145,7 +145,9 @@ extern "C" int njf_flow_gn_terms(const float* jbar, const float* p, const float*
   GnParams q{jbar, p, action, trgt_w2c, trgt_k_px, target_flow, ray_weight, n_rays, rays_per_view, action_dim, workspace};
   dim3 grid((rays_per_view + 127) / 128, B);
   gn_terms_kernel<<<grid, 128, 0, stream>>>(q);
+  njf::count_launch();
   gn_unpack_kernel<<<B, 128, 0, stream>>>(workspace, B, action_dim, H, g, loss);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }

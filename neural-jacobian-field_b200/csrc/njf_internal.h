@@ -39,4 +39,7 @@ void pack_sw32_bias_f16(const float* bias, int n_real, int n_pad, uint8_t* out);
 
 uint16_t f32_to_f16_bits(float f);
 
+// number of kernels this library has launched (njf_debug_launch_count; bench.py's gpu_launches)
+void count_launch(int n = 1);
+
 }  // namespace njf

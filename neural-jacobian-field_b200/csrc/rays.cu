@@ -76,6 +76,7 @@ extern "C" int njf_make_rays(const float* k_norm, const float* c2w, const float*
   const long long n = static_cast<long long>(B) * R;
   if (n > 0x7fffffffLL) NJF_FAIL("njf_make_rays: too many rays");
   rays_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(p);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -137,6 +138,7 @@ extern "C" int njf_invert_poses(const float* c2w, float* w2c, int n, void* strea
   if (!c2w || !w2c) NJF_FAIL("njf_invert_poses: null argument");
   if (n < 1) return 0;
   invert_poses_kernel<<<(n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream_)>>>(c2w, w2c, n);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }

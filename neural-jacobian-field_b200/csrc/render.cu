@@ -958,6 +958,7 @@ int launch_field(const NjfField* f, FieldParams& p, void* ws, size_t ws_bytes, c
       NJF_CUDA(cudaEventRecord(ev[0], stream));
     }
     field_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+    njf::count_launch();
     NJF_CUDA(cudaGetLastError());
     if (ev) NJF_CUDA(cudaEventRecord(ev[1], stream));
     if (xf) {
@@ -1083,6 +1084,7 @@ extern "C" int njf_hoist_features(const NjfField* f, const float* feat_nchw, int
     const int CH = (m < f->desc.n_proposal) ? f->ch_prop : f->ch_main;
     dim3 grid((HW + 127) / 128, (CH + 127) / 128, B);
     hoist_kernel<<<grid, 256, 0, stream>>>(feat_nchw, f->d_hoist_w, f->d_hoist_b, out, HW, CH, n0);
+    njf::count_launch();
     NJF_CUDA(cudaGetLastError());
     out += static_cast<size_t>(B) * HW * CH;
     n0 += CH;
@@ -1157,12 +1159,14 @@ extern "C" int njf_proposal_pass(const NjfField* f, const NjfCameras* cams, cons
     const int nitems = (p.g.NG + 1) / 2;
     const int grid = nitems < num_sms() ? nitems : num_sms();
     proposal_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+    njf::count_launch();
     NJF_CUDA(cudaGetLastError());
     pdf_kernel<<<(nrays + wpb - 1) / wpb, wpb * 32, pdf_smem, stream>>>(
         wbuf, /*from_dd=*/1, /*store_weights=*/a->prop_weights[level] != nullptr,
         bins_in + static_cast<size_t>(ray0) * bins_in_stride, bins_in_stride, p.u + static_cast<size_t>(ray0) * p.u_stride,
         p.u_stride, nrays, S, p.n_out, p.anneal, p.sum_vec, p.bins_out + static_cast<size_t>(ray0) * nb,
         p.inds_out ? p.inds_out + static_cast<size_t>(ray0) * nb : nullptr);
+    njf::count_launch();
     NJF_CUDA(cudaGetLastError());
   }
   return 0;
@@ -1194,8 +1198,10 @@ extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const N
   p.rgb_samples = a->rgb_samples;
   p.minmax = reinterpret_cast<uint32_t*>(a->minmax);
   init_minmax_kernel<<<1, 1, 0, stream>>>(p.minmax);
+  njf::count_launch();
   if (launch_field(f, p, a->workspace, a->workspace_bytes, stream)) return 1;
   decode_minmax_kernel<<<1, 1, 0, stream>>>(p.minmax);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1237,6 +1243,7 @@ extern "C" int njf_point_features(const float* feat_nchw, const float* ctxt_w2c,
   const int wpb = 8;
   point_features_kernel<<<(B * N + wpb - 1) / wpb, wpb * 32, 0, stream>>>(points, ctxt_w2c, ctxt_k, feat_nchw, B, N, C,
                                                                        Hf, Wf, xyz_features, pixel_aligned_features);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1264,6 +1271,7 @@ extern "C" int njf_finish_pass(const NjfField* f, const NjfCameras* cams, const 
   if ((q.flow || q.pw || q.packed) && (!q.jbar || !q.p || !q.action || !q.trgt_w2c || !q.trgt_k))
     NJF_FAIL("flow / pw outputs need jbar, p, action and the target camera");
   finish_kernel<<<(q.NR + 255) / 256, 256, 0, stream>>>(q);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1295,6 +1303,7 @@ extern "C" int njf_pdf_sample(const float* weights, const float* bins_in, int bi
   pdf_kernel<<<(n_rays + wpb - 1) / wpb, wpb * 32, smem, stream>>>(const_cast<float*>(weights), 0, 0, bins_in,
                                                                  bins_in_stride, u, u_stride, n_rays, s_in, n_out,
                                                                  anneal, sum_vec_width, bins_out, inds_out);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1308,6 +1317,7 @@ extern "C" int njf_transmittance_weights(const float* deltas, const float* sigma
   const int wpb = (static_cast<size_t>(4) * 2 * s * sizeof(float) <= 48 * 1024) ? 4 : 1;  // s <= 4096: <= 32 KB
   tw_kernel<<<(n_rays + wpb - 1) / wpb, wpb * 32, static_cast<size_t>(wpb) * 2 * s * sizeof(float), stream>>>(
       deltas, sigma, n_rays, s, weights_out);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1330,6 +1340,7 @@ extern "C" int njf_flow_from_encoding(const float* jbar, const float* p, const f
   q.pw = pw;
   q.flow = flow;
   finish_kernel<<<(n_rays + 255) / 256, 256, 0, stream>>>(q);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }

@@ -656,11 +656,14 @@ extern "C" int njf_xf_backward(const float* folded, int action_dim, const void* 
   for (int l = 0; l < 3; ++l) {
     p.layer = l;
     xfb_layer_fwd<<<grid, kBWarps * 32, smem, stream>>>(p);
+    njf::count_launch();
   }
   xfb_head_bwd<<<grid, kBWarps * 32, smem, stream>>>(p);
+  njf::count_launch();
   for (int l = 2; l >= 0; --l) {
     p.layer = l;
     xfb_layer_bwd<<<grid, kBWarps * 32, smem, stream>>>(p);
+    njf::count_launch();
   }
   NJF_CUDA(cudaGetLastError());
   return 0;
@@ -701,6 +704,7 @@ extern "C" int njf_query_backward(const NjfCameras* cams, const NjfRenderArgs* a
   const int units = 2 * n_tiles;
   const int grid = units < bwd_grid() ? units : bwd_grid();
   query_bwd_kernel<<<grid, kBWarps * 32, sizeof(BwdSmem), stream>>>(q);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -715,6 +719,7 @@ extern "C" int njf_flow_backward(const float* g_flow, const float* g_pw_in, cons
   if (g_action) NJF_CUDA(cudaMemsetAsync(g_action, 0, static_cast<size_t>(B) * action_dim * sizeof(float), stream));
   FlowBwdParams q{n_rays, rays_per_view, action_dim, g_flow, g_pw_in, jbar, p, action, trgt_w2c, trgt_k_px, g_jbar, g_action};
   flow_bwd_kernel<<<(n_rays + 255) / 256, 256, 0, stream>>>(q);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }

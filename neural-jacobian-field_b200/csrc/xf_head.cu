@@ -448,6 +448,7 @@ int njf_xf_launch(const NjfField* f, const XfParams& params, cudaStream_t stream
   const int nitems = (p.NG + kXfSlots - 1) / kXfSlots;
   const int grid = nitems < sms ? nitems : sms;
   xf_kernel<<<grid, kXfThreads, XfSmem::kTotal, stream>>>(p);
+  njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;
 }

@@ -286,6 +286,7 @@ class Model(nn.Module):
         self.sh_convention = "tcnn"  # or "nerfstudio_torch" (what nerfstudio computes without tiny-cuda-nn)
         self.cuda_graph = False    # eval-mode forward of a fixed shape as ONE CUDA-graph launch (encoder + hoist + render)
         self._graphs: Dict[tuple, "_FrameGraph"] = {}
+        self.output_device: Optional[torch.device] = None   # None: results go back to where the rays came from (reference)
         self.jitter_generator: Optional[torch.Generator] = None   # train-mode stratified jitter (None = torch's global CUDA RNG)
 
     # ------------------------------------------------------------------ training-schedule hooks (model.py:201-213)
@@ -399,7 +400,7 @@ class Model(nn.Module):
         self._check_mode()
         if self.training:
             return self._forward_train(camera_input, rendering_input, robot_input, compute_vis_features)
-        out_dev = rendering_input.origins.device
+        out_dev = self.output_device or rendering_input.origins.device
         if self.cuda_graph:
             res = self._graph_frame(camera_input, rendering_input, robot_input, compute_vis_features)
             if out_dev.type == "cuda":   # the graph's outputs are static buffers: hand CUDA callers their own copy
@@ -442,7 +443,7 @@ class Model(nn.Module):
             if self.cfg.action_decoder.name != "jacobian_transformer" or self._mode() != "regular":
                 raise NotImplementedError("backward kernels exist for the cross-attention Jacobian head "
                                           "('jacobian_transformer', mode 'regular') only")
-        out_dev = rendering_input.origins.device
+        out_dev = self.output_device or rendering_input.origins.device
         pe = self._encode(camera_input, robot_input)
         mv = lambda t: t.detach().to(dev, torch.float32, non_blocking=True).contiguous()
         o, d = mv(rendering_input.origins), mv(rendering_input.directions)

@@ -76,16 +76,32 @@ def render_sharded(fld, maps, Hf: int, Wf: int, cams, origins: torch.Tensor, dir
     return res, frame
 
 
-def gather_rendered(packed: torch.Tensor, n_rays_total: int, group=None) -> torch.Tensor:
-    """All-gather the per-rank packed ray buffers into the full (n_rays_total, C) frame buffer.
-    Shards may differ by one ray, so ranks pad to the largest shard for the single collective."""
+def gather_rendered(packed: torch.Tensor, n_rays_total: int, group=None, dst: Optional[int] = None) -> Optional[torch.Tensor]:
+    """The per-rank packed ray buffers -> the full (n_rays_total, C) frame buffer with ONE collective: a gather to
+    rank ``dst`` (the other ranks return None; moves world x less data than an all-gather) or, with dst=None, an
+    all-gather.  Shards may differ by one ray, so ranks pad to the largest shard."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return packed
+    rank = dist.get_rank(group)
     C = packed.shape[1]
     sizes = [ray_shard(n_rays_total, r, world) for r in range(world)]
     mx = max(b - a for a, b in sizes)
     padded = packed if packed.shape[0] == mx else torch.cat([packed, packed.new_zeros(mx - packed.shape[0], C)])
-    out = packed.new_empty(world * mx, C)
-    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+    padded = padded.contiguous()
+    if dst is None:
+        out = packed.new_empty(world * mx, C)
+        dist.all_gather_into_tensor(out, padded, group=group)
+    else:
+        out = packed.new_empty(world * mx, C) if rank == dst else None
+        dist.gather(padded, list(out.view(world, mx, C).unbind(0)) if rank == dst else None, dst=dst, group=group)
+        if rank != dst:
+            return None
+    if all(b - a == mx for a, b in sizes):
+        return out
     return torch.cat([out[r * mx: r * mx + (b - a)] for r, (a, b) in enumerate(sizes)], dim=0)
+
+
+def gather_rows(rows: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gather of row-sharded (n_local, C) buffers (ray_shard split of n_total rows) on every rank."""
+    return gather_rendered(rows, n_total, group, dst=None)
