@@ -423,6 +423,7 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg4 strong-scaling leg of the default run")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)
@@ -583,17 +584,29 @@ def main():
         torch.cuda.synchronize()
         return float(host_frame[0, 0, 0]) if (world > 1 and rank == 0) else (float(host_out["rgb"][0, 0, 0]) if world == 1 else 0.0)
 
+    e2e_steps = max(3, min(args.steps, 10))
+    te = float("nan")
+    t_enc = None
     with torch.no_grad():
-        for _ in range(3):
-            e2e_step()
-        torch.cuda.synchronize()
-        if dist: dist.barrier()
-        e2e_steps = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        te = (time.perf_counter() - t0)
+        if not args.no_e2e:
+            for _ in range(3):
+                e2e_step()
+            torch.cuda.synchronize()
+            if dist: dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            torch.cuda.synchronize()
+            te = (time.perf_counter() - t0)
+            img_d = hs["image"].to(dev)      # the encoder alone (inside e2e, outside value), for the record
+            e0, e1 = ev(), ev()
+            model.encoder(img_d)
+            e0.record()
+            for _ in range(5):
+                model.encoder(img_d)
+            e1.record()
+            torch.cuda.synchronize()
+            t_enc = e0.elapsed_time(e1) / 5
     te = max_over_ranks(te, dev, dist)
     e2e_value = world * R * e2e_steps / te
     h2d = world * sum(hs[k].numel() * 4 for k in hs)      # every rank copies its view's inputs in
@@ -657,7 +670,7 @@ def main():
                          "finish+gather": t_tail},
         "roofline": roof,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": te / e2e_steps * 1e3,
+                "ms_per_step": te / e2e_steps * 1e3, "encoder_ms": t_enc,
                 "path": "Model.forward(compute_vis_features=True), one CUDA-graph launch per frame (encoder + hoist + render), "
                         "pinned host inputs, rgb/depth/flow/Jbar/p/p' read back to pinned host memory"
                         + ("; per-rank frames gathered to rank 0 first" if world > 1 else "")},

@@ -123,12 +123,16 @@ __device__ __forceinline__ void cta_teardown(const CtaCtx& c) {
 // ----------------------------------------------------------------------------- loader
 // `nrun` = how many times the program is executed by this CTA (items x tiles-per-item).
 __device__ __forceinline__ void loader_role(const CtaCtx& c, const Program& prog,
-                                            const uint8_t* __restrict__ blob, int nrun) {
+                                            const uint8_t* __restrict__ blob, int nrun, int debug = 0) {
   uint32_t cnt = 0;
   for (int run = 0; run < nrun; ++run) {
     for (int s = 0; s < prog.nsteps; ++s, ++cnt) {
       const uint32_t stage = cnt % kStages, par = (cnt / kStages) & 1u;
       mbar_wait_backoff(&c.bars->w_empty[stage], par ^ 1u);
+      if (debug & 8) {  // NJF_DEBUG_SKIP bit 3 (timing attribution only): no weight traffic, stale operands
+        mbar_arrive(&c.bars->w_full[stage]);
+        continue;
+      }
       const uint32_t bytes = prog.steps[s].w_bytes;
       mbar_arrive_expect_tx(&c.bars->w_full[stage], bytes);
       bulk_g2s(c.smem + SmemMap::kW + stage * kStageBytes, blob + prog.steps[s].w_off, bytes,

@@ -113,18 +113,19 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
   CtaCtx c = cta_setup(smem_raw);
   const PassGeom& g = p.g;
   const int warp = threadIdx.x >> 5;
-  const int nitems = (g.NG + 1) / 2;
+  const bool one_slot = (g.debug & 4) != 0;  // NJF_DEBUG_SKIP bit 2 (measurement only): slot 1 idles
+  const int nitems = one_slot ? g.NG : (g.NG + 1) / 2;
   int my_items = 0;
   for (int it = blockIdx.x; it < nitems; it += gridDim.x) ++my_items;
 
   if (warp == kLoaderWarp) {
-    if ((threadIdx.x & 31) == 0) loader_role(c, p.prog, p.blob, my_items * g.T);
+    if ((threadIdx.x & 31) == 0) loader_role(c, p.prog, p.blob, my_items * g.T, g.debug);
   } else if (warp == kIssuerWarp) {
     if ((threadIdx.x & 31) == 0) {
       const int NG = g.NG, T = g.T, bx = blockIdx.x, gx = gridDim.x;
       issuer_role(c, p.prog, my_items * g.T, [=](int run) {
         const int it = bx + (run / T) * gx;
-        return (2 * it + 1 < NG) ? 2 : 1;
+        return (!one_slot && 2 * it + 1 < NG) ? 2 : 1;
       });
     }
   } else {
@@ -132,15 +133,15 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
     SlotScratch* sc = slot_scratch(c, e.slot);
     const int lane = threadIdx.x & 31;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-      const int lgroup = 2 * it + e.slot;  // launch-local ray group
-      if (lgroup >= g.NG) continue;
+      const int lgroup = one_slot ? it : 2 * it + e.slot;  // launch-local ray group
+      if (lgroup >= g.NG || (one_slot && e.slot)) continue;
       const int group = g.group0 + lgroup;
       for (int tile = 0; tile < g.T; ++tile) {
         RowState rs;
         PROF(e, kPOther);
         row_setup(g, group, tile, e.row, rs);
         PROF(e, kPPdf);
-        if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
+        write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
         PROF(e, kPHead);
         write_posenc(e, rs.cam, rs.ray >= 0, g.debug);
         PROF(e, kPColor);
@@ -209,7 +210,7 @@ __device__ __forceinline__ void store_query_stream(const EpiCtx& e, uint4* qs_ti
   ld_acc32(e, x);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const uint4 q = *reinterpret_cast<const uint4*>(e.tz + tz_offset(e.row, 4 * e.half + j));
+    const uint4 q = *reinterpret_cast<const uint4*>(e.tz + tz_offset(e.row, 8 * e.half + j));  // gather_rows<64> layout
     const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
   __syncthreads();
 
   if (warp == kLoaderWarp) {
-    if ((threadIdx.x & 31) == 0) loader_role(c, p.prog, p.blob, my_items * g.T);
+    if ((threadIdx.x & 31) == 0) loader_role(c, p.prog, p.blob, my_items * g.T, g.debug);
   } else if (warp == kIssuerWarp) {
     if ((threadIdx.x & 31) == 0) {
       const int NG = g.NG, T = g.T, bx = blockIdx.x, gx = gridDim.x;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         float J[16];  // this thread's 16 of the 32 (padded) Jacobian columns: 16h .. 16h+15 (MLP head)
 #pragma unroll
         for (int j = 0; j < 16; ++j) J[j] = 0.f;
-        if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
+        write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
         write_posenc(e, rs.cam, valid, g.debug);
         epi_publish(e);  // -> lin_in (+ q_enc for the transformer head)
         __syncwarp();

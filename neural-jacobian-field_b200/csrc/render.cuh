@@ -4,6 +4,10 @@
 #pragma once
 #include "field.h"
 
+#ifndef NJF_GATHER_U
+#define NJF_GATHER_U 8
+#endif
+
 namespace njf {
 
 // ----------------------------------------------------------------------------- pass geometry
@@ -185,8 +189,9 @@ __device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)
 }
 
 // ----------------------------------------------------------------------------- gather
-// Per-row bilinear taps (F.grid_sample align_corners=True, padding_mode="border"): computed ONCE per
-// row by the row's own thread, then broadcast-read by the gathering warp for every channel segment.
+// Per-row bilinear taps (F.grid_sample align_corners=True, padding_mode="border"): computed once per row and read
+// by the gathering lanes for every channel segment.  BOTH threads of a row write the (identical) entry, so each of
+// the two warps of a row quarter reads only what it wrote itself.
 struct TapEntry {
   uint32_t off[4];  // BYTE offset of the nw, ne, sw, se tap pixels inside the hoisted map (< 4 GiB)
   uint32_t w2[4];   // their weights as packed fp16 pairs {w, w} (all zero for padding rows)
@@ -214,37 +219,49 @@ __device__ __forceinline__ void write_taps(TapEntry* tab, int row, const RowStat
       make_uint4(pack_f16x2(w.x, w.x), pack_f16x2(w.y, w.y), pack_f16x2(w.z, w.z), pack_f16x2(w.w, w.w));
 }
 
-// Gather of NCH hoisted channels starting at channel ch0 for the 16 rows owned by this warp
-// (rows 32q + 16h ..); each tap is one contiguous NCH*2-byte read spread over the lanes
-// (8 B / lane).  The four taps are blended in packed fp16 (HFMA2; the map, the weights and the
-// staged result are fp16 anyway -- 4 instead of 1 fp16 roundings).
-// The staging buffer is read by the row's two epilogue threads: pair barriers fence both ways.
-// gather_rows: rows [j_begin, j_end) of the warp's 16 rows, NO barriers -- the caller fences the staging buffer
-// with pair_bar (before the first rows of a segment: the partner warp has finished reading the previous
-// segment; after the last rows: the writes are visible to the row's two epilogue threads).  Splitting a segment
-// over several calls lets the trunk driver spread the L2-latency-bound loads over BOTH MMA wait windows of a
-// residual block (fc_0 and fc_1) instead of stacking them behind one.
+// Gather of NCH hoisted channels starting at channel ch0.  Warp (q, h) gathers, for ALL 32 rows of its row quarter,
+// exactly the channel half [ch0 + h*NCH/2, ch0 + (h+1)*NCH/2) that its own threads consume afterwards (a thread
+// owns columns 64h.. of its row): the staging buffer is written and read by the same warp, so the only fence
+// is a __syncwarp -- no named barrier between the two warps of a row quarter, and no waiting for the slower one.
+// A tap is one contiguous NCH-byte read spread over NCH/8 lanes (8 B per lane; 32*8/NCH rows per instruction).
+// The four taps are blended in packed fp16 (HFMA2; the map, the weights and the staged result are fp16 anyway --
+// 4 instead of 1 fp16 roundings).
+// gather_rows: row groups [j_begin, j_end) of the warp's kGroups<NCH> groups; the trunk driver spreads a segment
+// over BOTH MMA wait windows of a residual block (fc_0 and fc_1) instead of stacking it behind one.
+template <int NCH>
+struct GatherShape {
+  static constexpr int kLanesPerRow = NCH / 8;              // 16 (128 channels) or 8 (64 channels)
+  static constexpr int kRowsPerInstr = 32 / kLanesPerRow;   // 2 or 4
+  static constexpr int kGroups = 32 / kRowsPerInstr;        // 16 or 8 row groups per warp and segment
+};
 template <int NCH>
 __device__ __forceinline__ void gather_rows(EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0, int j_begin,
                                             int j_end) {
   static_assert(NCH == 128 || NCH == 64, "segment width");
+  using GS = GatherShape<NCH>;
   PROF(e, kPOther);
   if (g.debug & 1) return;
   const int lane = threadIdx.x & 31;
-  const int wrow0 = e.q * 32 + e.half * 16;
-  const bool active = (NCH == 128) || lane < 16;
-  const uint8_t* mp = reinterpret_cast<const uint8_t*>(g.map + ch0) + lane * 8;
-  constexpr int U = 4;
+  const int sub = lane / GS::kLanesPerRow;        // which row of the group this lane works on
+  const int piece = lane % GS::kLanesPerRow;      // which 8 B piece of the half-row
+  const int row0 = e.q * 32 + sub;                // + kRowsPerInstr * group
+  const uint8_t* mp = reinterpret_cast<const uint8_t*>(g.map + ch0) + e.half * NCH + piece * 8;
+  // staging: 16 B chunk index inside the row's 256 B.  Half h always stays inside chunks [8h, 8h+8) -- also for a
+  // 64-channel segment -- so that the XOR swizzle (row & 7) never moves one warp's data into the chunks the other
+  // warp of the row quarter reads or writes (the two warps are not synchronised with each other)
+  const int chunk = e.half * 8 + (piece >> 1);
+  const int chunk_sub = (piece & 1) * 8;
+  // U row groups x 4 taps of 8 B per lane are in flight per batch; the tap weights are fetched only when a row is
+  // blended, which keeps a batch at 8 B x 4 x U registers
+  constexpr int U = NJF_GATHER_U;
 #pragma unroll 1
   for (int j0 = j_begin; j0 < j_end; j0 += U) {
     uint2 t[U][4];
-    uint4 w[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const TapEntry* te = taps + wrow0 + j0 + u;
-      const uint4 px = *reinterpret_cast<const uint4*>(te->off);
-      w[u] = *reinterpret_cast<const uint4*>(te->w2);
-      if (active) {
+      if (j0 + u < j_end) {
+        const TapEntry* te = taps + row0 + GS::kRowsPerInstr * (j0 + u);
+        const uint4 px = *reinterpret_cast<const uint4*>(te->off);
         t[u][0] = __ldg(reinterpret_cast<const uint2*>(mp + px.x));
         t[u][1] = __ldg(reinterpret_cast<const uint2*>(mp + px.y));
         t[u][2] = __ldg(reinterpret_cast<const uint2*>(mp + px.z));
@@ -255,7 +272,10 @@ __device__ __forceinline__ void gather_rows(EpiCtx& e, const PassGeom& g, const 
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const uint32_t wq[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+      if (j0 + u >= j_end) break;
+      const int row = row0 + GS::kRowsPerInstr * (j0 + u);
+      const uint4 w = *reinterpret_cast<const uint4*>(taps[row].w2);
+      const uint32_t wq[4] = {w.x, w.y, w.z, w.w};
       __half2 lo = __hmul2(*reinterpret_cast<const __half2*>(&t[u][0].x), *reinterpret_cast<const __half2*>(&wq[0]));
       __half2 hi = __hmul2(*reinterpret_cast<const __half2*>(&t[u][0].y), *reinterpret_cast<const __half2*>(&wq[0]));
 #pragma unroll
@@ -263,26 +283,21 @@ __device__ __forceinline__ void gather_rows(EpiCtx& e, const PassGeom& g, const 
         lo = __hfma2(*reinterpret_cast<const __half2*>(&t[u][q].x), *reinterpret_cast<const __half2*>(&wq[q]), lo);
         hi = __hfma2(*reinterpret_cast<const __half2*>(&t[u][q].y), *reinterpret_cast<const __half2*>(&wq[q]), hi);
       }
-      if (active) {
-        uint2 o;
-        o.x = *reinterpret_cast<const uint32_t*>(&lo);
-        o.y = *reinterpret_cast<const uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(e.tz + tz_offset(wrow0 + j0 + u, lane >> 1) + (lane & 1) * 8) = o;
-      }
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo);
+      o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(e.tz + tz_offset(row, chunk) + chunk_sub) = o;
     }
   }
   PROF(e, kPGather);
 }
 
-// a whole segment at once, fenced both ways
+// a whole segment at once; __syncwarp orders it against this warp's own reads of the staging buffer
 template <int NCH>
 __device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0) {
-  PROF(e, kPOther);
-  pair_bar(e);  // the partner warp has finished reading the previous segment
-  PROF(e, kPBar);
-  gather_rows<NCH>(e, g, taps, ch0, 0, 16);
-  pair_bar(e);
-  PROF(e, kPBar);
+  __syncwarp();
+  gather_rows<NCH>(e, g, taps, ch0, 0, GatherShape<NCH>::kGroups);
+  __syncwarp();
 }
 
 // ----------------------------------------------------------------------------- trunk epilogues
@@ -299,8 +314,7 @@ __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom&
     // the next hoisted segment is gathered in two halves: one while the tensor pipe runs fc_0, one while it
     // runs fc_1 -- each half's load latency hides behind one MMA round trip
     if (k < 2) {
-      pair_bar(e);  // both warps of the row quarter have consumed segment k (the x update above)
-      PROF(e, kPBar);
+      __syncwarp();  // this warp has consumed segment k (the x update above)
       gather_rows<128>(e, g, taps, seg_ch0 + 128 * (k + 1), 0, 8);
     }
     PROF(e, kPEpi);
@@ -309,8 +323,7 @@ __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom&
     epi_publish(e);  // -> fc_1 (block k), accumulates onto x
     if (k < 2) {
       gather_rows<128>(e, g, taps, seg_ch0 + 128 * (k + 1), 8, 16);
-      pair_bar(e);  // segment k+1 complete and visible to the row's two threads
-      PROF(e, kPBar);
+      __syncwarp();  // segment k+1 complete: written and read by this warp only
     }
     PROF(e, kPEpi);
     epi_wait_acc(e);

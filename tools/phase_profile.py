@@ -22,13 +22,14 @@ def main():
     L.njf_prof_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    model = bench.build_model(dev)
-    sc = bench.scene(0, dev, rays_device=dev)
+    cfg = bench.CONFIGS["cfg3"]
+    model = bench.build_model(cfg, dev)
+    sc = bench.scene(cfg, 0, dev, rays_device=dev)
     with torch.no_grad():
         feat = model.encoder(sc["image"]).float().contiguous()
     fld = model.field()
     Hf, Wf = feat.shape[-2:]
-    R = bench.RENDER_H * bench.RENDER_W
+    R = cfg["H"] * cfg["W"]
     cams, keep = api.make_cameras(sc["ctxt_c2w"], sc["ctxt_k"], sc["trgt_c2w"], sc["trgt_k_px"], dev)
     maps = fld.hoist(feat)
     from njf_b200.render import render
@@ -40,7 +41,7 @@ def main():
         return list(buf)[:len(PH)]
 
     # full render once for warm-up, then reset
-    args = (fld, maps, Hf, Wf, cams, sc["origins"], sc["dirs"], sc["z_near"], sc["z_far"], sc["action"], bench.S_PROP, bench.S_NERF)
+    args = (fld, maps, Hf, Wf, cams, sc["origins"], sc["dirs"], sc["z_near"], sc["z_far"], sc["action"], cfg["s_prop"], cfg["s_nerf"])
     res = render(*args)
     read()
     out = {}
