@@ -131,40 +131,78 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
   } else {
     EpiCtx e = epi_ctx(c);
     SlotScratch* sc = slot_scratch(c, e.slot);
-    const int lane = threadIdx.x & 31;
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-      const int lgroup = one_slot ? it : 2 * it + e.slot;  // launch-local ray group
-      if (lgroup >= g.NG || (one_slot && e.slot)) continue;
-      const int group = g.group0 + lgroup;
-      for (int tile = 0; tile < g.T; ++tile) {
-        RowState rs;
-        PROF(e, kPOther);
-        row_setup(g, group, tile, e.row, rs);
-        PROF(e, kPPdf);
-        write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
-        PROF(e, kPHead);
+    // This slot's tiles form a software pipeline: while tile n runs blocks 2..4 (whose MMA wait windows carry no
+    // gather of tile n), the warp sets up tile n+1 (bins -> position -> projection -> taps) and prefetches ITS part
+    // of tile n+1's first hoisted segment into the staging buffer, which tile n stopped using after block 1.
+    int n_my = 0;  // tiles of this slot in this CTA
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x)
+      if ((one_slot ? it : 2 * it + e.slot) < g.NG && !(one_slot && e.slot)) n_my += g.T;
+    auto tile_of = [&](int n, int& group, int& tile) {
+      const int it = blockIdx.x + (n / g.T) * gridDim.x;
+      group = g.group0 + (one_slot ? it : 2 * it + e.slot);
+      tile = n - (n / g.T) * g.T;
+    };
+    RowState rs;
+    if (n_my > 0) {
+      int group, tile;
+      tile_of(0, group, tile);
+      PROF(e, kPOther);
+      row_setup(g, group, tile, e.row, rs);
+      PROF(e, kPPdf);
+      write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
+      PROF(e, kPHead);
+      write_posenc(e, rs.cam, rs.ray >= 0, g.debug);
+      PROF(e, kPColor);
+      epi_publish(e);  // -> lin_in
+      PROF(e, kPSetup);
+      gather_segment<128>(e, g, sc->taps, 0);
+    }
+    for (int n = 0; n < n_my; ++n) {
+      const bool has_next = n + 1 < n_my;
+      RowState nx;
+      nx.ray = -1; nx.s = 0; nx.delta = 0.f; nx.cam[0] = nx.cam[1] = nx.cam[2] = 0.f;
+      epi_wait_acc(e);  // lin_in
+      trunk_blocks_epilogue(e, g, 0, sc->taps, [&](int k, int w) {
+        if (!has_next) return;
+        if (k == 2 && w == 1) {
+          // every thread of the slot is past block 1 here (the fc_0(2) accumulator needed all 256 arrivals), so
+          // nobody reads tile n's tap table any more
+          int group, tile;
+          tile_of(n + 1, group, tile);
+          PROF(e, kPOther);
+          row_setup(g, group, tile, e.row, nx);
+          PROF(e, kPPdf);
+          write_taps(sc->taps, e.row, nx, g.Hf, g.Wf, g.CH);
+          PROF(e, kPHead);
+        } else if (k == 3 && w == 0) {
+          __syncwarp();
+          gather_rows<128>(e, g, sc->taps, 0, 0, 8);
+        } else if (k == 3 && w == 1) {
+          gather_rows<128>(e, g, sc->taps, 0, 8, 16);
+          __syncwarp();
+        }
+      });
+      epi_wait_acc(e);  // lin_out accumulator ready
+      float dd = 0.f;
+      if (e.half == 0) {
+        uint32_t r[16];
+        tmem_ld16(e.tmem + 128, r);
+        tmem_ld_wait();
+        // density = trunc_exp(x - 1) (density_decoder.py:64-66, activations.py:32-35)
+        const float sigma = expf(__fsub_rn(__uint_as_float(r[0]), 1.f));
+        dd = (rs.ray >= 0 && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
+      }
+      // delta*sigma goes out; the per-ray kernel that follows does the transmittance scan
+      // (RaySamples.get_weights) and the PDF resampling with one warp per ray
+      if (e.half == 0 && rs.ray >= 0) p.weights_out[static_cast<size_t>(rs.ray - p.w_ray0) * g.S + rs.s] = dd;
+      PROF(e, kPWeights);
+      if (has_next) {
+        rs = nx;
+        tc_fence_before();  // this thread's TMEM reads of tile n are done before lin_in of tile n+1 overwrites x
         write_posenc(e, rs.cam, rs.ray >= 0, g.debug);
         PROF(e, kPColor);
-        epi_publish(e);  // -> lin_in
-        __syncwarp();
+        epi_publish(e);  // -> lin_in of tile n+1 (its first segment is already staged)
         PROF(e, kPSetup);
-        gather_segment<128>(e, g, sc->taps, 0);
-        epi_wait_acc(e);
-        trunk_blocks_epilogue(e, g, 0, sc->taps);
-        epi_wait_acc(e);  // lin_out accumulator ready
-        float dd = 0.f;
-        if (e.half == 0) {
-          uint32_t r[16];
-          tmem_ld16(e.tmem + 128, r);
-          tmem_ld_wait();
-          // density = trunc_exp(x - 1) (density_decoder.py:64-66, activations.py:32-35)
-          const float sigma = expf(__fsub_rn(__uint_as_float(r[0]), 1.f));
-          dd = (rs.ray >= 0 && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
-        }
-        // delta*sigma goes out; the per-ray kernel that follows does the transmittance scan
-        // (RaySamples.get_weights) and the PDF resampling with one warp per ray
-        if (e.half == 0 && rs.ray >= 0) p.weights_out[static_cast<size_t>(rs.ray - p.w_ray0) * g.S + rs.s] = dd;
-        PROF(e, kPWeights);
       }
     }
     prof_flush(e);
@@ -290,36 +328,82 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
     const int lane = threadIdx.x & 31;
     const int A3 = 3 * p.A;
     const int nch = 8 + A3;  // composite channels: rgb3, t, 1, pos3, J(3A)
-    // e.tz doubles as the composite staging buffer: [128 rows][64 fp32], 16 B chunks XOR-swizzled by row
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
-      const int lgroup = 2 * it + e.slot;  // launch-local ray group
-      if (lgroup >= g.NG) continue;
-      const int group = g.group0 + lgroup;
-      double carry = 0.0;
-      float cs0 = 0.f, cs1 = 0.f;  // column sums held by warp 0 of the slot across the tiles of a long ray
-      for (int tile = 0; tile < g.T; ++tile) {
-        RowState rs;
-        PROF(e, kPOther);
-        row_setup(g, group, tile, e.row, rs);
+    // The slot's tiles form a software pipeline (like proposal_kernel): during blocks 2..4 of the LAST trunk of
+    // tile n the warp sets up tile n+1 (row set-up, tap table) and prefetches its part of tile n+1's first hoisted
+    // segment (the 64 query channels for the cross-attention head, segment 0 for the MLP head) into the staging
+    // buffer.  The composite therefore stages its rows in the A tile (idle after the tile's last MMA), not in e.tz.
+    const bool xf_head = p.head_kind == NJF_HEAD_TRANSFORMER;
+    int n_my = 0;  // tiles of this slot in this CTA
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x)
+      if (2 * it + e.slot < g.NG) n_my += g.T;
+    auto tile_of = [&](int n, int& lgroup, int& tile) {
+      const int it = blockIdx.x + (n / g.T) * gridDim.x;
+      lgroup = 2 * it + e.slot;  // launch-local ray group
+      tile = n - (n / g.T) * g.T;
+    };
+    RowState rs;
+    if (n_my > 0) {
+      int lgroup, tile;
+      tile_of(0, lgroup, tile);
+      PROF(e, kPOther);
+      row_setup(g, g.group0 + lgroup, tile, e.row, rs);
+      write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
+      write_posenc(e, rs.cam, rs.ray >= 0, g.debug);
+      epi_publish(e);  // -> lin_in (+ q_enc for the transformer head)
+      PROF(e, kPSetup);
+      if (xf_head) gather_segment<64>(e, g, sc->taps, 384);
+      else gather_segment<128>(e, g, sc->taps, 0);
+    }
+    double carry = 0.0;
+    float cs0 = 0.f, cs1 = 0.f;  // column sums held by warp 0 of the slot across the tiles of a long ray
+    for (int n = 0; n < n_my; ++n) {
+      {
+        int lgroup, tile;
+        tile_of(n, lgroup, tile);
+        const int group = g.group0 + lgroup;
+        if (tile == 0) {
+          carry = 0.0;
+          cs0 = cs1 = 0.f;
+        }
+        const bool has_next = n + 1 < n_my;
+        RowState nx;
+        nx.ray = -1; nx.s = 0; nx.tmid = 0.f; nx.delta = 0.f;
+        nx.pos[0] = nx.pos[1] = nx.pos[2] = 0.f;
+        nx.cam[0] = nx.cam[1] = nx.cam[2] = 0.f;
+        // set-up of tile n+1 in an MMA wait window of the last trunk's block 2: every thread of the slot is past
+        // block 1 of that trunk then, so nobody reads tile n's tap table any more
+        auto setup_next = [&]() {
+          int lg2, t2;
+          tile_of(n + 1, lg2, t2);
+          PROF(e, kPOther);
+          row_setup(g, g.group0 + lg2, t2, e.row, nx);
+          write_taps(sc->taps, e.row, nx, g.Hf, g.Wf, g.CH);
+          PROF(e, kPSetup);
+        };
         const bool valid = rs.ray >= 0;
         float J[16];  // this thread's 16 of the 32 (padded) Jacobian columns: 16h .. 16h+15 (MLP head)
 #pragma unroll
         for (int j = 0; j < 16; ++j) J[j] = 0.f;
-        write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
-        write_posenc(e, rs.cam, valid, g.debug);
-        epi_publish(e);  // -> lin_in (+ q_enc for the transformer head)
-        __syncwarp();
-        PROF(e, kPSetup);
         const size_t tidx = static_cast<size_t>(lgroup) * g.T + tile;
-        if (p.head_kind == NJF_HEAD_TRANSFORMER) {
-          gather_segment<64>(e, g, sc->taps, 384);
-          epi_wait_acc(e);
+        if (xf_head) {
+          epi_wait_acc(e);  // lin_in + q_enc; the query channels were gathered by the prologue / the previous tile
           if (p.qs) store_query_stream(e, p.qs + tidx * 8 * kRows);
           PROF(e, kPHead);
+          gather_segment<128>(e, g, sc->taps, 0);
+          trunk_blocks_epilogue(e, g, 0, sc->taps, [&](int k, int w) {
+            if (!has_next) return;
+            if (k == 2 && w == 1) {
+              setup_next();
+            } else if (k == 3 && w == 0) {
+              __syncwarp();
+              gather_rows<64>(e, g, sc->taps, 384, 0, GatherShape<64>::kGroups);
+              __syncwarp();
+            }
+          });
+        } else {
+          epi_wait_acc(e);  // lin_in; segment 0 was gathered by the prologue / the previous tile
+          trunk_blocks_epilogue(e, g, 0, sc->taps);  // (the tap table is still needed by the Jacobian trunk)
         }
-        gather_segment<128>(e, g, sc->taps, 0);
-        if (p.head_kind != NJF_HEAD_TRANSFORMER) epi_wait_acc(e);
-        trunk_blocks_epilogue(e, g, 0, sc->taps);
         // lin_out: 15 geometry features + density pre-activation (action_decoder_jacobian.py:106-112); colour head
         // input [geo15 | sh16 | 0...] (:208).  The h=0 thread handles the geometry half (columns 0..15: geo, sh0),
         // the h=1 thread the view direction (columns 16..31: sh1..15, 0) -- its loads are issued before the wait.
@@ -393,7 +477,18 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           epi_publish(e);  // -> lin_in (jacobian head)
           gather_segment<128>(e, g, sc->taps, 384);
           epi_wait_acc(e);
-          trunk_blocks_epilogue(e, g, 384, sc->taps);
+          trunk_blocks_epilogue(e, g, 384, sc->taps, [&](int k, int w) {
+            if (!has_next) return;
+            if (k == 2 && w == 1) {
+              setup_next();
+            } else if (k == 3 && w == 0) {
+              __syncwarp();
+              gather_rows<128>(e, g, sc->taps, 0, 0, 8);
+            } else if (k == 3 && w == 1) {
+              gather_rows<128>(e, g, sc->taps, 0, 8, 16);
+              __syncwarp();
+            }
+          });
           epi_wait_acc(e);
           uint32_t r[16];
           tmem_ld16(e.tmem + 128 + 16 * e.half, r);
@@ -405,7 +500,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         const float dd = (valid && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
         const float w = tile_weights(e, sc, g, tile, dd, carry);
         const float ww = valid ? w : 0.f;
-        uint8_t* rowp = e.tz + e.row * 256;
+        // composite staging: [128 rows][64 fp32] in the slot's A tile (32 KB), 16 B chunks XOR-swizzled by row; the
+        // tile's last MMA has completed, and the staging buffer e.tz may already hold tile n+1's prefetched segment
+        uint8_t* rowp = e.a_tile + e.row * 256;
         const bool stage_j = p.jbar != nullptr;  // MLP head: J composited here; transformer: by xf_kernel
         if (e.half == 0) {
           if (p.wts) __stcs(p.wts + tidx * kRows + e.row, ww);
@@ -473,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         slot_bar(e);
         auto colsum = [&](int r0, int n, float& s0, float& s1) {
           for (int r = r0; r < r0 + n; ++r) {
-            const uint8_t* rp = e.tz + r * 256;
+            const uint8_t* rp = e.a_tile + r * 256;
             if (stage_j || lane < 8)
               s0 += *reinterpret_cast<const float*>(rp + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
             if (stage_j && nch > 32)
@@ -529,6 +626,12 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           slot_bar(e);
         }
         PROF(e, kPComposite);
+        if (has_next) {   // tile n+1: its rows are set up, its first segment is staged; the A tile is free again
+          rs = nx;
+          write_posenc(e, rs.cam, rs.ray >= 0, g.debug);
+          epi_publish(e);  // -> lin_in (+ q_enc) of tile n+1
+          PROF(e, kPSetup);
+        }
       }
     }
     prof_flush(e);

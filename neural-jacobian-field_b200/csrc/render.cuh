@@ -305,7 +305,15 @@ __device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, con
 // lin_in's accumulator wait has completed (x = W_in . [enc | xyz] + b_in in TMEM) and segment 0 of this
 // trunk's hoisted channels is in the staging buffer.  Ends with lin_out issued: after the caller's
 // epi_wait_acc its accumulator (bias included) is in TMEM columns [128, 128+n_out).
-__device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom& g, int seg_ch0, const TapEntry* taps) {
+// `hook(k, w)` is called in the MMA wait windows of blocks 2..4 (w = 0: fc_0 is running, w = 1: fc_1 is running),
+// which carry no gather of this tile: the kernels use them to set up the NEXT tile of the slot and to prefetch its
+// first hoisted segment, so that neither sits on the next tile's critical path.
+struct NoHook {
+  __device__ __forceinline__ void operator()(int, int) const {}
+};
+template <class Hook = NoHook>
+__device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom& g, int seg_ch0, const TapEntry* taps,
+                                                      Hook hook = Hook()) {
   // E0: X_0 = lin_in(enc, xyz) + b_in + tz_0
   for (int c0 = e.col0; c0 < e.col0 + 64; c0 += 32) epi_x_update<true>(e, c0);
   epi_publish(e);  // -> fc_0 (block 0)
@@ -316,6 +324,8 @@ __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom&
     if (k < 2) {
       __syncwarp();  // this warp has consumed segment k (the x update above)
       gather_rows<128>(e, g, taps, seg_ch0 + 128 * (k + 1), 0, 8);
+    } else {
+      hook(k, 0);
     }
     PROF(e, kPEpi);
     epi_wait_acc(e);
@@ -324,6 +334,8 @@ __device__ __forceinline__ void trunk_blocks_epilogue(EpiCtx& e, const PassGeom&
     if (k < 2) {
       gather_rows<128>(e, g, taps, seg_ch0 + 128 * (k + 1), 8, 16);
       __syncwarp();  // segment k+1 complete: written and read by this warp only
+    } else {
+      hook(k, 1);
     }
     PROF(e, kPEpi);
     epi_wait_acc(e);
