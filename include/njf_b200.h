@@ -173,11 +173,19 @@ int njf_field_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArg
                    int bins_stride, void* stream);
 int njf_finish_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* args, void* stream);
 
-/* ---- Model.compute_density (models/model.py:416-456): density head + Jacobian head at explicit
- * world-space points (no rays).  points [B][N][3]; sigma [B][N], geo [B][N][15], jac [B][N][3A]. */
+/* ---- Model.compute_density (models/model.py:416-456) and the decoder plugin surface
+ * ActionDecoderJacobian.forward / encode_image / compute_density (action_decoder_jacobian.py:92-249): density head,
+ * Jacobian head and colour head at explicit world-space points (no rays).  points [B][N][3]; dirs [B][N][3] unit
+ * view directions (NULL unless rgb is wanted); sigma [B][N], geo [B][N][15], jac [B][N][3A], rgb [B][N][3]; any
+ * output may be NULL. */
 int njf_query_points(const NjfField* f, const float* ctxt_w2c, const float* ctxt_k, const void* maps, int Hf,
-                     int Wf, const float* points, int B, int N, float* sigma, float* geo, float* jac,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     int Wf, const float* points, const float* dirs, int B, int N, float* sigma, float* geo,
+                     float* jac, float* rgb, void* workspace, size_t workspace_bytes, void* stream);
+/* DensityDecoderMlp.get_density (models/decoder/density_decoder.py:45-71) of proposal network `level` at explicit
+ * points: sigma [B][N] */
+int njf_query_proposal_density(const NjfField* f, int level, const float* ctxt_w2c, const float* ctxt_k,
+                               const void* maps, int Hf, int Wf, const float* points, int B, int N, float* sigma,
+                               void* stream);
 /* workspace for njf_query_points (cross-attention head hand-over; 0 for the MLP head) */
 size_t njf_query_workspace_bytes(const NjfField* f, int B, int N);
 /* by-products returned by the reference's DensityHeadOutput: positional encoding (63) of the

@@ -106,6 +106,7 @@ struct ProposalParams {
                          // seven wait); row 0 belongs to ray `w_ray0`
   int w_ray0;
   int32_t* inds_out;     // optional [NR][n_out+1]
+  float* sigma_out;      // point-query mode (DensityDecoderMlp.get_density at explicit points): [NR] densities
 };
 
 __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_constant__ ProposalParams p) {
@@ -183,18 +184,22 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
         }
       });
       epi_wait_acc(e);  // lin_out accumulator ready
-      float dd = 0.f;
+      float dd = 0.f, sigma_pt = 0.f;
       if (e.half == 0) {
         uint32_t r[16];
         tmem_ld16(e.tmem + 128, r);
         tmem_ld_wait();
         // density = trunc_exp(x - 1) (density_decoder.py:64-66, activations.py:32-35)
         const float sigma = expf(__fsub_rn(__uint_as_float(r[0]), 1.f));
+        sigma_pt = sigma;
         dd = (rs.ray >= 0 && rs.delta > 0.f) ? __fmul_rn(rs.delta, sigma) : 0.f;
       }
       // delta*sigma goes out; the per-ray kernel that follows does the transmittance scan
       // (RaySamples.get_weights) and the PDF resampling with one warp per ray
-      if (e.half == 0 && rs.ray >= 0) p.weights_out[static_cast<size_t>(rs.ray - p.w_ray0) * g.S + rs.s] = dd;
+      if (e.half == 0 && rs.ray >= 0) {
+        if (p.sigma_out) p.sigma_out[rs.ray] = sigma_pt;
+        else p.weights_out[static_cast<size_t>(rs.ray - p.w_ray0) * g.S + rs.s] = dd;
+      }
       PROF(e, kPWeights);
       if (has_next) {
         rs = nx;
@@ -1311,8 +1316,9 @@ extern "C" int njf_field_pass(const NjfField* f, const NjfCameras* cams, const N
 }
 
 extern "C" int njf_query_points(const NjfField* f, const float* ctxt_w2c, const float* ctxt_k, const void* maps,
-                                int Hf, int Wf, const float* points, int B, int N, float* sigma, float* geo,
-                                float* jac, void* workspace, size_t workspace_bytes, void* stream_) {
+                                int Hf, int Wf, const float* points, const float* dirs, int B, int N, float* sigma,
+                                float* geo, float* jac, float* rgb, void* workspace, size_t workspace_bytes,
+                                void* stream_) {
   if (!f || !ctxt_w2c || !ctxt_k || !maps || !points) NJF_FAIL("njf_query_points: null argument");
   if (B < 1 || N < 1) NJF_FAIL("njf_query_points: B=%d N=%d", B, N);
   if (static_cast<size_t>(B) * Hf * Wf * 768 * 2 >= (1ull << 32)) NJF_FAIL("njf_query_points: maps too large");
@@ -1330,12 +1336,46 @@ extern "C" int njf_query_points(const NjfField* f, const float* ctxt_w2c, const 
   g.map = static_cast<const __half*>(maps) + px * f->ch_prop * f->desc.n_proposal;
   g.CH = f->ch_main; g.Hf = Hf; g.Wf = Wf;
   g.points = points;
+  g.dirs = dirs;  // per point (point i plays the role of "ray" i); NULL: the colour head sees direction (0,0,1)
+  if (rgb && !dirs) NJF_FAIL("njf_query_points: rgb output needs per-point view directions");
   p.head_kind = f->desc.head;
   p.A = f->desc.action_dim;
+  p.sh_conv = f->desc.sh_convention;
   p.sigma = sigma;
   p.geo_out = geo;
   p.jac_out = jac;
+  p.rgb_samples = rgb;
   return launch_field(f, p, workspace, workspace_bytes, stream);
+}
+
+extern "C" int njf_query_proposal_density(const NjfField* f, int level, const float* ctxt_w2c, const float* ctxt_k,
+                                          const void* maps, int Hf, int Wf, const float* points, int B, int N,
+                                          float* sigma, void* stream_) {
+  if (!f || !ctxt_w2c || !ctxt_k || !maps || !points || !sigma) NJF_FAIL("njf_query_proposal_density: null argument");
+  if (level < 0 || level >= f->desc.n_proposal) NJF_FAIL("njf_query_proposal_density: level %d out of range", level);
+  if (B < 1 || N < 1) NJF_FAIL("njf_query_proposal_density: B=%d N=%d", B, N);
+  if (static_cast<size_t>(B) * Hf * Wf * 768 * 2 >= (1ull << 32)) NJF_FAIL("njf_query_proposal_density: maps too large");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ProposalParams p{};
+  p.prog = f->prop_prog[level];
+  p.blob = f->prop_blob[level];
+  PassGeom& g = p.g;
+  g.NR = B * N; g.R = N; g.S = 1; g.G = kRows; g.T = 1;
+  g.NG = (g.NR + g.G - 1) / g.G;
+  g.ctxt_w2c = ctxt_w2c;
+  g.ctxt_k = ctxt_k;
+  const size_t px = static_cast<size_t>(B) * Hf * Wf;
+  g.map = static_cast<const __half*>(maps) + px * f->ch_prop * level;
+  g.CH = f->ch_prop; g.Hf = Hf; g.Wf = Wf;
+  g.points = points;
+  p.sigma_out = sigma;
+  if (set_smem(proposal_kernel)) return 1;
+  const int nitems = (g.NG + 1) / 2;
+  const int grid = nitems < num_sms() ? nitems : num_sms();
+  proposal_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+  njf::count_launch();
+  NJF_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int njf_point_features(const float* feat_nchw, const float* ctxt_w2c, const float* ctxt_k,

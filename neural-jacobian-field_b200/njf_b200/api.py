@@ -78,8 +78,11 @@ def _declare():
     L.njf_field_pass.restype = c_int
     L.njf_field_pass.argtypes = [c_void_p, POINTER(NjfCameras), POINTER(NjfRenderArgs), c_void_p, c_int, c_void_p]
     L.njf_query_points.restype = c_int
-    L.njf_query_points.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
-                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.njf_query_points.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.njf_query_proposal_density.restype = c_int
+    L.njf_query_proposal_density.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                             c_int, c_void_p, c_void_p]
     L.njf_query_workspace_bytes.restype = c_size_t
     L.njf_query_workspace_bytes.argtypes = [c_void_p, c_int, c_int]
     L.njf_workspace_bytes.restype = c_size_t
@@ -251,18 +254,31 @@ def make_cameras(ctxt_c2w, ctxt_k, trgt_c2w, trgt_k_px, device):
     return cams, (cw, ck, tw, tk, cw_h, ck_h)
 
 
-def query_points(fld: "Field", w2c, k_norm, maps, Hf, Wf, points, want_jac=True):
-    """njf_query_points: density head (+ Jacobian head) at explicit world points (B,N,3)."""
+def query_points(fld: "Field", w2c, k_norm, maps, Hf, Wf, points, want_jac=True, dirs=None):
+    """njf_query_points: density head (+ Jacobian head, + colour head when view directions are given) at explicit
+    world points (B,N,3).  Returns (sigma, geo, jac) or, with ``dirs``, (sigma, geo, jac, rgb)."""
     L = _declare()
     B, N = points.shape[:2]
     A = fld.action_dim
     o = dict(device=points.device, dtype=torch.float32)
     sigma, geo = torch.empty(B, N, 1, **o), torch.empty(B, N, 15, **o)
     jac = torch.empty(B, N, 3 * A, **o) if want_jac else None
+    rgb = torch.empty(B, N, 3, **o) if dirs is not None else None
     ws = fld.workspace(int(L.njf_query_workspace_bytes(fld.handle, B, N)))
-    _lib.check(L.njf_query_points(fld.handle, dptr(w2c), dptr(k_norm), dptr(maps), int(Hf), int(Wf), dptr(points), B, N,
-                                  dptr(sigma), dptr(geo), dptr(jac), ws.data_ptr(), ws.numel(), stream_ptr()))
-    return sigma, geo, jac
+    _lib.check(L.njf_query_points(fld.handle, dptr(w2c), dptr(k_norm), dptr(maps), int(Hf), int(Wf), dptr(points),
+                                  dptr(dirs), B, N, dptr(sigma), dptr(geo), dptr(jac), dptr(rgb), ws.data_ptr(), ws.numel(),
+                                  stream_ptr()))
+    return (sigma, geo, jac) if dirs is None else (sigma, geo, jac, rgb)
+
+
+def query_proposal_density(fld: "Field", level, w2c, k_norm, maps, Hf, Wf, points):
+    """njf_query_proposal_density: proposal network ``level`` at explicit world points (B,N,3) -> (B,N,1)."""
+    L = _declare()
+    B, N = points.shape[:2]
+    sigma = torch.empty(B, N, 1, device=points.device, dtype=torch.float32)
+    _lib.check(L.njf_query_proposal_density(fld.handle, int(level), dptr(w2c), dptr(k_norm), dptr(maps), int(Hf), int(Wf),
+                                            dptr(points), B, N, dptr(sigma), stream_ptr()))
+    return sigma
 
 
 def eval_tables(s_prop: Sequence[int], s_nerf: int, device):

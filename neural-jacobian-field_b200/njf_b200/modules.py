@@ -80,6 +80,84 @@ def _check_mlp(cfg: MlpCfg, who: str) -> None:
             f"(n_blocks=5, d_hidden=128, combine_layer=3, beta=0); got {cfg}")
 
 
+# ----------------------------------------------------------------------------- decoder-level plugin surface
+@dataclass
+class DecoderOutput:  # models/decoder/action_decoder.py:19-24
+    density: torch.Tensor
+    color: torch.Tensor
+    flow: torch.Tensor
+    action_features: torch.Tensor
+
+
+@dataclass
+class DecoderFeatureOnlyOutput:  # action_decoder.py:27-30
+    density: torch.Tensor
+    action_features: torch.Tensor
+
+
+@dataclass
+class DensityHeadOutput:  # action_decoder_jacobian.py:63-68
+    density: torch.Tensor
+    density_features: torch.Tensor
+    xyz_features: torch.Tensor
+    pixel_aligned_features: torch.Tensor
+
+
+class _StandaloneKernels:
+    """What lets a B200 decoder object stand in for the reference's OWN decoder inside the reference's OWN ``Model``
+    (registered under the reference's DENSITY_DECODERS / ACTION_DECODERS by ``njf_b200.plugin``): the per-point
+    methods the reference calls -- ``get_density`` (density_decoder.py:45-71), ``forward`` / ``encode_image`` /
+    ``compute_density`` (action_decoder_jacobian.py:92-249) -- evaluated by the fused point-query kernels
+    (njf_query_points / njf_query_proposal_density).  Inference only: the reference's sampler, PDF resampling and
+    compositing stay in its torch code, so this path is for drop-in compatibility, not speed; ``njf_b200.Model``
+    is the fused path."""
+
+    _sk_field = None
+    _sk_key = None
+    _sk_maps = None
+    _sk_maps_key = None
+
+    def _sk_parts(self):  # -> (head, action_dim, {field key: tensor})  implemented by the two decoder kinds
+        raise NotImplementedError
+
+    def _sk_get_field(self):
+        from . import api, synth
+
+        params = list(self.parameters())
+        if not params or params[0].device.type != "cuda":
+            from ._lib import NjfError
+            raise NjfError("the B200 decoders run on a CUDA device only (there is no CPU fallback)")
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._sk_field is None or self._sk_key != key:
+            head, A, mine = self._sk_parts()
+            weights = {}
+            for k, shp in synth.field_shapes(head, A, n_proposal=1).items():   # parts this module does not own: zeros
+                weights[k] = mine[k].detach() if k in mine else torch.zeros(shp)
+            with torch.cuda.device(params[0].device):
+                self._sk_field = api.Field(head, A, 1, weights)
+            self._sk_key, self._sk_maps_key = key, None
+        return self._sk_field
+
+    def _sk_context(self, pixel_encoding):
+        """(field, hoisted maps, w2c, K, Hf, Wf) for a reference-style PixelEncoding (features, extrinsics, intrinsics)."""
+        from . import api
+
+        fld = self._sk_get_field()
+        feats = pixel_encoding.features
+        mkey = (feats.data_ptr(), feats._version, tuple(feats.shape))
+        if self._sk_maps_key != mkey:
+            self._sk_maps = fld.hoist(feats.detach().to(fld.device, torch.float32).contiguous())
+            self._sk_maps_key = mkey
+        cams, keep = api.make_cameras(pixel_encoding.extrinsics.to(fld.device), pixel_encoding.intrinsics.to(fld.device),
+                                      None, None, fld.device)
+        return fld, self._sk_maps, keep[0], keep[1], feats.shape[-2], feats.shape[-1]
+
+    def _sk_check_inference(self):
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("the decoder-level B200 plugin is inference-only; train through njf_b200.Model "
+                                      "(action phase) -- see INTEGRATION.md")
+
+
 # ----------------------------------------------------------------------------- containers
 class ResnetBlockParams(nn.Module):
     def __init__(self, d: int):
@@ -152,7 +230,7 @@ def _color_head(geo: int) -> nn.Sequential:
                          nn.Sigmoid())
 
 
-class DensityDecoderMlp(nn.Module):
+class DensityDecoderMlp(nn.Module, _StandaloneKernels):
     """Proposal-network density field (models/decoder/density_decoder.py:23-43)."""
 
     def __init__(self, cfg: DensityDecoderMlpCfg, encoder_dim: int):
@@ -163,12 +241,96 @@ class DensityDecoderMlp(nn.Module):
         self.cfg = cfg
         self.density_head = ResnetFCParams(cfg.mlp, 63, encoder_dim, 1)
 
+    def _sk_parts(self):
+        return "jacobian_mlp", 1, {"proposal_networks.0." + k: v for k, v in self.state_dict().items()}
 
-class ActionDecoderJacobian(nn.Module):
+    def get_density(self, world_space_xyz: torch.Tensor, pixel_encoding) -> torch.Tensor:
+        """density_decoder.py:45-71: (batch, ray, sample, 3) world points -> (batch, ray, sample, 1) densities."""
+        from . import api
+
+        self._sk_check_inference()
+        fld, maps, w2c, kn, Hf, Wf = self._sk_context(pixel_encoding)
+        B, R, S = world_space_xyz.shape[:3]
+        pts = world_space_xyz.detach().to(fld.device, torch.float32).reshape(B, R * S, 3).contiguous()
+        with torch.cuda.device(fld.device):
+            sigma = api.query_proposal_density(fld, 0, w2c, kn, maps, Hf, Wf, pts)
+        return sigma.reshape(B, R, S, 1).to(world_space_xyz.device)
+
+
+class ActionDecoderJacobian(nn.Module, _StandaloneKernels):
     """Common surface of the two Jacobian decoders (action_decoder_jacobian.py:86-258)."""
 
     spatial_dim: int = 3
     action_param_glob_pattern = "jacobian"
+
+    def _sk_parts(self):
+        arm = getattr(self, "mode", "regular") == "arm"
+        sd = {}
+        for k, v in self.state_dict().items():
+            if arm:
+                if k.startswith("jacobian_head_arm."):
+                    sd["decoder.jacobian_head." + k[len("jacobian_head_arm."):]] = v
+                elif "jacobian" not in k:
+                    sd["decoder." + k] = v
+            elif "jacobian_head_arm" not in k:
+                sd["decoder." + k] = v
+        if arm:
+            return "jacobian_mlp", int(self.cfg.arm_action_dim), sd
+        return self.cfg.name, int(self.action_dim), sd
+
+    def _sk_get_field(self):   # the decoder's mode is part of what is packed
+        if getattr(self, "_sk_mode", None) != getattr(self, "mode", "regular"):
+            self._sk_field, self._sk_mode = None, getattr(self, "mode", "regular")
+        return super()._sk_get_field()
+
+    def _sk_query(self, xyz_flat: torch.Tensor, dirs_flat, pixel_encoding):
+        from . import api
+
+        self._sk_check_inference()
+        fld, maps, w2c, kn, Hf, Wf = self._sk_context(pixel_encoding)
+        pts = xyz_flat.detach().to(fld.device, torch.float32).contiguous()
+        dirs = None if dirs_flat is None else dirs_flat.detach().to(fld.device, torch.float32).contiguous()
+        with torch.cuda.device(fld.device):
+            return api.query_points(fld, w2c, kn, maps, Hf, Wf, pts, dirs=dirs), (fld, w2c, kn, Hf, Wf, pts)
+
+    def compute_density(self, world_space_xyz: torch.Tensor, pixel_encoding) -> DensityHeadOutput:
+        """action_decoder_jacobian.py:92-119 at (batch, n, 3) world points."""
+        from . import _lib, api
+
+        out, (fld, w2c, kn, Hf, Wf, pts) = self._sk_query(world_space_xyz, None, pixel_encoding)
+        sigma, geo = out[0], out[1]
+        B, N = pts.shape[:2]
+        feats = pixel_encoding.features.detach().to(fld.device, torch.float32).contiguous()
+        C = feats.shape[1]
+        xyzf = torch.empty(B, N, 63, device=fld.device)
+        pixf = torch.empty(B, N, C, device=fld.device)
+        L = api._declare()
+        with torch.cuda.device(fld.device):
+            _lib.check(L.njf_point_features(api.dptr(feats), api.dptr(w2c), api.dptr(kn), api.dptr(pts), B, N, C, Hf, Wf,
+                                            api.dptr(xyzf), api.dptr(pixf), api.stream_ptr()))
+        dev = world_space_xyz.device
+        return DensityHeadOutput(density=sigma.to(dev), density_features=geo.to(dev), xyz_features=xyzf.to(dev),
+                                 pixel_aligned_features=pixf.to(dev))
+
+    def forward(self, world_space_xyz: torch.Tensor, world_space_dir: torch.Tensor, pixel_encoding) -> DecoderOutput:
+        """action_decoder_jacobian.py:147-215: density, colour, J and flow = J u at (batch, ray, sample, 3) points."""
+        B, R, S = world_space_xyz.shape[:3]
+        (sigma, geo, jac, rgb), (fld, *_rest) = self._sk_query(world_space_xyz.reshape(B, R * S, 3),
+                                                               world_space_dir.reshape(B, R * S, 3), pixel_encoding)
+        A = fld.action_dim
+        action = pixel_encoding.action.detach().to(fld.device, torch.float32)
+        flow = torch.einsum("bnad,ba->bnd", jac.reshape(B, R * S, A, 3), action)   # :135-143 (tiny, per call)
+        dev = world_space_xyz.device
+        r = lambda t: t.reshape(B, R, S, -1).to(dev)
+        return DecoderOutput(density=r(sigma), color=r(rgb), flow=r(flow), action_features=r(jac))
+
+    def encode_image(self, world_space_xyz: torch.Tensor, pixel_encoding) -> DecoderFeatureOnlyOutput:
+        """action_decoder_jacobian.py:217-249."""
+        B, R, S = world_space_xyz.shape[:3]
+        (sigma, geo, jac), _ = self._sk_query(world_space_xyz.reshape(B, R * S, 3), None, pixel_encoding)
+        dev = world_space_xyz.device
+        return DecoderFeatureOnlyOutput(density=sigma.reshape(B, R, S, 1).to(dev),
+                                        action_features=jac.reshape(B, R, S, -1).to(dev))
 
     def switch_mode(self, mode: Literal["regular", "arm"]):
         """action_decoder_jacobian.py:89-90.  "arm" renders with ``jacobian_head_arm`` (a ResnetFC Jacobian head of

@@ -156,3 +156,54 @@ def test_training_mode_is_rejected_loudly():
     with pytest.raises(NotImplementedError):
         m.forward(CameraInput(sc["img"], sc["ctxt"], sc["K"], sc["trgt"], sc["kpx"]),
                   RenderingInput(sc["o"], sc["d"], sc["zn"], sc["zf"]), RobotInput(sc["act"]))
+
+
+@pytest.mark.parametrize("head,A", [("jacobian_transformer", 8), ("jacobian_mlp", 6)])
+def test_decoder_level_plugin_methods(head, A):
+    """The per-point methods the reference's own Model calls on registry-built decoders (njf_b200.plugin):
+    DensityDecoderMlp.get_density, ActionDecoderJacobian.forward / encode_image / compute_density, stand-alone modules
+    with their own packed field, against the oracle's per-point formulation."""
+    from types import SimpleNamespace
+
+    from njf_b200 import modules as mod
+
+    mlp = mod.MlpCfg()
+    dcfg = (mod.ActionDecoderJacobianTransformerCfg(name=head, mlp=mlp, transformer=mod.TransformerCfg())
+            if head == "jacobian_transformer" else mod.ActionDecoderJacobianMlpCfg(name=head, mlp=mlp))
+    dec = mod.get_action_decoder(dcfg, action_dim=A, encoder_dim=512)
+    prop = mod.get_density_decoder(mod.DensityDecoderMlpCfg("density_mlp", mlp), encoder_dim=512)
+    w = synth.synth_state_dict(synth.field_shapes(head, A), 31)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in w.items() if k.startswith("decoder.")})
+    prop.load_state_dict({k[len("proposal_networks.0."):]: v for k, v in w.items() if k.startswith("proposal_networks.0.")})
+    dec, prop = dec.to(DEV).eval(), prop.to(DEV).eval()
+    g = torch.Generator().manual_seed(12)
+    B, R, S = 2, 9, 7
+    feat = torch.randn(B, 512, 12, 16, generator=g).abs() * 0.7
+    K = synth.normalized_intrinsics(**synth.ALLEGRO_INTRINSICS_PX)[None].repeat(B, 1, 1)
+    ctxt = torch.eye(4)[None].repeat(B, 1, 1)
+    xyz = torch.rand(B, R, S, 3, generator=g) * torch.tensor([1.0, 0.8, 2.0]) + torch.tensor([-0.5, -0.4, 0.6])
+    dirs = torch.nn.functional.normalize(torch.randn(B, R, S, 3, generator=g), dim=-1)
+    act = 0.1 * torch.randn(B, A, generator=g)
+    pe = SimpleNamespace(features=feat.to(DEV), extrinsics=ctxt.to(DEV), intrinsics=K.to(DEV), action=act.to(DEV))
+    spec = O.FieldSpec(head, A)
+    with torch.no_grad():
+        out = dec.forward(xyz.to(DEV), dirs.to(DEV), pe)
+        enc = dec.encode_image(xyz.to(DEV), pe)
+        dho = dec.compute_density(xyz.reshape(B, R * S, 3).to(DEV), pe)
+        sig_p = prop.get_density(xyz.to(DEV), pe)
+        sig, geo, jac, z, encf = O.field_heads(w, xyz.reshape(B, R * S, 3), feat, ctxt, K, spec)
+        rgb = O.color_head(w, geo, O.sh4((dirs.reshape(B, R * S, 3) + 1.0) / 2.0))
+        flow = torch.einsum("bnad,ba->bnd", jac.reshape(B, R * S, A, 3), act)
+        sig_prop = O.proposal_density(w, 0, xyz.reshape(B, R * S, 3), feat, ctxt, K, spec)
+    c = lambda t: t.reshape(B, R * S, -1).cpu().numpy()
+    assert out.density.shape == (B, R, S, 1) and out.action_features.shape == (B, R, S, 3 * A)
+    np.testing.assert_allclose(c(out.density), sig.numpy(), rtol=3e-2, atol=2e-3)
+    np.testing.assert_allclose(c(out.color), rgb.numpy(), atol=4e-3)
+    jm = float(jac.abs().max())
+    np.testing.assert_allclose(c(out.action_features), jac.numpy(), atol=3e-2 * jm)
+    np.testing.assert_allclose(c(out.flow), flow.numpy(), atol=3e-2 * float(flow.abs().max()) + 1e-6)
+    np.testing.assert_allclose(c(enc.action_features), jac.numpy(), atol=3e-2 * jm)
+    np.testing.assert_allclose(dho.density_features.cpu().numpy(), geo.numpy(), atol=2e-2 * float(geo.abs().max()))
+    np.testing.assert_allclose(dho.xyz_features.cpu().numpy(), encf.numpy(), atol=2e-5)
+    np.testing.assert_allclose(dho.pixel_aligned_features.cpu().numpy(), z.numpy(), atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(c(sig_p), sig_prop.numpy(), rtol=3e-2, atol=2e-3)

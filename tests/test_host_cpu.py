@@ -214,3 +214,38 @@ def test_c_abi_argument_errors_without_a_gpu():
     assert L.njf_pdf_sample(None, None, 0, None, 0, 1, 8, 8, 1.0, 8, None, None, None) != 0
     assert L.njf_flow_gn_terms(None, None, None, None, None, None, None, 10, 10, 6, None, None, None, None, None) != 0
     assert L.njf_flow_gn_workspace_doubles(3) > 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/project"), reason="needs the reference checkout (build container)")
+@pytest.mark.parametrize("head,A", [("jacobian_transformer", 8), ("jacobian_mlp", 6)])
+def test_registration_into_the_reference_registries(head, A):
+    """njf_b200.plugin.register_into_reference(): the reference's own factories / Model then build B200 decoders
+    (models/decoder/__init__.py:11-44), with the reference's state-dict keys; unregister restores its classes."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    from njf_b200 import modules as mod, plugin
+
+    ref_model = ref_shim.reference_modules()
+    import neural_jacobian_field.models.decoder as ref_dec
+
+    cfg = ref_shim.build_reference_cfg(A, head, (16,), 24)
+    plain = ref_model.Model(cfg)
+    own_flow = ref_dec.ACTION_DECODERS["flow_mlp"]
+    assert plugin.register_into_reference()
+    try:
+        assert ref_dec.ACTION_DECODERS[head] is mod.ACTION_DECODERS[head]
+        assert ref_dec.DENSITY_DECODERS["density_mlp"] is mod.DensityDecoderMlp
+        assert ref_dec.ACTION_DECODERS["flow_mlp"] is own_flow          # no B200 kernel: the reference keeps its own
+        m = ref_model.Model(cfg)                                         # the REFERENCE's Model, built from B200 decoders
+        assert isinstance(m.decoder, mod.ActionDecoderJacobian) and isinstance(m.proposal_networks[0], mod.DensityDecoderMlp)
+        assert m.decoder.action_dim == A
+        m.load_state_dict(plain.state_dict(), strict=True)               # same parameter names and shapes
+        for name in ("forward", "encode_image", "compute_density", "freeze_non_action_parameters", "switch_mode"):
+            assert callable(getattr(m.decoder, name))
+        assert callable(m.proposal_networks[0].get_density)
+        with pytest.raises(Exception):                                   # no CUDA device here: fails loudly, no CPU fallback
+            m.proposal_networks[0].get_density(torch.zeros(1, 2, 3, 3), None)
+    finally:
+        plugin.unregister_from_reference()
+    assert ref_dec.ACTION_DECODERS[head] is not mod.ACTION_DECODERS[head]
