@@ -391,10 +391,16 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
         for (int j = 0; j < 16; ++j) J[j] = 0.f;
         const size_t tidx = static_cast<size_t>(lgroup) * g.T + tile;
         if (xf_head) {
-          epi_wait_acc(e);  // lin_in + q_enc; the query channels were gathered by the prologue / the previous tile
+          // lin_in / q_enc window: the upper half of segment 0 goes into the staging chunks the query channels
+          // (gathered by the prologue / the previous tile) do not occupy
+          __syncwarp();
+          gather_seg128_part(e, g, sc->taps, 0, 1);
+          epi_wait_acc(e);  // lin_in + q_enc
           if (p.qs) store_query_stream(e, p.qs + tidx * 8 * kRows);
           PROF(e, kPHead);
-          gather_segment<128>(e, g, sc->taps, 0);
+          __syncwarp();     // the query channels are consumed: their chunks take the lower half of segment 0
+          gather_seg128_part(e, g, sc->taps, 0, 0);
+          __syncwarp();
           trunk_blocks_epilogue(e, g, 0, sc->taps, [&](int k, int w) {
             if (!has_next) return;
             if (k == 2 && w == 1) {

@@ -292,6 +292,68 @@ __device__ __forceinline__ void gather_rows(EpiCtx& e, const PassGeom& g, const 
   PROF(e, kPGather);
 }
 
+// the generic form: HB bytes per tap starting `byte_off` bytes into the pixel's channels, staged from 16 B chunk
+// `chunk0` of the row on
+template <int HB>
+__device__ __forceinline__ void gather_bytes(EpiCtx& e, const PassGeom& g, const TapEntry* taps, int byte_off, int chunk0,
+                                             int j_begin, int j_end) {
+  static_assert(HB == 128 || HB == 64, "bytes per tap");
+  using GS = GatherShape<HB>;  // HB bytes per warp and tap == the warp's half of an HB-channel segment
+  PROF(e, kPOther);
+  if (g.debug & 1) return;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / GS::kLanesPerRow;        // which row of the group this lane works on
+  const int piece = lane % GS::kLanesPerRow;      // which 8 B piece of the row's HB bytes
+  const int row0 = e.q * 32 + sub;                // + kRowsPerInstr * group
+  const uint8_t* mp = reinterpret_cast<const uint8_t*>(g.map) + byte_off + piece * 8;
+  const int chunk = chunk0 + (piece >> 1);
+  const int chunk_sub = (piece & 1) * 8;
+  // U row groups x 4 taps of 8 B per lane are in flight per batch; the tap weights are fetched only when a row is
+  // blended, which keeps a batch at 8 B x 4 x U registers
+  constexpr int U = NJF_GATHER_U;
+#pragma unroll 1
+  for (int j0 = j_begin; j0 < j_end; j0 += U) {
+    uint2 t[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (j0 + u < j_end) {
+        const TapEntry* te = taps + row0 + GS::kRowsPerInstr * (j0 + u);
+        const uint4 px = *reinterpret_cast<const uint4*>(te->off);
+        t[u][0] = __ldg(reinterpret_cast<const uint2*>(mp + px.x));
+        t[u][1] = __ldg(reinterpret_cast<const uint2*>(mp + px.y));
+        t[u][2] = __ldg(reinterpret_cast<const uint2*>(mp + px.z));
+        t[u][3] = __ldg(reinterpret_cast<const uint2*>(mp + px.w));
+      } else {
+        t[u][0] = t[u][1] = t[u][2] = t[u][3] = make_uint2(0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (j0 + u >= j_end) break;
+      const int row = row0 + GS::kRowsPerInstr * (j0 + u);
+      const uint4 w = *reinterpret_cast<const uint4*>(taps[row].w2);
+      const uint32_t wq[4] = {w.x, w.y, w.z, w.w};
+      __half2 lo = __hmul2(*reinterpret_cast<const __half2*>(&t[u][0].x), *reinterpret_cast<const __half2*>(&wq[0]));
+      __half2 hi = __hmul2(*reinterpret_cast<const __half2*>(&t[u][0].y), *reinterpret_cast<const __half2*>(&wq[0]));
+#pragma unroll
+      for (int q = 1; q < 4; ++q) {
+        lo = __hfma2(*reinterpret_cast<const __half2*>(&t[u][q].x), *reinterpret_cast<const __half2*>(&wq[q]), lo);
+        hi = __hfma2(*reinterpret_cast<const __half2*>(&t[u][q].y), *reinterpret_cast<const __half2*>(&wq[q]), hi);
+      }
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo);
+      o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(e.tz + tz_offset(row, chunk) + chunk_sub) = o;
+    }
+  }
+  PROF(e, kPGather);
+}
+// a 128-channel segment in two 32-channel-per-warp parts: part 1 (the upper 32 channels of the warp's half) lands in
+// chunks [8h+4, 8h+8) and can be gathered while a 64-channel segment still occupies [8h, 8h+4)
+__device__ __forceinline__ void gather_seg128_part(EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0, int part) {
+  gather_bytes<64>(e, g, taps, (ch0 + e.half * 64 + part * 32) * 2, e.half * 8 + part * 4, 0, GatherShape<64>::kGroups);
+}
+
 // a whole segment at once; __syncwarp orders it against this warp's own reads of the staging buffer
 template <int NCH>
 __device__ __forceinline__ void gather_segment(EpiCtx& e, const PassGeom& g, const TapEntry* taps, int ch0) {

@@ -207,3 +207,31 @@ def test_decoder_level_plugin_methods(head, A):
     np.testing.assert_allclose(dho.xyz_features.cpu().numpy(), encf.numpy(), atol=2e-5)
     np.testing.assert_allclose(dho.pixel_aligned_features.cpu().numpy(), z.numpy(), atol=1e-5, rtol=1e-5)
     np.testing.assert_allclose(c(sig_p), sig_prop.numpy(), rtol=3e-2, atol=2e-3)
+
+
+def test_validation_video_renderer():
+    """njf_b200.video.render_interpolated_view (models/model_wrapper.py:213-327): the first frame is the target view, the
+    last the context view; every frame equals a direct Model.forward at the interpolated camera."""
+    from njf_b200 import geometry as G, video as V
+    from njf_b200.model import CameraInput, RenderingInput, RobotInput
+
+    A, H, W = 8, 12, 16
+    m, _ = _model("jacobian_transformer", A, (32,), 32)
+    sc = _scene(A)
+    K = sc["K"]
+    pair = V.CameraPair(ctxt_extrinsics=sc["ctxt"], ctxt_intrinsics=K, trgt_extrinsics=sc["trgt"], trgt_intrinsics=K,
+                        trgt_intrinsics_px=V.denormalize_intrinsics(K, W, H), height=H, width=W)
+    for graph in (False, True):
+        m.cuda_graph = graph
+        vid = V.render_interpolated_view(m, sc["img"], pair, sc["act"], sc["zn"], sc["zf"], H, W, num_frames=4)
+        assert vid["rgb"].shape == (1, 4, 3, H, W) and vid["depth"].shape == (1, 4, 3, H, W)
+        assert vid["optical_flow"].shape == (1, 4, 3, H, W) and vid["pred_flow_t0"].shape == (1, 2, H, W)
+        xy, _ = G.get_pixel_coordinates(H, W, device=torch.device(DEV))
+        for idx, c2w in ((0, sc["trgt"]), (3, sc["ctxt"])):
+            o, d = G.get_world_rays(xy.reshape(1, -1, 2), K.to(DEV), c2w.to(DEV))
+            with torch.no_grad():
+                out = m.forward(CameraInput(sc["img"].to(DEV), sc["ctxt"].to(DEV), K.to(DEV), c2w.to(DEV),
+                                            V.denormalize_intrinsics(K, W, H).to(DEV)),
+                                RenderingInput(o, d, sc["zn"].to(DEV), sc["zf"].to(DEV)), RobotInput(sc["act"].to(DEV)))
+            ref = out.standard_output.rgb.reshape(1, H, W, 3).permute(0, 3, 1, 2)
+            np.testing.assert_allclose(vid["rgb"][:, idx].cpu().numpy(), ref.cpu().numpy(), atol=2e-4)

@@ -249,3 +249,46 @@ def test_registration_into_the_reference_registries(head, A):
     finally:
         plugin.unregister_from_reference()
     assert ref_dec.ACTION_DECODERS[head] is not mod.ACTION_DECODERS[head]
+
+
+def test_pose_interpolation_and_camera_rig_conventions():
+    """njf_b200.video: interpolate_pose against the reference's scipy-based one, and CameraRig against
+    the dataset's conventions (convention.post_process_camera_to_world, DatasetCommon.get_relative_transform, intrinsics
+    normalisation) on the real Allegro rig file -- when the reference checkout is present; analytic checks otherwise."""
+    import json
+    import math
+
+    from njf_b200 import video as V
+
+    g = torch.Generator().manual_seed(0)
+    a, b = synth.relative_target_pose(1), synth.relative_target_pose(4)
+    assert torch.allclose(V.interpolate_pose(a, b, 0.0), a, atol=1e-6) and torch.allclose(V.interpolate_pose(a, b, 1.0), b, atol=1e-5)
+    mid = V.interpolate_pose(a, b, 0.5)
+    assert torch.allclose(mid[:3, :3] @ mid[:3, :3].T, torch.eye(3), atol=1e-5) and torch.allclose(mid[:3, 3], (a[:3, 3] + b[:3, 3]) / 2, atol=1e-6)
+    ref_root = "/root/reference"
+    if not os.path.isdir(ref_root):
+        return
+    import sys
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    ref_shim.install()
+    from neural_jacobian_field.utils import convention as C
+    from neural_jacobian_field.visualization.view_interpolation import interpolate_pose as ref_interp
+
+    for t in (0.0, 0.13, 0.5, 0.87, 1.0):
+        assert torch.allclose(V.interpolate_pose(a, b, t), ref_interp(a, b, t), atol=2e-6)
+    cams = json.load(open(os.path.join(ref_root, "notebooks/real_world/dataset_configs/allegro_config.json")))["cameras"]
+    rig = V.CameraRig(cams)
+    assert len(rig) == 12
+    raw = torch.tensor([c["transform_matrix"] for c in cams], dtype=torch.float32)
+    for i in (0, 5, 11):
+        assert torch.equal(rig.c2w[i], C.post_process_camera_to_world(raw[i]))
+    pair = rig.pair(2, 7)
+    inv = torch.inverse(rig.c2w[2])                      # dataset.py:321-327 get_relative_transform
+    assert torch.allclose(pair.ctxt_extrinsics[0], torch.eye(4), atol=1e-5)
+    assert torch.equal(pair.trgt_extrinsics[0], torch.einsum("ij,jk->ik", inv, rig.c2w[7]))
+    k = torch.eye(3); k[0, 0], k[1, 1], k[0, 2], k[1, 2] = cams[7]["fl_x"], cams[7]["fl_y"], cams[7]["cx"], cams[7]["cy"]
+    k[:2] /= torch.tensor([cams[7]["w"], cams[7]["h"]])[:, None].float()   # dataset.py:283-294
+    assert torch.allclose(pair.trgt_intrinsics[0], k)
+    assert torch.allclose(pair.trgt_intrinsics_px, C.denormalize_intrinsics(pair.trgt_intrinsics, width=640, height=480))
