@@ -262,9 +262,9 @@ def main_reference(args):
         "impl": "reference", "metric": METRIC, "value": rps, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(cfg, args.gpus, {"note": "reference algorithm on the host cores (oracle/njf_oracle.py port; "
-                                                       "/root/reference is absent on the GPU box); each step renders a bounded "
-                                                       "random-ray sample of the frame"}),
+        "config": config_dict(cfg, args.gpus),   # the same object as this repo's arm prints
+        "note": "reference algorithm on the host cores (oracle/njf_oracle.py port; /root/reference is absent on the GPU box); "
+                "each step renders a bounded random-ray sample of the frame",
         "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": f"{nrays} random rays of the {cfg['H']}x{cfg['W']} frame per step, {cfg['s_prop'][0]}+{cfg['s_nerf']} samples"},
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -665,7 +665,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
-        "config": config_dict(cfg, world, {"rays_per_gpu": R}),
+        "config": config_dict(cfg, world),
         "breakdown_ms": {"hoist": t_hoist, "proposal_kernel": t_prop, "field_pass": t_field, "field_kernel": t_fk, "xf_kernel": t_xf,
                          "finish+gather": t_tail},
         "roofline": roof,
