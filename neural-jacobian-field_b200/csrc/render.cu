@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
   } else {
     EpiCtx e = epi_ctx(c);
     SlotScratch* sc = slot_scratch(c, e.slot);
+    const int lane = threadIdx.x & 31;
     // This slot's tiles form a software pipeline: while tile n runs blocks 2..4 (whose MMA wait windows carry no
     // gather of tile n), the warp sets up tile n+1 (bins -> position -> projection -> taps) and prefetches ITS part
     // of tile n+1's first hoisted segment into the staging buffer, which tile n stopped using after block 1.
@@ -150,11 +151,12 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
       PROF(e, kPOther);
       row_setup(g, group, tile, e.row, rs);
       PROF(e, kPPdf);
-      write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
+      if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
       PROF(e, kPHead);
       write_posenc(e, rs.cam, rs.ray >= 0, g.debug);
       PROF(e, kPColor);
       epi_publish(e);  // -> lin_in
+      pair_bar(e);     // the row quarter's tap entries (16 written by each of its two warps) are complete
       PROF(e, kPSetup);
       gather_segment<128>(e, g, sc->taps, 0);
     }
@@ -173,7 +175,9 @@ __global__ void __launch_bounds__(kThreads, 1) proposal_kernel(const __grid_cons
           PROF(e, kPOther);
           row_setup(g, group, tile, e.row, nx);
           PROF(e, kPPdf);
-          write_taps(sc->taps, e.row, nx, g.Hf, g.Wf, g.CH);
+          pair_bar(e);  // the partner warp has issued its last read of tile n's entries
+          if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, nx, g.Hf, g.Wf, g.CH);
+          pair_bar(e);  // tile n+1's entries of this row quarter are complete
           PROF(e, kPHead);
         } else if (k == 3 && w == 0) {
           __syncwarp();
@@ -352,9 +356,10 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
       tile_of(0, lgroup, tile);
       PROF(e, kPOther);
       row_setup(g, g.group0 + lgroup, tile, e.row, rs);
-      write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
+      if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, rs, g.Hf, g.Wf, g.CH);
       write_posenc(e, rs.cam, rs.ray >= 0, g.debug);
       epi_publish(e);  // -> lin_in (+ q_enc for the transformer head)
+      pair_bar(e);     // the row quarter's tap entries (16 written by each of its two warps) are complete
       PROF(e, kPSetup);
       if (xf_head) gather_segment<64>(e, g, sc->taps, 384);
       else gather_segment<128>(e, g, sc->taps, 0);
@@ -382,7 +387,9 @@ __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constan
           tile_of(n + 1, lg2, t2);
           PROF(e, kPOther);
           row_setup(g, g.group0 + lg2, t2, e.row, nx);
-          write_taps(sc->taps, e.row, nx, g.Hf, g.Wf, g.CH);
+          pair_bar(e);  // the partner warp has issued its last read of tile n's entries
+          if ((lane >> 4) == e.half) write_taps(sc->taps, e.row, nx, g.Hf, g.Wf, g.CH);
+          pair_bar(e);  // tile n+1's entries of this row quarter are complete
           PROF(e, kPSetup);
         };
         const bool valid = rs.ray >= 0;

@@ -189,9 +189,10 @@ __device__ __forceinline__ void write_posenc(const EpiCtx& e, const float (&cam)
 }
 
 // ----------------------------------------------------------------------------- gather
-// Per-row bilinear taps (F.grid_sample align_corners=True, padding_mode="border"): computed once per row and read
-// by the gathering lanes for every channel segment.  BOTH threads of a row write the (identical) entry, so each of
-// the two warps of a row quarter reads only what it wrote itself.
+// Per-row bilinear taps (F.grid_sample align_corners=True, padding_mode="border"): computed once per row (by the
+// thread of the row whose warp owns it: rows 32q+16h.. belong to warp (q,h)) and read by the gathering lanes of
+// both warps of the row quarter for every channel segment; a named barrier between the two warps fences the table
+// once per tile (after the writes, and before the next tile's writes).
 struct TapEntry {
   uint32_t off[4];  // BYTE offset of the nw, ne, sw, se tap pixels inside the hoisted map (< 4 GiB)
   uint32_t w2[4];   // their weights as packed fp16 pairs {w, w} (all zero for padding rows)
