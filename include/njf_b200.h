@@ -68,6 +68,11 @@ typedef struct NjfTensor {
  * builds the per-kernel step programs.  Synchronous. */
 int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tensors, int n_tensors, NjfField** out);
 void njf_field_destroy(NjfField* f);
+/* Partial re-pack after an optimiser step of the action phase (only `decoder.jacobian_*` changed,
+ * models/model_wrapper.py:75-85): `tensors` = the cross-attention head's tensors (jacobian_query_mlp, jacobian_index_embedding,
+ * jacobian_attn_decoder.*, jacobian_head).  Re-packs the head blob, the query step image and the 64 hoisted query rows in
+ * place (synchronises `stream` first; no allocation).  Cross-attention head only. */
+int njf_field_update_head(NjfField* f, const NjfTensor* tensors, int n_tensors, void* stream);
 
 /* ---- hoisted feature maps ---------------------------------------------------------------------
  * Replaces the three `lin_z[k](z)` Linear(512->128) layers of every ResnetFC

@@ -124,62 +124,15 @@ void trunk_blocks(Builder& b, Program& prog, const std::string& p, int d_out, in
   b.step(prog, wo, d_out, 128, 128, n_out_pad, 128, /*d_col=*/128, 0, 0, bo, true);
 }
 
-}  // namespace
-
-extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tensors, int n_tensors,
-                                NjfField** out) {
-  if (!desc || !tensors || !out) NJF_FAIL("njf_field_create: null argument");
-  if (desc->encoder_dim != 512) NJF_FAIL("encoder_dim %d unsupported (kernels are built for 512)", desc->encoder_dim);
-  if (desc->n_proposal < 1 || desc->n_proposal > NJF_MAX_LEVELS) NJF_FAIL("n_proposal %d out of range", desc->n_proposal);
-  const int A = desc->action_dim;
-  if (desc->head == NJF_HEAD_TRANSFORMER) {
-    if (A < 1 || A > 8) NJF_FAIL("jacobian_transformer: action_dim %d unsupported (1..8)", A);
-  } else if (desc->head == NJF_HEAD_MLP) {
-    if (A < 1 || A > 10) NJF_FAIL("jacobian_mlp: action_dim %d unsupported (1..10)", A);
-  } else {
-    NJF_FAIL("unknown head %d", desc->head);
-  }
-  Builder b;
-  for (int i = 0; i < n_tensors; ++i) b.t[tensors[i].name] = {tensors[i].data, tensors[i].numel};
-
-  // owned until success: every failure path below frees the device buffers already allocated
-  struct Guard {
-    NjfField* f;
-    ~Guard() { if (f) njf_field_destroy(f); }
-  } guard{new NjfField()};   // value-initialised: all tables start at zero
-  NjfField* f = guard.f;
-  f->desc = *desc;
-  if (desc->sh_convention != NJF_SH_TCNN && desc->sh_convention != NJF_SH_NERFSTUDIO_TORCH)
-    NJF_FAIL("unknown sh_convention %d", desc->sh_convention);
-  // hoist channel order: proposal nets (384 each), then the main map (dens 384 + head part)
-  for (int i = 0; i < desc->n_proposal; ++i) {
-    const std::string p = "proposal_networks." + std::to_string(i) + ".density_head";
-    trunk_lin_in(b, f->prop_prog[i], p);
-    trunk_blocks(b, f->prop_prog[i], p, 1, 16);
-  }
-  Program& fp = f->field_prog;
-  std::vector<uint8_t> xf_blob;
-  // transformer head: lin_in and q_enc read the same A tile (the positional encoding) and are
-  // covered by ONE accumulator commit (two arrivals on one mbarrier phase would be unsafe)
-  trunk_lin_in(b, fp, "decoder.density_head", desc->head == NJF_HEAD_TRANSFORMER ? kStepNoCommit : 0);
-  if (desc->head == NJF_HEAD_TRANSFORMER) {
-    f->ch_main = 448;
-    const float* wq = b.get("decoder.jacobian_query_mlp.weight", 64 * 575);
-    const float* bq = b.get("decoder.jacobian_query_mlp.bias", 64);
-    const float* emb = b.get("decoder.jacobian_index_embedding", static_cast<int64_t>(A) * 64);
-    b.step(fp, wq ? enc_cols(wq, 64, 575).data() : nullptr, 64, 128, 128, 64, 128, /*d_col=*/128, 0,
-           kStepReuseA | kStepK16Tail, bq, true);
-    if (wq && bq) {
-      // hoisted query channels: the 512 feature columns of jacobian_query_mlp (its bias rides in the q_enc step)
-      for (int c = 0; c < 64; ++c) b.hoist_w.insert(b.hoist_w.end(), wq + c * 575 + 63, wq + c * 575 + 575);
-      b.hoist_b.insert(b.hoist_b.end(), 64, 0.f);
-    }
-    // ---- the attention / feed-forward layers and jacobian_head run in xf_kernel from their own blob.
-    // Exact folds done here in fp64: keys/values (they depend only on the learned index embedding,
-    // transformer.py:63-78, action_decoder_jacobian.py:431-435), the LayerNorm affine (PreNorm,
-    // transformer.py:14-21: W (g*n + b) = (W diag g) n + W b) and log2(e) into the logits.
+// The attention / feed-forward layers and jacobian_head run in xf_kernel from their own blob.
+// Exact folds done here in fp64: keys/values (they depend only on the learned index embedding,
+// transformer.py:63-78, action_decoder_jacobian.py:431-435), the LayerNorm affine (PreNorm,
+// transformer.py:14-21: W (g*n + b) = (W diag g) n + W b) and log2(e) into the logits.
+void build_head(Builder& b, int A, Program& hp, std::vector<uint8_t>& xf_blob) {
+  const float* emb = b.get("decoder.jacobian_index_embedding", static_cast<int64_t>(A) * 64);
+  hp = Program{};
+  {
     Builder hb;
-    Program& hp = f->head_prog;
     for (int l = 0; l < 3; ++l) {
       const std::string p = "decoder.jacobian_attn_decoder.layers." + std::to_string(l);
       const float* g1 = b.get(p + ".0.norm.weight", 64);
@@ -245,6 +198,69 @@ extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tenso
     hb.step(hp, wh, 3 * A, 64, 64, 32, 64, /*d_col=*/64, 0, 0, bh, true);
     xf_blob.swap(hb.blob);
   }
+}
+
+// q_enc step image: jacobian_query_mlp's positional-encoding / xyz columns (+ bias block); `out` = n*k*2 + n*32 bytes
+void pack_q_enc(const float* wq, const float* bq, uint8_t* out) {
+  const std::vector<float> cols = enc_cols(wq, 64, 575);
+  pack_sw128_f16(cols.data(), 64, 128, 128, 64, 128, out);
+  pack_sw32_bias_f16(bq, 64, 64, out + 64 * 128 * 2);
+}
+
+}  // namespace
+
+extern "C" int njf_field_create(const NjfFieldDesc* desc, const NjfTensor* tensors, int n_tensors,
+                                NjfField** out) {
+  if (!desc || !tensors || !out) NJF_FAIL("njf_field_create: null argument");
+  if (desc->encoder_dim != 512) NJF_FAIL("encoder_dim %d unsupported (kernels are built for 512)", desc->encoder_dim);
+  if (desc->n_proposal < 1 || desc->n_proposal > NJF_MAX_LEVELS) NJF_FAIL("n_proposal %d out of range", desc->n_proposal);
+  const int A = desc->action_dim;
+  if (desc->head == NJF_HEAD_TRANSFORMER) {
+    if (A < 1 || A > 8) NJF_FAIL("jacobian_transformer: action_dim %d unsupported (1..8)", A);
+  } else if (desc->head == NJF_HEAD_MLP) {
+    if (A < 1 || A > 10) NJF_FAIL("jacobian_mlp: action_dim %d unsupported (1..10)", A);
+  } else {
+    NJF_FAIL("unknown head %d", desc->head);
+  }
+  Builder b;
+  for (int i = 0; i < n_tensors; ++i) b.t[tensors[i].name] = {tensors[i].data, tensors[i].numel};
+
+  // owned until success: every failure path below frees the device buffers already allocated
+  struct Guard {
+    NjfField* f;
+    ~Guard() { if (f) njf_field_destroy(f); }
+  } guard{new NjfField()};   // value-initialised: all tables start at zero
+  NjfField* f = guard.f;
+  f->desc = *desc;
+  if (desc->sh_convention != NJF_SH_TCNN && desc->sh_convention != NJF_SH_NERFSTUDIO_TORCH)
+    NJF_FAIL("unknown sh_convention %d", desc->sh_convention);
+  // hoist channel order: proposal nets (384 each), then the main map (dens 384 + head part)
+  for (int i = 0; i < desc->n_proposal; ++i) {
+    const std::string p = "proposal_networks." + std::to_string(i) + ".density_head";
+    trunk_lin_in(b, f->prop_prog[i], p);
+    trunk_blocks(b, f->prop_prog[i], p, 1, 16);
+  }
+  Program& fp = f->field_prog;
+  std::vector<uint8_t> xf_blob;
+  // transformer head: lin_in and q_enc read the same A tile (the positional encoding) and are
+  // covered by ONE accumulator commit (two arrivals on one mbarrier phase would be unsafe)
+  trunk_lin_in(b, fp, "decoder.density_head", desc->head == NJF_HEAD_TRANSFORMER ? kStepNoCommit : 0);
+  if (desc->head == NJF_HEAD_TRANSFORMER) {
+    f->ch_main = 448;
+    const float* wq = b.get("decoder.jacobian_query_mlp.weight", 64 * 575);
+    const float* bq = b.get("decoder.jacobian_query_mlp.bias", 64);
+    const float* emb = b.get("decoder.jacobian_index_embedding", static_cast<int64_t>(A) * 64);
+    b.step(fp, wq ? enc_cols(wq, 64, 575).data() : nullptr, 64, 128, 128, 64, 128, /*d_col=*/128, 0,
+           kStepReuseA | kStepK16Tail, bq, true);
+    f->q_enc_step = fp.nsteps - 1;
+    (void)emb;
+    if (wq && bq) {
+      // hoisted query channels: the 512 feature columns of jacobian_query_mlp (its bias rides in the q_enc step)
+      for (int c = 0; c < 64; ++c) b.hoist_w.insert(b.hoist_w.end(), wq + c * 575 + 63, wq + c * 575 + 575);
+      b.hoist_b.insert(b.hoist_b.end(), 64, 0.f);
+    }
+    build_head(b, A, f->head_prog, xf_blob);
+  }
   trunk_blocks(b, fp, "decoder.density_head", 16, 16);
   {
     const float* w1 = b.get("decoder.color_head.0.weight", 64 * 31);
@@ -297,4 +313,48 @@ extern "C" void njf_field_destroy(NjfField* f) {
   cudaFree(f->d_hoist_w);
   cudaFree(f->d_hoist_b);
   delete f;
+}
+
+// ---- partial re-pack: only the Jacobian-head tensors changed (an optimiser step of the action phase,
+// models/model_wrapper.py:75-85).  Re-packs the cross-attention blob, the q_enc step image and the 64 hoisted query
+// rows in place -- no allocation, ~0.6 MB of host->device copies instead of a full njf_field_create.
+extern "C" int njf_field_update_head(NjfField* f, const NjfTensor* tensors, int n_tensors, void* stream_) {
+  if (!f || !tensors) NJF_FAIL("njf_field_update_head: null argument");
+  if (f->desc.head != NJF_HEAD_TRANSFORMER) NJF_FAIL("njf_field_update_head: cross-attention head only");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int A = f->desc.action_dim;
+  Builder b;
+  for (int i = 0; i < n_tensors; ++i) b.t[tensors[i].name] = {tensors[i].data, tensors[i].numel};
+  Program hp{};
+  std::vector<uint8_t> xf_blob;
+  build_head(b, A, hp, xf_blob);
+  const float* wq = b.get("decoder.jacobian_query_mlp.weight", 64 * 575);
+  const float* bq = b.get("decoder.jacobian_query_mlp.bias", 64);
+  if (!b.err.empty()) NJF_FAIL("njf_field_update_head: %s", b.err.c_str());
+  if (xf_blob.size() != f->xf_bytes) NJF_FAIL("internal: head blob size changed");
+  const MmaStep& st = f->field_prog.steps[f->q_enc_step];
+  std::vector<uint8_t> qimg(st.w_bytes, 0);
+  if (qimg.size() != 64 * 128 * 2 + 64 * 32) NJF_FAIL("internal: q_enc image size");
+  pack_q_enc(wq, bq, qimg.data());
+  // hoisted query rows: rows [384, 448) of the main map's slab, 8 K-block images of [N rows x 128 B]
+  const NjfField::HoistJobHost* job = nullptr;
+  for (const auto& j : f->hoist_jobs)
+    if (j.map == f->desc.n_proposal && j.c0 <= 384 && 384 + 64 <= j.c0 + j.N) job = &j;
+  if (!job) NJF_FAIL("internal: hoist slab of the query rows not found");
+  std::vector<float> rows(64 * 512);
+  for (int c = 0; c < 64; ++c) std::memcpy(rows.data() + c * 512, wq + c * 575 + 63, 512 * sizeof(float));
+  std::vector<uint8_t> himg(8 * 64 * 128);
+  for (int kb = 0; kb < 8; ++kb) pack_sw128_f16(rows.data() + kb * 64, 64, 64, 512, 64, 64, himg.data() + kb * 64 * 128);
+  // the previous render on this stream may still read the old images
+  NJF_CUDA(cudaStreamSynchronize(stream));
+  NJF_CUDA(cudaMemcpy(f->d_xf_blob, xf_blob.data(), xf_blob.size(), cudaMemcpyHostToDevice));
+  NJF_CUDA(cudaMemcpy(f->d_blob + st.w_off, qimg.data(), qimg.size(), cudaMemcpyHostToDevice));
+  const int r0 = 384 - job->c0;
+  for (int kb = 0; kb < 8; ++kb)
+    NJF_CUDA(cudaMemcpy(f->d_hoist_img + job->w_off + static_cast<size_t>(kb) * job->N * 128 + static_cast<size_t>(r0) * 128,
+                        himg.data() + kb * 64 * 128, 64 * 128, cudaMemcpyHostToDevice));
+  const size_t grow = static_cast<size_t>(f->desc.n_proposal) * f->ch_prop + 384;   // row in the fp32 hoist matrix
+  NJF_CUDA(cudaMemcpy(f->d_hoist_w + grow * 512, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice));
+  f->head_prog = hp;
+  return 0;
 }

@@ -36,6 +36,7 @@ struct NjfField {
   struct HoistJobHost { int map, c0, N; uint32_t w_off; int bias_off; };
   NjfFieldDesc desc;
   uint8_t* d_hoist_img = nullptr;          // tcgen05 weight images of the hoist GEMM (hoist_tc.cu)
+  int q_enc_step = -1;                     // index of the q_enc step in field_prog (transformer head)
   njf::Program head_prog;                  // transformer head: steps of xf_kernel
   uint8_t* d_xf_blob = nullptr;
   uint32_t xf_bytes = 0;

@@ -62,6 +62,8 @@ def _declare():
     L.njf_field_create.argtypes = [POINTER(NjfFieldDesc), POINTER(NjfTensor), c_int, POINTER(c_void_p)]
     L.njf_field_destroy.restype = None
     L.njf_field_destroy.argtypes = [c_void_p]
+    L.njf_field_update_head.restype = c_int
+    L.njf_field_update_head.argtypes = [c_void_p, POINTER(NjfTensor), c_int, c_void_p]
     L.njf_hoisted_bytes.restype = c_size_t
     L.njf_hoisted_bytes.argtypes = [c_void_p, c_int, c_int, c_int]
     L.njf_hoist_features.restype = c_int
@@ -157,6 +159,19 @@ class Field:
     @property
     def handle(self) -> c_void_p:
         return self._h
+
+    def update_head(self, weights: Dict[str, torch.Tensor]) -> None:
+        """Re-pack only the cross-attention Jacobian head in place (njf_field_update_head): what an optimiser step of the
+        action phase changes.  ``weights``: the ``decoder.jacobian_*`` tensors."""
+        L = _declare()
+        keep = []
+        arr = (NjfTensor * len(weights))()
+        for i, (k, v) in enumerate(weights.items()):
+            t = v.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            keep.append(t)
+            arr[i] = NjfTensor(k.encode(), t.data_ptr(), t.numel())
+        with torch.cuda.device(self.device):
+            _lib.check(L.njf_field_update_head(self._h, arr, len(weights), stream_ptr()))
 
     def _check_device(self, t: torch.Tensor, what: str) -> None:
         if t.device != self.device:

@@ -282,6 +282,7 @@ class Model(nn.Module):
         self._steps_since_update = 0
         self._field: Optional[api.Field] = None
         self._field_key = None
+        self._field_key_head = None
         self.sh_fp16_round = True  # tiny-cuda-nn's SH encoding returns fp16
         self.sh_convention = "tcnn"  # or "nerfstudio_torch" (what nerfstudio computes without tiny-cuda-nn)
         self.cuda_graph = False    # eval-mode forward of a fixed shape as ONE CUDA-graph launch (encoder + hoist + render)
@@ -333,18 +334,29 @@ class Model(nn.Module):
         return sd
 
     def field(self) -> api.Field:
-        """Packed weights for the kernels; re-packed whenever a hot-path parameter or a packing option changed."""
+        """Packed weights for the kernels; re-packed whenever a hot-path parameter or a packing option changed.  When only
+        the cross-attention Jacobian head changed (an optimiser step of the action phase) the head is re-packed in place
+        (njf_field_update_head) instead of rebuilding the whole field."""
         dev = self._device()
-        params = [p for n, p in self.named_parameters() if not n.startswith("encoder.")]
-        key = (dev, self._mode(), bool(self.sh_fp16_round), self.sh_convention,
-               tuple((p.data_ptr(), p._version) for p in params))
+        is_head = lambda n: n.startswith("decoder.") and "jacobian" in n and "jacobian_head_arm" not in n
+        named = [(n, p) for n, p in self.named_parameters() if not n.startswith("encoder.")]
+        ver = lambda sel: tuple((p.data_ptr(), p._version) for n, p in named if sel(n))
+        key = (dev, self._mode(), bool(self.sh_fp16_round), self.sh_convention, ver(lambda n: not is_head(n)))
+        key_head = ver(is_head)
         if self._field is None or self._field_key != key:
             head, A = self._head_and_dim()
             with torch.cuda.device(dev):
                 self._field = api.Field(head, A, len(self.proposal_networks), self._hot_state(),
                                         sh_fp16_round=self.sh_fp16_round, sh_convention=self.sh_convention)
-            self._field_key = key
+            self._field_key, self._field_key_head = key, key_head
             self._graphs.clear()
+        elif self._field_key_head != key_head:
+            if self.cfg.action_decoder.name == "jacobian_transformer" and self._mode() == "regular":
+                self._field.update_head({n: p for n, p in self.state_dict().items() if is_head(n)})
+                self._field_key_head = key_head
+            else:
+                self._field = None
+                return self.field()
         return self._field
 
     def _device(self) -> torch.device:

@@ -205,3 +205,30 @@ def test_arm_mode_uses_the_arm_head():
     with torch.no_grad():
         out2 = m.forward(cam, rin, RobotInput(torch.zeros(1, A)), compute_vis_features=True)
     assert out2.vis_output.action_features.shape[-1] == 3 * A
+
+
+def test_partial_repack_equals_full_repack():
+    """After a change of the Jacobian-head parameters only (an optimiser step of the action phase) Model.field() re-packs
+    the head in place (njf_field_update_head); the render must equal that of a freshly packed field bit for bit."""
+    from njf_b200.model import CameraInput, RenderingInput, RobotInput
+
+    m, _ = _model("jacobian_transformer", 8, (32,), 32)
+    sc = _scene(8)
+    cam = CameraInput(sc["img"], sc["ctxt"], sc["K"], sc["trgt"], sc["kpx"])
+    rin, rob = RenderingInput(sc["o"], sc["d"], sc["zn"], sc["zf"]), RobotInput(sc["act"])
+    with torch.no_grad():
+        before = m.forward(cam, rin, rob, compute_vis_features=True)
+        fld = m._field
+        g = torch.Generator(device=DEV).manual_seed(1)
+        for n, p in m.named_parameters():
+            if n.startswith("decoder.") and "jacobian" in n:
+                p.add_(0.05 * p.abs().mean() * torch.randn(p.shape, generator=g, device=DEV))
+        after = m.forward(cam, rin, rob, compute_vis_features=True)
+        assert m._field is fld                                   # updated in place, not rebuilt
+        fresh, _ = _model("jacobian_transformer", 8, (32,), 32)
+        fresh.load_state_dict(m.state_dict())
+        ref = fresh.forward(cam, rin, rob, compute_vis_features=True)
+    assert not torch.equal(before.vis_output.action_features, after.vis_output.action_features)
+    for a, b in ((after.standard_output.rgb, ref.standard_output.rgb), (after.standard_output.optical_flow, ref.standard_output.optical_flow),
+                 (after.vis_output.action_features, ref.vis_output.action_features)):
+        assert torch.equal(a, b)
