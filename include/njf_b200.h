@@ -212,7 +212,9 @@ int njf_invert_poses(const float* c2w, float* w2c, int n, void* stream);
 int njf_make_rays(const float* k_norm, const float* c2w, const float* coords_xy, int B, int R, int H, int W,
                   float* origins, float* dirs, float* z, void* stream);
 
-/* ---- PDFSampler alone (rendering/ray_samplers.py:351-451, eval/train u supplied by the caller) */
+/* ---- PDFSampler alone (rendering/ray_samplers.py:351-451, eval/train u supplied by the caller); s_in <= 4096.
+ * With sum_vec_width = 8 the fp32 row sum reproduces ATen's CPU order bit for bit for rows of up to 512 samples (the
+ * render path's limit). */
 int njf_pdf_sample(const float* weights, const float* bins_in, int bins_in_stride, const float* u, int u_stride,
                    int n_rays, int s_in, int n_out, float anneal, int sum_vec_width, float* bins_out,
                    int32_t* inds_out, void* stream);

@@ -20,6 +20,9 @@ from helpers import GOLDEN, O, RENDER_FIXTURES, load_fixture, oracle_render, syn
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
+# end-to-end searchsorted mismatch vs the reference's indices on the small fixtures (48 rays, 16-32 coarse samples: few,
+# wide CDF steps); measured values in profiles/parity_r02.json, bound = measured + margin
+FIXTURE_INDEX_MISMATCH_BOUND = 0.01   # measured 0 .. 0.0012
 
 
 def _field_and_maps(head, A, s_prop, weights, feat):
@@ -139,7 +142,7 @@ def test_full_render_vs_reference(name):
         ref = fx[f"inds_{lvl + 1}"]
         mism = float(np.mean(inds != ref))
         print(f"{name}: level {lvl} searchsorted mismatch rate {mism:.4f}")
-        assert mism < 0.03
+        assert mism < FIXTURE_INDEX_MISMATCH_BOUND
     np.testing.assert_allclose(res.level_bins[-1].cpu().numpy(), fx["final_bins"], atol=2e-3, rtol=0)
     np.testing.assert_allclose(res.prop_weights[-1].cpu().numpy(), fx["proposal_weights"], atol=2e-3, rtol=0)
     _check_composites(res, fx, nf, loose=2.0)

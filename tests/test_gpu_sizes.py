@@ -273,3 +273,33 @@ def test_sh_convention_switch():
         np.testing.assert_allclose(st.rgb_samples.cpu().numpy(), ref["rgb_samples"].numpy(), atol=4e-3, rtol=0)
         outs[conv] = st.rgb_samples.cpu()
     assert float((outs["tcnn"] - outs["nerfstudio_torch"]).abs().max()) > 1e-2   # the switch changes the colours
+
+
+@pytest.mark.parametrize("s_in,n_out", [(1531, 64), (2048, 300), (4096, 128)])
+def test_sampler_entry_points_at_their_size_limits(s_in, n_out):
+    """njf_pdf_sample / njf_transmittance_weights accept up to 4096 input samples; beyond ~1530 the per-warp scan
+    buffers no longer fit four warps in the default 48 KB of shared memory, so the launch drops to one warp per block
+    (csrc/render.cu).  Vs the oracle's PDFSampler restatement on the same weights: the bit-exact reproduction of ATen's
+    fp32 row sum covers rows of up to 512 samples (the render path's own limit; longer rows go through more levels of
+    ATen's cascade summation), so here a last-bit difference of the normaliser may move an index at an exact CDF tie:
+    <= 0.1 % of the indices, bins within 2e-5."""
+    from njf_b200 import _lib, api
+
+    g = torch.Generator().manual_seed(s_in)
+    N = 37
+    w = torch.rand(N, s_in, generator=g) ** 4
+    w[3] = 0.0                                   # a zero-weight ray
+    w[5, : s_in // 2] = 0.0
+    edges = torch.sort(torch.rand(N, s_in + 1, generator=g), dim=-1).values
+    _, us = api.eval_tables([s_in], n_out, DEV)
+    bins, inds = api.pdf_sample(w.to(DEV), edges.to(DEV), us[0], n_out)
+    rb, ri = O.pdf_resample(w, edges, n_out)
+    assert float(np.mean(inds.cpu().numpy() != ri.numpy().astype(np.int32))) < 1e-3
+    np.testing.assert_allclose(bins.cpu().numpy(), rb.numpy(), atol=2e-5, rtol=0)
+    deltas = (edges[:, 1:] - edges[:, :-1]) * 3.0
+    sigma = torch.rand(N, s_in, generator=g) * 5.0
+    tw = api.transmittance_weights(deltas.to(DEV), sigma.to(DEV))
+    ref = O.transmittance_weights(deltas[..., None], sigma[..., None])[..., 0]
+    np.testing.assert_allclose(tw.cpu().numpy(), ref.numpy(), atol=1e-6, rtol=1e-5)
+    with pytest.raises(_lib.NjfError):            # beyond the limit: rejected at the boundary, not at launch
+        api.pdf_sample(torch.rand(2, 4097).to(DEV), torch.rand(2, 4098).sort(-1).values.to(DEV), us[0], n_out)
