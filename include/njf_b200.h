@@ -256,6 +256,37 @@ int njf_flow_backward(const float* g_flow, const float* g_pw_in, const float* jb
                       const float* trgt_w2c, const float* trgt_k_px, int n_rays, int rays_per_view, int action_dim,
                       float* g_jbar, float* g_action, void* stream);
 
+/* ---- training of the ResnetFC trunks: perception phase (models/model_wrapper.py:116-146: density
+ * head, colour head, proposal networks, the encoder through the feature map) and the MLP Jacobian head of the action
+ * phase.  The fused render kernels keep no activations, so a training step evaluates the trunks layer by layer in
+ * fp32 with the activations in caller-owned HBM tensors; torch.autograd chains these entry points
+ * (njf_b200/train_trunk.py) the way it chains nn.Linear in the reference (model_components/resnet_fc.py:70-79,
+ * 130-154).  lin_z is hoisted onto the feature map exactly as at inference: lin_z(bilinear(f)) = bilinear(lin_z(f)),
+ * the per-pixel maps being one plain GEMM over the NHWC encoder output.  Every matrix is row-major, contiguous, fp32;
+ * inner sizes are multiples of 4 in [4,128] (the caller zero-pads 63 -> 64, 31 -> 32, 3 -> 4, ...).
+ *
+ * njf_train_sample_setup: world points [B][N][3] -> context-camera point -> NeRFEncoding enc [B*N][64] (63 columns in
+ *   nerfstudio's order + one zero) and the four bilinear taps of F.grid_sample(align_corners=True, border)
+ *   (pixel_aligned_features.py:11-35): tap_pix [B*N][4] pixel indices view*Hf*Wf + y*Wf + x, tap_w [B*N][4].
+ * njf_train_gather / njf_train_scatter: out[m][c] = sum_t tap_w[m][t] map[tap_pix[m][t]][c] and its adjoint
+ *   dmap[tap_pix[m][t]][c] += tap_w[m][t] g[m][c] (dmap is accumulated into); CH a multiple of 128.
+ * njf_train_linear: c[M][n_out] = mask(act(a[M][k_red]) . Wm + bias) + residual, act = ReLU when relu_in, mask zeroes
+ *   entries whose mask_src[M][n_out] <= 0; bias / residual / mask_src may be NULL.
+ *   trans_w = 1: w is a Linear weight [n_out][k_red] (forward, y = x W^T + b);
+ *   trans_w = 0: w is the same weight seen as [k_red][n_out] (input gradient g_x = g_y W, masked by ReLU' of the saved x).
+ * njf_train_linear_wgrad: gw[N][K] += gy[M][N]^T . act(x[M][K]), gb[N] += column sums of gy (gb may be NULL).
+ * njf_train_sh16: SH degree 4 of unit directions dirs [M][3] -> out [M][16] (action_decoder_jacobian.py:24-30, 284),
+ *   optionally rounded through fp16 like tiny-cuda-nn's output. */
+int njf_train_sample_setup(const float* ctxt_w2c, const float* ctxt_k, const float* points, int B, int N, int Hf, int Wf,
+                           float* enc, int* tap_pix, float* tap_w, void* stream);
+int njf_train_gather(const float* map, const int* tap_pix, const float* tap_w, int M, int CH, float* out, void* stream);
+int njf_train_scatter(const float* g, const int* tap_pix, const float* tap_w, int M, int CH, float* dmap, void* stream);
+int njf_train_linear(const float* a, const float* w, const float* bias, const float* residual, const float* mask_src,
+                     float* c, int M, int n_out, int k_red, int trans_w, int relu_in, void* stream);
+int njf_train_linear_wgrad(const float* gy, const float* x, int M, int N, int K, int relu_in, float* gw, float* gb,
+                           void* stream);
+int njf_train_sh16(const float* dirs, int M, int sh_convention, int fp16_round, float* out, void* stream);
+
 /* ---- inverse dynamics on the collapsed encoding (the Adam loop of notebooks/real_world/2_inverse_dynamics.ipynb
  * over Model.infer_optical_flow, models/model.py:497-525): Gauss-Newton normal equations of
  *   min_u sum_i w_i | flow_i(u) - target_i |^2 ,  flow_i(u) = proj(p_i + Jbar_i^T u) - proj(p_i)

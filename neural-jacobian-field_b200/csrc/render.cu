@@ -273,38 +273,6 @@ __device__ __forceinline__ void store_query_stream(const EpiCtx& e, uint4* qs_ti
                                        pack_f16x2(x[8 * j + 4], x[8 * j + 5]), pack_f16x2(x[8 * j + 6], x[8 * j + 7])));
 }
 
-// SH degree 4 of the unit direction (action_decoder_jacobian.py:194-199): the colour head's directional encoding.
-//  conv = NJF_SH_TCNN            : tiny-cuda-nn's SphericalHarmonics (input d01 re-mapped x*2-1, tcnn's signs)
-//  conv = NJF_SH_NERFSTUDIO_TORCH: nerfstudio's torch fallback (components_from_spherical_harmonics evaluated on
-//                                  the [0,1] input as passed, all-positive leading signs)
-__device__ __forceinline__ void sh16(float dx, float dy, float dz, int conv, float (&o)[16]) {
-  // get_normalized_directions: (d + 1) / 2
-  const float hx = __fmul_rn(__fadd_rn(dx, 1.f), 0.5f), hy = __fmul_rn(__fadd_rn(dy, 1.f), 0.5f),
-              hz = __fmul_rn(__fadd_rn(dz, 1.f), 0.5f);
-  const bool tc = conv == NJF_SH_TCNN;
-  const float x = tc ? __fsub_rn(__fmul_rn(hx, 2.f), 1.f) : hx;
-  const float y = tc ? __fsub_rn(__fmul_rn(hy, 2.f), 1.f) : hy;
-  const float z = tc ? __fsub_rn(__fmul_rn(hz, 2.f), 1.f) : hz;
-  const float sg = tc ? -1.f : 1.f;  // tcnn flips the sign of the odd-in-(x,y) terms below
-  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
-  o[0] = 0.28209479177387814f;
-  o[1] = sg * 0.48860251190291987f * y;
-  o[2] = 0.48860251190291987f * z;
-  o[3] = sg * 0.48860251190291987f * x;
-  o[4] = 1.0925484305920792f * xy;
-  o[5] = sg * 1.0925484305920792f * yz;
-  o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
-  o[7] = sg * 1.0925484305920792f * xz;
-  o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-  o[9] = sg * 0.59004358992664352f * y * (3.0f * x2 - y2);
-  o[10] = 2.8906114426405538f * xy * z;
-  o[11] = sg * 0.45704579946446572f * y * (5.0f * z2 - 1.0f);
-  o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
-  o[13] = sg * 0.45704579946446572f * x * (5.0f * z2 - 1.0f);
-  o[14] = 1.4453057213202769f * z * (x2 - y2);
-  o[15] = sg * 0.59004358992664352f * x * (x2 - 3.0f * y2);
-}
-
 __global__ void __launch_bounds__(kThreads, 1) field_kernel(const __grid_constant__ FieldParams p) {
   extern __shared__ uint8_t smem_raw[];
   CtaCtx c = cta_setup(smem_raw);

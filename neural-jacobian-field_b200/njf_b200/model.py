@@ -444,17 +444,11 @@ class Model(nn.Module):
         r = self.cfg.rendering
         s_prop, s_nerf = tuple(r.num_proposal_samples), int(r.num_nerf_samples)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if need_grad:
-            outside = self._trainable_outside_head()
-            if outside:
-                raise NotImplementedError(
-                    "njf_b200.Model trains the ACTION phase only (everything but the Jacobian head frozen, "
-                    "models/model_wrapper.py:75-85): call model.decoder.freeze_non_action_parameters() and freeze the "
-                    "encoder / proposal networks, or run under torch.no_grad().  Perception-phase gradients (density, "
-                    f"colour, proposal networks, encoder) have no backward kernels yet; trainable outside the head: {outside[:4]} ...")
-            if self.cfg.action_decoder.name != "jacobian_transformer" or self._mode() != "regular":
-                raise NotImplementedError("backward kernels exist for the cross-attention Jacobian head "
-                                          "('jacobian_transformer', mode 'regular') only")
+        if need_grad and (self._trainable_outside_head() or self.cfg.action_decoder.name != "jacobian_transformer"
+                          or self._mode() != "regular"):
+            # perception phase (density / colour / proposal networks / encoder trainable) or an MLP Jacobian head:
+            # the trunks run layer by layer on the fp32 training kernels (csrc/trunk_train.cu) under autograd
+            return self._forward_train_trunks(camera_input, rendering_input, robot_input, compute_vis_features)
         out_dev = self.output_device or rendering_input.origins.device
         pe = self._encode(camera_input, robot_input)
         mv = lambda t: t.detach().to(dev, torch.float32, non_blocking=True).contiguous()
@@ -492,9 +486,10 @@ class Model(nn.Module):
             w = res.prop_weights[lvl] if lvl < len(s_prop) else res.weights
             e = euclid(b)
             weights_list.append(w[..., None])
-            samples_list.append(SampleBins(spacing_starts=b[..., :-1, None], spacing_ends=b[..., 1:, None],
-                                           starts=e[..., :-1, None], ends=e[..., 1:, None]))
+            samples_list.append((b, e))
         back = (lambda t: t) if out_dev.type == "cuda" else (lambda t: t.to(out_dev))
+        samples_list = [SampleBins(spacing_starts=back(b[..., :-1, None]), spacing_ends=back(b[..., 1:, None]),
+                                   starts=back(e[..., :-1, None]), ends=back(e[..., 1:, None])) for b, e in samples_list]
         out = ModelOutput(
             standard_output=ModelStandardOutput(rgb=back(res.rgb), depth=back(res.depth), optical_flow=back(res_flow)),
             training_output=ModelTrainingOutput(weights_list=[back(w) for w in weights_list], ray_samples_list=samples_list),
@@ -503,6 +498,36 @@ class Model(nn.Module):
             out.vis_output = ModelVisOutput(action_features=back(res_jbar), steps=back(res.steps),
                                             weights=back(res.weights), ray_positions=back(res.p),
                                             ray_positions_warped=back(res_pw))
+        return out
+
+    def _update_schedule(self, step) -> float:
+        """models/model.py:181-189: how many steps may pass between proposal-network updates."""
+        r = self.cfg.rendering
+        return float(np.clip(np.interp(step, [0, r.proposal_warmup], [0, r.proposal_update_every]), 1,
+                             r.proposal_update_every))
+
+    def _forward_train_trunks(self, camera_input, rendering_input, robot_input, compute_vis_features) -> ModelOutput:
+        from . import train_trunk as TT
+
+        out_dev = self.output_device or rendering_input.origins.device
+        with torch.cuda.device(self._device()):
+            t = TT.forward_train(self, camera_input, rendering_input, robot_input, compute_vis_features)
+        back = (lambda v: v) if out_dev.type == "cuda" else (lambda v: v.to(out_dev))
+        euclid = lambda b: b * t["far"] + (1 - b) * t["near"]
+        samples_list = []
+        for b in t["bins_list"]:
+            e = euclid(b)
+            samples_list.append(SampleBins(spacing_starts=back(b[..., :-1, None]), spacing_ends=back(b[..., 1:, None]),
+                                           starts=back(e[..., :-1, None]), ends=back(e[..., 1:, None])))
+        out = ModelOutput(
+            standard_output=ModelStandardOutput(rgb=back(t["rgb"]), depth=back(t["depth"]), optical_flow=back(t["flow"])),
+            training_output=ModelTrainingOutput(weights_list=[back(w) for w in t["weights_list"]],
+                                                ray_samples_list=samples_list),
+            vis_output=None)
+        if compute_vis_features:
+            out.vis_output = ModelVisOutput(action_features=back(t["jbar"]), steps=back(t["steps"]),
+                                            weights=back(t["weights"]), ray_positions=back(t["p"]),
+                                            ray_positions_warped=back(t["pw"]))
         return out
 
     # ------------------------------------------------------------------ one CUDA-graph launch per frame

@@ -134,8 +134,8 @@ def test_train_mode_without_grad_and_perception_phase():
     with torch.no_grad():   # jittered forward, no autograd: works with everything trainable
         out = m.forward(cam, rin, rob, compute_vis_features=True)
     assert out.training_output is not None and torch.isfinite(out.standard_output.rgb).all()
-    with pytest.raises(NotImplementedError):   # perception phase (all parameters trainable): no backward kernels yet
-        m.forward(cam, rin, rob)
+    out = m.forward(cam, rin, rob)   # perception phase (all parameters trainable): the trunk-training path (test_gpu_train_trunks.py)
+    assert out.standard_output.rgb.requires_grad and out.training_output.weights_list[0].requires_grad
 
 
 def test_cuda_graph_frame_replays_bit_identically():
