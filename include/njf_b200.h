@@ -275,6 +275,9 @@ int njf_flow_backward(const float* g_flow, const float* g_pw_in, const float* jb
  *   trans_w = 1: w is a Linear weight [n_out][k_red] (forward, y = x W^T + b);
  *   trans_w = 0: w is the same weight seen as [k_red][n_out] (input gradient g_x = g_y W, masked by ReLU' of the saved x).
  * njf_train_linear_wgrad: gw[N][K] += gy[M][N]^T . act(x[M][K]), gb[N] += column sums of gy (gb may be NULL).
+ * tensor_cores = 0: fp32 SIMT kernels (exact to fp32 round-off); tensor_cores = 1: tcgen05 kind::tf32 with fp32
+ *   accumulation in tensor memory -- what the reference's nn.Linear layers run under
+ *   torch.set_float32_matmul_precision("high") (train.py:64-65); the Python layer follows that torch switch.
  * njf_train_sh16: SH degree 4 of unit directions dirs [M][3] -> out [M][16] (action_decoder_jacobian.py:24-30, 284),
  *   optionally rounded through fp16 like tiny-cuda-nn's output. */
 int njf_train_sample_setup(const float* ctxt_w2c, const float* ctxt_k, const float* points, int B, int N, int Hf, int Wf,
@@ -282,9 +285,9 @@ int njf_train_sample_setup(const float* ctxt_w2c, const float* ctxt_k, const flo
 int njf_train_gather(const float* map, const int* tap_pix, const float* tap_w, int M, int CH, float* out, void* stream);
 int njf_train_scatter(const float* g, const int* tap_pix, const float* tap_w, int M, int CH, float* dmap, void* stream);
 int njf_train_linear(const float* a, const float* w, const float* bias, const float* residual, const float* mask_src,
-                     float* c, int M, int n_out, int k_red, int trans_w, int relu_in, void* stream);
+                     float* c, int M, int n_out, int k_red, int trans_w, int relu_in, int tensor_cores, void* stream);
 int njf_train_linear_wgrad(const float* gy, const float* x, int M, int N, int K, int relu_in, float* gw, float* gb,
-                           void* stream);
+                           int tensor_cores, void* stream);
 int njf_train_sh16(const float* dirs, int M, int sh_convention, int fp16_round, float* out, void* stream);
 
 /* ---- inverse dynamics on the collapsed encoding (the Adam loop of notebooks/real_world/2_inverse_dynamics.ipynb

@@ -327,6 +327,295 @@ __global__ void __launch_bounds__(kTtThreads, 2) tt_wgrad_kernel(const __grid_co
   }
 }
 
+
+// ============================================================================= TF32 tensor-core variants
+// The same two GEMM shapes on tcgen05 (kind::tf32, fp32 accumulators in tensor memory), selected by the caller when
+// torch's float32 matmul precision is not "highest" -- the reference trains with
+// torch.set_float32_matmul_precision("high") (train.py:64-65), i.e. its nn.Linear layers run TF32 too.  Operands are
+// staged from global memory by the CTA's threads straight into the K-major SWIZZLE_128B shared-memory image
+// (rounded to TF32 with cvt.rna), one elected thread issues the MMAs, and both kernels are software pipelines over
+// 128-row (64-row for the weight gradient) sample tiles so that the loads of tile j+1 overlap the MMAs of tile j;
+// with K, N <= 128 they are bound by the HBM traffic of the activations, not by the tensor pipe.
+__device__ __forceinline__ uint32_t f32_to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t n) {
+  return (1u << 4)               // D format: f32
+         | (2u << 7)             // A format: tf32
+         | (2u << 10)            // B format: tf32
+         | ((n >> 3) << 17)      // N >> 3
+         | ((128u >> 4) << 24);  // M >> 4
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// byte offset of fp32 element (row, col) in a K-major SWIZZLE_128B tile whose K-blocks (32 columns = 128 B rows)
+// are kb_stride bytes apart
+__device__ __forceinline__ uint32_t sw128_f32(uint32_t row, uint32_t col, uint32_t kb_stride) {
+  return (col >> 5) * kb_stride + row * 128u + (((((col & 31u) >> 2) ^ (row & 7u)) << 4) | ((col & 3u) << 2));
+}
+
+constexpr int kTcABytes = 4 * 128 * 128;  // one A buffer: 4 K-blocks x 128 rows x 128 B
+constexpr int kTcGemmSmem = 3 * kTcABytes + 64 + 1024;
+
+__global__ void __launch_bounds__(kTtThreads, 1) tt_gemm_tc_kernel(const __grid_constant__ TtGemm p) {
+  extern __shared__ uint8_t tc_raw[];
+  uint8_t* base = tc_raw + ((1024u - (smem_u32(tc_raw) & 1023u)) & 1023u);
+  uint8_t* Bt = base + 2 * kTcABytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 3 * kTcABytes);   // MMA-done, one per accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NO = p.NO, KR = p.KR;
+  const int NOp = (NO + 15) & ~15, KRp = (KR + 7) & ~7, nkb = (KRp + 31) >> 5, kc = KR >> 2;
+  const uint32_t b_kb = static_cast<uint32_t>(NOp) * 128u;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  for (int i = tid; i < 3 * kTcABytes / 16; i += kTtThreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (p.trans_w) {  // B[no][kr] = W[no][kr]
+    for (int i = tid; i < NO * kc; i += kTtThreads) {
+      const int no = i / kc, c4 = i - no * kc;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(no) * KR + c4 * 4));
+      *reinterpret_cast<uint4*>(Bt + sw128_f32(no, c4 * 4, b_kb)) =
+          make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
+    }
+  } else {  // B[no][kr] = W[kr][no]
+    const int nc = NO >> 2;
+    for (int i = tid; i < KR * nc; i += kTtThreads) {
+      const int kr = i / nc, no = (i - kr * nc) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(kr) * NO + no));
+      *reinterpret_cast<uint32_t*>(Bt + sw128_f32(no + 0, kr, b_kb)) = f32_to_tf32(v.x);
+      *reinterpret_cast<uint32_t*>(Bt + sw128_f32(no + 1, kr, b_kb)) = f32_to_tf32(v.y);
+      *reinterpret_cast<uint32_t*>(Bt + sw128_f32(no + 2, kr, b_kb)) = f32_to_tf32(v.z);
+      *reinterpret_cast<uint32_t*>(Bt + sw128_f32(no + 3, kr, b_kb)) = f32_to_tf32(v.w);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(NOp));
+  const int ntiles = (p.M + kTtBM - 1) / kTtBM;
+  const int n_my = (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  auto load_a = [&](int buf, int tile) {
+    uint8_t* A = base + buf * kTcABytes;
+    for (int i = tid; i < kTtBM * kc; i += kTtThreads) {
+      const int r = i / kc, c4 = i - r * kc;
+      const int m = tile * kTtBM + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < p.M) v = __ldg(reinterpret_cast<const float4*>(p.a + static_cast<size_t>(m) * KR + c4 * 4));
+      if (p.relu_in) {
+        v.x = fmaxf(v.x, 0.f);
+        v.y = fmaxf(v.y, 0.f);
+        v.z = fmaxf(v.z, 0.f);
+        v.w = fmaxf(v.w, 0.f);
+      }
+      *reinterpret_cast<uint4*>(A + sw128_f32(r, c4 * 4, 128u * 128u)) =
+          make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
+    }
+  };
+  auto issue = [&](int buf, int acc_slot) {  // one thread
+    const uint32_t a0 = smem_u32(base + buf * kTcABytes), b0 = smem_u32(Bt);
+    uint32_t acc = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int ks = min(4, (KRp - kb * 32) >> 3);
+      for (int k = 0; k < ks; ++k) {
+        umma_tf32(tmem + acc_slot * 128, make_sw128_desc(a0 + kb * (128 * 128) + k * 32),
+                  make_sw128_desc(b0 + kb * b_kb + k * 32), idesc, acc);
+        acc = 1;
+      }
+    }
+  };
+
+  if (n_my > 0) {
+    load_a(0, blockIdx.x);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue(0, 0);
+      umma_commit(&bar[0]);
+    }
+  }
+  const int q = warp & 3, h = warp >> 2;
+  const int nch = NOp >> 4, ch_begin = h ? (nch + 1) / 2 : 0, ch_end = h ? nch : (nch + 1) / 2;
+  for (int j = 0; j < n_my; ++j) {
+    const int s = j & 1;
+    const int tile = blockIdx.x + j * gridDim.x;
+    if (j + 1 < n_my) load_a(s ^ 1, tile + gridDim.x);  // that buffer's MMAs (tile j-1) completed: waited on below
+    mbar_wait(&bar[s], (j >> 1) & 1);
+    tc_fence_after();
+    fence_proxy_async_smem();
+    __syncthreads();  // tile j+1 staged by everybody; everybody is done reading accumulator s^1 (tile j-1)
+    if (tid == 0 && j + 1 < n_my) {
+      tc_fence_after();
+      issue(s ^ 1, s ^ 1);
+      umma_commit(&bar[s ^ 1]);
+    }
+    const int m = tile * kTtBM + 32 * q + lane;
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+      uint32_t r[16];
+      tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + s * 128 + ch * 16, r);
+      tmem_ld_wait();
+      if (m < p.M) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int no = ch * 16 + jj * 4;
+          if (no >= NO) break;
+          float4 v = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
+                                 __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
+          if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + no));
+            v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
+          }
+          const size_t o = static_cast<size_t>(m) * NO + no;
+          if (p.mask_src) {
+            const float4 sgn = __ldg(reinterpret_cast<const float4*>(p.mask_src + o));
+            v.x = sgn.x > 0.f ? v.x : 0.f;
+            v.y = sgn.y > 0.f ? v.y : 0.f;
+            v.z = sgn.z > 0.f ? v.z : 0.f;
+            v.w = sgn.w > 0.f ? v.w : 0.f;
+          }
+          if (p.residual) {
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + o));
+            v.x += rr.x, v.y += rr.y, v.z += rr.z, v.w += rr.w;
+          }
+          *reinterpret_cast<float4*>(p.c + o) = v;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// weight gradient: D[n][k] (n on the 128 TMEM lanes) += gY^T[n][m] . act(X)^T[k][m]^T over 64-sample tiles; an extra
+// all-ones row k = K of the B operand makes column K of D the bias gradient.
+constexpr int kTcWgA = 2 * 128 * 128;      // gY^T tile: 2 K-blocks (32 samples each) x 128 rows x 128 B
+constexpr int kTcWgB = 2 * 144 * 128;      // act(X)^T tile: 2 K-blocks x (K + 16 <= 144 rows) x 128 B
+constexpr int kTcWgradSmem = 2 * (kTcWgA + kTcWgB) + 64 + 1024;
+
+__global__ void __launch_bounds__(kTtThreads, 1) tt_wgrad_tc_kernel(const __grid_constant__ TtWgrad p) {
+  extern __shared__ uint8_t tc_raw[];
+  uint8_t* base = tc_raw + ((1024u - (smem_u32(tc_raw) & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 2 * (kTcWgA + kTcWgB));   // [0],[1]: buffer free; [2]: all done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, K = p.K;
+  const int Kp = (K + 1 + 15) & ~15;   // MMA N: the K weight columns + the ones row, rounded up to 16
+  const uint32_t b_kb = static_cast<uint32_t>(Kp) * 128u;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_init(&bar[2], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  for (int i = tid; i < 2 * (kTcWgA + kTcWgB) / 16; i += kTtThreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (tid < 128) {  // the ones row of both B buffers (never overwritten: the X rows are k < K)
+    const int buf = tid >> 6, ml = tid & 63;
+    *reinterpret_cast<uint32_t*>(base + buf * (kTcWgA + kTcWgB) + kTcWgA + sw128_f32(K, ml, b_kb)) = 0x3f800000u;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(Kp));
+  const int m_begin = blockIdx.x * p.rows_per_cta, m_end = min(p.M, m_begin + p.rows_per_cta);
+  const int n_my = m_end > m_begin ? (m_end - m_begin + 63) / 64 : 0;
+  // transposing loads: a lane owns one sample row (conflict-free stores: 32 lanes fill one 128-byte operand row),
+  // warp pair wq = warp >> 1 owns a quarter of the 16-byte column chunks
+  const int rg = warp & 1, wq = warp >> 1;
+  const int ncn = N >> 2, nck = K >> 2;
+  for (int j = 0; j < n_my; ++j) {
+    const int s = j & 1;
+    uint8_t* A = base + s * (kTcWgA + kTcWgB);
+    uint8_t* Bm = A + kTcWgA;
+    if (j >= 2) {
+      mbar_wait(&bar[s], ((j - 2) >> 1) & 1);  // the MMAs of tile j-2 are done with this buffer
+      tc_fence_after();
+    }
+    const int ml = rg * 32 + lane;
+    const int m = m_begin + j * 64 + ml;
+    const bool valid = m < m_end;
+    for (int c4 = (wq * ncn) >> 2; c4 < ((wq + 1) * ncn) >> 2; ++c4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) v = __ldg(reinterpret_cast<const float4*>(p.gy + static_cast<size_t>(m) * N + c4 * 4));
+      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 0, ml, 128u * 128u)) = f32_to_tf32(v.x);
+      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 1, ml, 128u * 128u)) = f32_to_tf32(v.y);
+      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 2, ml, 128u * 128u)) = f32_to_tf32(v.z);
+      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 3, ml, 128u * 128u)) = f32_to_tf32(v.w);
+    }
+    for (int c4 = (wq * nck) >> 2; c4 < ((wq + 1) * nck) >> 2; ++c4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) v = __ldg(reinterpret_cast<const float4*>(p.x + static_cast<size_t>(m) * K + c4 * 4));
+      if (p.relu_in) {
+        v.x = fmaxf(v.x, 0.f);
+        v.y = fmaxf(v.y, 0.f);
+        v.z = fmaxf(v.z, 0.f);
+        v.w = fmaxf(v.w, 0.f);
+      }
+      *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 0, ml, b_kb)) = f32_to_tf32(v.x);
+      *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 1, ml, b_kb)) = f32_to_tf32(v.y);
+      *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 2, ml, b_kb)) = f32_to_tf32(v.z);
+      *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 3, ml, b_kb)) = f32_to_tf32(v.w);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(A), b0 = smem_u32(Bm);
+      for (int kb = 0; kb < 2; ++kb)
+        for (int k = 0; k < 4; ++k)
+          umma_tf32(tmem, make_sw128_desc(a0 + kb * (128 * 128) + k * 32), make_sw128_desc(b0 + kb * b_kb + k * 32), idesc,
+                    (j | kb | k) ? 1u : 0u);
+      umma_commit(&bar[s]);
+      if (j == n_my - 1) umma_commit(&bar[2]);
+    }
+  }
+  if (n_my > 0) {
+    mbar_wait(&bar[2], 0);
+    tc_fence_after();
+    const int q = warp & 3, h = warp >> 2;
+    const int n = 32 * q + lane;
+    const int nch = Kp >> 4, ch_begin = h ? (nch + 1) / 2 : 0, ch_end = h ? nch : (nch + 1) / 2;
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+      uint32_t r[16];
+      tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + ch * 16, r);
+      tmem_ld_wait();
+      if (n < N) {
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int k = ch * 16 + jj;
+          if (k < K)
+            atomicAdd(p.gw + static_cast<size_t>(n) * K + k, __uint_as_float(r[jj]));
+          else if (k == K && p.gb)
+            atomicAdd(p.gb + n, __uint_as_float(r[jj]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 // ----------------------------------------------------------------------------- SH-16 of the view direction
 __global__ void __launch_bounds__(256) tt_sh16_kernel(const float* __restrict__ dirs, int M, int conv, int fp16_round,
                                                       float* __restrict__ out) {
@@ -406,13 +695,20 @@ int njf_train_scatter(const float* g, const int* tap_pix, const float* tap_w, in
 }
 
 int njf_train_linear(const float* a, const float* w, const float* bias, const float* residual, const float* mask_src,
-                     float* c, int M, int n_out, int k_red, int trans_w, int relu_in, void* stream) {
+                     float* c, int M, int n_out, int k_red, int trans_w, int relu_in, int tensor_cores, void* stream) {
   if (!a || !w || !c) NJF_FAIL("njf_train_linear: null argument");
   if (M <= 0 || !tt_dim_ok(n_out) || !tt_dim_ok(k_red))
     NJF_FAIL("njf_train_linear: M=%d n_out=%d k_red=%d (inner sizes must be multiples of 4 in [4,128])", M, n_out, k_red);
   TtGemm p{a, w, bias, residual, mask_src, c, M, n_out, k_red, trans_w, relu_in};
-  const int smem = 2 * 128 * kTtLd * 4;
   const int grid = std::min((M + kTtBM - 1) / kTtBM, tt_sms());
+  if (tensor_cores) {
+    if (tt_set_smem(tt_gemm_tc_kernel, kTcGemmSmem)) return 1;
+    tt_gemm_tc_kernel<<<grid, kTtThreads, kTcGemmSmem, static_cast<cudaStream_t>(stream)>>>(p);
+    NJF_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
+  const int smem = 2 * 128 * kTtLd * 4;
   if (n_out > 64) {
     if (tt_set_smem(tt_gemm_kernel<2>, smem)) return 1;
     tt_gemm_kernel<2><<<grid, kTtThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
@@ -426,15 +722,24 @@ int njf_train_linear(const float* a, const float* w, const float* bias, const fl
 }
 
 int njf_train_linear_wgrad(const float* gy, const float* x, int M, int N, int K, int relu_in, float* gw, float* gb,
-                           void* stream) {
+                           int tensor_cores, void* stream) {
   if (!gy || !x || !gw) NJF_FAIL("njf_train_linear_wgrad: null argument");
   if (M <= 0 || !tt_dim_ok(N) || !tt_dim_ok(K))
     NJF_FAIL("njf_train_linear_wgrad: M=%d N=%d K=%d (inner sizes must be multiples of 4 in [4,128])", M, N, K);
   const int chunks = (M + 63) / 64;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tensor_cores) {
+    const int grid_tc = std::min(chunks, tt_sms());
+    TtWgrad ptc{gy, x, gw, gb, M, N, K, relu_in, ((chunks + grid_tc - 1) / grid_tc) * 64};
+    if (tt_set_smem(tt_wgrad_tc_kernel, kTcWgradSmem)) return 1;
+    tt_wgrad_tc_kernel<<<grid_tc, kTtThreads, kTcWgradSmem, st>>>(ptc);
+    NJF_CUDA(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   const int grid = std::min(chunks, 2 * tt_sms());
   TtWgrad p{gy, x, gw, gb, M, N, K, relu_in, ((chunks + grid - 1) / grid) * 64};
   const int smem = 2 * 64 * 128 * 4;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool n2 = N > 64, k2 = K > 64;
 #define NJF_TT_WGRAD(A_, B_)                                              \
   do {                                                                    \

@@ -44,9 +44,10 @@ def _declare():
         fn.restype = c_int
         fn.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
     L.njf_train_linear.restype = c_int
-    L.njf_train_linear.argtypes = [c_void_p] * 6 + [c_int] * 5 + [c_void_p]
+    L.njf_train_linear.argtypes = [c_void_p] * 6 + [c_int] * 6 + [c_void_p]
     L.njf_train_linear_wgrad.restype = c_int
-    L.njf_train_linear_wgrad.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    L.njf_train_linear_wgrad.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                         c_void_p]
     L.njf_train_sh16.restype = c_int
     L.njf_train_sh16.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
     L._njf_trunk_train_declared = True
@@ -59,6 +60,12 @@ def _f32c(t: Tensor) -> Tensor:
 
 def _pad4(n: int) -> int:
     return (n + 3) // 4 * 4
+
+
+def tensor_cores() -> bool:
+    """The trunk GEMMs follow torch's own float32 matmul switch: "highest" (torch's default) -> fp32 SIMT kernels,
+    "high" / "medium" (what the reference's train.py:64-65 selects) -> tcgen05 kind::tf32."""
+    return torch.get_float32_matmul_precision() != "highest"
 
 
 # ----------------------------------------------------------------------------- kernels as autograd functions
@@ -76,7 +83,7 @@ class _Linear(torch.autograd.Function):
         N = w.shape[0]
         y = torch.empty(M, N, device=x.device, dtype=torch.float32)
         _lib.check(L.njf_train_linear(api.dptr(x), api.dptr(w), api.dptr(b), api.dptr(residual), None, api.dptr(y),
-                                      M, N, K, 1, int(relu_in), api.stream_ptr()))
+                                      M, N, K, 1, int(relu_in), int(tensor_cores()), api.stream_ptr()))
         ctx.save_for_backward(x, w)
         ctx.relu_in, ctx.has_b = bool(relu_in), b is not None
         return y
@@ -93,12 +100,12 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.empty(M, K, device=x.device, dtype=torch.float32)
             _lib.check(L.njf_train_linear(api.dptr(g), api.dptr(w), None, None, api.dptr(x) if ctx.relu_in else None,
-                                          api.dptr(gx), M, K, N, 0, 0, st))
+                                          api.dptr(gx), M, K, N, 0, 0, int(tensor_cores()), st))
         if ctx.needs_input_grad[1] or (ctx.has_b and ctx.needs_input_grad[2]):
             gw = torch.zeros(N, K, device=x.device, dtype=torch.float32)
             gb = torch.zeros(N, device=x.device, dtype=torch.float32) if ctx.has_b else None
             _lib.check(L.njf_train_linear_wgrad(api.dptr(g), api.dptr(x), M, N, K, int(ctx.relu_in), api.dptr(gw),
-                                                api.dptr(gb), st))
+                                                api.dptr(gb), int(tensor_cores()), st))
         return gx, gw, gb, None, (g if ctx.needs_input_grad[4] else None)
 
 

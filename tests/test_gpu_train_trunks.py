@@ -47,6 +47,41 @@ def test_linear_kernels_vs_torch(M, N, K, relu, res):
         np.testing.assert_allclose(a.cpu().numpy(), c.cpu().numpy(), atol=1e-5 * scale + 1e-6, rtol=1e-5, err_msg=name)
 
 
+@pytest.mark.parametrize("M,N,K,relu,res", [(1, 4, 4, False, False), (300, 128, 64, False, False), (257, 128, 128, True, True),
+                                            (1000, 64, 128, True, False), (129, 16, 128, True, False),
+                                            (513, 4, 128, True, False), (77, 64, 32, False, False),
+                                            (5000, 20, 128, True, False), (40000, 128, 128, True, True),
+                                            (20011, 128, 20, True, False), (333, 128, 4, False, False)])
+def test_linear_kernels_tf32_tensor_cores_vs_torch(M, N, K, relu, res):
+    """The tcgen05 kind::tf32 variants (selected by torch.set_float32_matmul_precision("high"), the reference's
+    train.py:64-65 setting) against float64: operands rounded to 10 mantissa bits, fp32 accumulation -> errors of
+    ~1e-3 of the result's scale."""
+    from njf_b200 import train_trunk as TT
+
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(DEV).requires_grad_(True)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).requires_grad_(True)
+    b = torch.randn(N, generator=g).to(DEV).requires_grad_(True)
+    r = torch.randn(M, N, generator=g).to(DEV).requires_grad_(True) if res else None
+    gy = torch.randn(M, N, generator=g).to(DEV)
+    prev = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("high")
+    try:
+        assert TT.tensor_cores()
+        y = TT._Linear.apply(x, w, b, relu, r)
+        got = torch.autograd.grad(y, [x, w, b] + ([r] if res else []), gy)
+    finally:
+        torch.set_float32_matmul_precision(prev)
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    rd = r.detach().double().requires_grad_(True) if res else None
+    yr = F.linear(torch.relu(xd) if relu else xd, wd, bd) + (rd if res else 0)
+    ref = torch.autograd.grad(yr, [xd, wd, bd] + ([rd] if res else []), gy.double())
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().cpu().numpy(), atol=6e-3, rtol=2e-3)
+    for a, c, name in zip(got, ref, "xwbr"):
+        scale = float(c.abs().max()) + 1e-12
+        np.testing.assert_allclose(a.cpu().numpy(), c.cpu().numpy(), atol=3e-3 * scale, rtol=2e-3, err_msg=name)
+
+
 def test_padded_linear_and_gather_scatter_vs_torch():
     from njf_b200 import train_trunk as TT
 
@@ -132,12 +167,26 @@ def _grad_report(got, ref, tol):
     return worst
 
 
-@pytest.mark.parametrize("head,A,s_prop,s_nerf,B,R", [("jacobian_transformer", 8, (32,), 48, 2, 70),
-                                                      ("jacobian_mlp", 6, (24, 16), 40, 1, 50)])
-def test_perception_phase_gradients_vs_oracle_autograd(head, A, s_prop, s_nerf, B, R):
+@pytest.fixture
+def matmul_precision(request):
+    prev = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision(request.param)
+    yield request.param
+    torch.set_float32_matmul_precision(prev)
+
+
+@pytest.mark.parametrize("head,A,s_prop,s_nerf,B,R,matmul_precision",
+                         [("jacobian_transformer", 8, (32,), 48, 2, 70, "highest"),
+                          ("jacobian_mlp", 6, (24, 16), 40, 1, 50, "highest"),
+                          ("jacobian_transformer", 8, (32,), 48, 2, 70, "high")], indirect=["matmul_precision"])
+def test_perception_phase_gradients_vs_oracle_autograd(head, A, s_prop, s_nerf, B, R, matmul_precision):
+    """matmul_precision "highest": fp32 SIMT kernels, tolerance 2e-3.  "high" (the reference's training setting):
+    the trunk GEMMs run kind::tf32 on the tensor cores and torch's own GEMMs TF32 as well; the CPU oracle stays fp32,
+    tolerance 5e-2 relative L2 per tensor (measured 2.5e-2 on lin_in: 10-bit operand mantissas through an 11-layer chain)."""
     from njf_b200 import train as T
     from njf_b200.model import CameraInput, RenderingInput, RobotInput
 
+    tf32 = matmul_precision != "highest"
     m, sd = _model(head, A, s_prop, s_nerf)
     m.train()
     img, K, kpx, ctxt, trgt, o, d, zn, zf, act, _, _ = _inputs(A, B, R, 3 + s_nerf)
@@ -176,13 +225,14 @@ def test_perception_phase_gradients_vs_oracle_autograd(head, A, s_prop, s_nerf, 
     ref_loss = _perception_loss(ref["rgb"], ref_w, ref_mid, target_rgb, target_depth)
     ref_loss.backward()
     ref_g = {n: (w[n].grad if n in w else dict(m.named_parameters())[n].grad.detach().cpu()) for n in got}
-    np.testing.assert_allclose(float(loss), float(ref_loss), rtol=2e-4)
-    np.testing.assert_allclose(out.standard_output.rgb.detach().numpy(), ref["rgb"].detach().numpy(), atol=2e-5)
-    np.testing.assert_allclose(to.weights_list[0][..., 0].detach().numpy(), ref["prop_weights_0"].detach().numpy(), atol=2e-5)
+    np.testing.assert_allclose(float(loss), float(ref_loss), rtol=5e-3 if tf32 else 2e-4)
+    np.testing.assert_allclose(out.standard_output.rgb.detach().numpy(), ref["rgb"].detach().numpy(), atol=3e-3 if tf32 else 2e-5)
+    np.testing.assert_allclose(to.weights_list[0][..., 0].detach().numpy(), ref["prop_weights_0"].detach().numpy(),
+                               atol=2e-3 if tf32 else 2e-5)
     np.testing.assert_allclose(out.standard_output.optical_flow.detach().numpy(), ref["optical_flow"].detach().numpy(),
                                atol=4e-2 * float(ref["optical_flow"].abs().max()) + 1e-3)
-    worst = _grad_report(got, ref_g, 2e-3)
-    print(f"perception-phase gradients ({head}), {len(got)} tensors: worst relative L2 error {worst[1]:.2e} ({worst[0]})")
+    worst = _grad_report(got, ref_g, 5e-2 if tf32 else 2e-3)
+    print(f"perception-phase gradients ({head}, matmul precision {matmul_precision}), {len(got)} tensors: worst relative L2 error {worst[1]:.2e} ({worst[0]})")
 
 
 def test_mlp_head_action_phase_gradients_vs_oracle_autograd():
