@@ -410,21 +410,42 @@ __global__ void __launch_bounds__(kTtThreads, 1) tt_gemm_tc_kernel(const __grid_
   const int ntiles = (p.M + kTtBM - 1) / kTtBM;
   const int n_my = (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
+  // eight 16-byte loads in flight per thread before the first shared-memory store (one CTA of 8 warps per SM: the
+  // memory-level parallelism has to come from the unrolling)
+  const int dr = kTtThreads / kc, dc = kTtThreads - dr * kc;
   auto load_a = [&](int buf, int tile) {
     uint8_t* A = base + buf * kTcABytes;
-    for (int i = tid; i < kTtBM * kc; i += kTtThreads) {
-      const int r = i / kc, c4 = i - r * kc;
-      const int m = tile * kTtBM + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < p.M) v = __ldg(reinterpret_cast<const float4*>(p.a + static_cast<size_t>(m) * KR + c4 * 4));
-      if (p.relu_in) {
-        v.x = fmaxf(v.x, 0.f);
-        v.y = fmaxf(v.y, 0.f);
-        v.z = fmaxf(v.z, 0.f);
-        v.w = fmaxf(v.w, 0.f);
+    const int total = kTtBM * kc;
+    int r = tid / kc, c4 = tid - r * kc;
+    for (int i0 = tid; i0 < total; i0 += 8 * kTtThreads) {
+      float4 v[8];
+      uint32_t off[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int m = tile * kTtBM + r;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i0 + u * kTtThreads < total && m < p.M)
+          v[u] = __ldg(reinterpret_cast<const float4*>(p.a + static_cast<size_t>(m) * KR + c4 * 4));
+        off[u] = sw128_f32(r, c4 * 4, 128u * 128u);
+        r += dr;
+        c4 += dc;
+        if (c4 >= kc) {
+          c4 -= kc;
+          ++r;
+        }
       }
-      *reinterpret_cast<uint4*>(A + sw128_f32(r, c4 * 4, 128u * 128u)) =
-          make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (i0 + u * kTtThreads >= total) break;
+        float4 t = v[u];
+        if (p.relu_in) {
+          t.x = fmaxf(t.x, 0.f);
+          t.y = fmaxf(t.y, 0.f);
+          t.z = fmaxf(t.z, 0.f);
+          t.w = fmaxf(t.w, 0.f);
+        }
+        *reinterpret_cast<uint4*>(A + off[u]) = make_uint4(f32_to_tf32(t.x), f32_to_tf32(t.y), f32_to_tf32(t.z), f32_to_tf32(t.w));
+      }
     }
   };
   auto issue = [&](int buf, int acc_slot) {  // one thread
@@ -471,6 +492,15 @@ __global__ void __launch_bounds__(kTtThreads, 1) tt_gemm_tc_kernel(const __grid_
       tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + s * 128 + ch * 16, r);
       tmem_ld_wait();
       if (m < p.M) {
+        // the (up to 8) reads of mask source / residual first, then the arithmetic and the stores
+        const size_t o0 = static_cast<size_t>(m) * NO + ch * 16;
+        float4 sg[4], rr[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const bool in = ch * 16 + jj * 4 < NO;
+          sg[jj] = (p.mask_src && in) ? __ldg(reinterpret_cast<const float4*>(p.mask_src + o0 + jj * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+          rr[jj] = (p.residual && in) ? __ldg(reinterpret_cast<const float4*>(p.residual + o0 + jj * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int no = ch * 16 + jj * 4;
@@ -478,22 +508,14 @@ __global__ void __launch_bounds__(kTtThreads, 1) tt_gemm_tc_kernel(const __grid_
           float4 v = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
                                  __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
           if (p.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + no));
-            v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + no));
+            v.x += bb.x, v.y += bb.y, v.z += bb.z, v.w += bb.w;
           }
-          const size_t o = static_cast<size_t>(m) * NO + no;
-          if (p.mask_src) {
-            const float4 sgn = __ldg(reinterpret_cast<const float4*>(p.mask_src + o));
-            v.x = sgn.x > 0.f ? v.x : 0.f;
-            v.y = sgn.y > 0.f ? v.y : 0.f;
-            v.z = sgn.z > 0.f ? v.z : 0.f;
-            v.w = sgn.w > 0.f ? v.w : 0.f;
-          }
-          if (p.residual) {
-            const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + o));
-            v.x += rr.x, v.y += rr.y, v.z += rr.z, v.w += rr.w;
-          }
-          *reinterpret_cast<float4*>(p.c + o) = v;
+          v.x = (sg[jj].x > 0.f ? v.x : 0.f) + rr[jj].x;
+          v.y = (sg[jj].y > 0.f ? v.y : 0.f) + rr[jj].y;
+          v.z = (sg[jj].z > 0.f ? v.z : 0.f) + rr[jj].z;
+          v.w = (sg[jj].w > 0.f ? v.w : 0.f) + rr[jj].w;
+          *reinterpret_cast<float4*>(p.c + o0 + jj * 4) = v;
         }
       }
     }
@@ -554,17 +576,33 @@ __global__ void __launch_bounds__(kTtThreads, 1) tt_wgrad_tc_kernel(const __grid
     const int ml = rg * 32 + lane;
     const int m = m_begin + j * 64 + ml;
     const bool valid = m < m_end;
-    for (int c4 = (wq * ncn) >> 2; c4 < ((wq + 1) * ncn) >> 2; ++c4) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) v = __ldg(reinterpret_cast<const float4*>(p.gy + static_cast<size_t>(m) * N + c4 * 4));
-      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 0, ml, 128u * 128u)) = f32_to_tf32(v.x);
-      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 1, ml, 128u * 128u)) = f32_to_tf32(v.y);
-      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 2, ml, 128u * 128u)) = f32_to_tf32(v.z);
-      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 3, ml, 128u * 128u)) = f32_to_tf32(v.w);
+    // all (up to 16) 16-byte loads of this lane's sample row are issued before the first shared-memory store
+    const int ca0 = (wq * ncn) >> 2, ca1 = ((wq + 1) * ncn) >> 2, cx0 = (wq * nck) >> 2, cx1 = ((wq + 1) * nck) >> 2;
+    float4 va[8], vx[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid && ca0 + u < ca1) va[u] = __ldg(reinterpret_cast<const float4*>(p.gy + static_cast<size_t>(m) * N + (ca0 + u) * 4));
     }
-    for (int c4 = (wq * nck) >> 2; c4 < ((wq + 1) * nck) >> 2; ++c4) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) v = __ldg(reinterpret_cast<const float4*>(p.x + static_cast<size_t>(m) * K + c4 * 4));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      vx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid && cx0 + u < cx1) vx[u] = __ldg(reinterpret_cast<const float4*>(p.x + static_cast<size_t>(m) * K + (cx0 + u) * 4));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c4 = ca0 + u;
+      if (c4 >= ca1) break;
+      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 0, ml, 128u * 128u)) = f32_to_tf32(va[u].x);
+      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 1, ml, 128u * 128u)) = f32_to_tf32(va[u].y);
+      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 2, ml, 128u * 128u)) = f32_to_tf32(va[u].z);
+      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 3, ml, 128u * 128u)) = f32_to_tf32(va[u].w);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c4 = cx0 + u;
+      if (c4 >= cx1) break;
+      float4 v = vx[u];
       if (p.relu_in) {
         v.x = fmaxf(v.x, 0.f);
         v.y = fmaxf(v.y, 0.f);

@@ -286,6 +286,9 @@ class Model(nn.Module):
         self.sh_fp16_round = True  # tiny-cuda-nn's SH encoding returns fp16
         self.sh_convention = "tcnn"  # or "nerfstudio_torch" (what nerfstudio computes without tiny-cuda-nn)
         self.cuda_graph = False    # eval-mode forward of a fixed shape as ONE CUDA-graph launch (encoder + hoist + render)
+        # eval-mode proposal levels in fp32 (njf_b200/precise.py): sample indices follow the fp32 reference to ~1e-5
+        # instead of ~2e-3, at ~10x the frame time; the final level stays on the fused tcgen05 field pass
+        self.precise_proposal = False
         self._graphs: Dict[tuple, "_FrameGraph"] = {}
         self.output_device: Optional[torch.device] = None   # None: results go back to where the rays came from (reference)
         self.jitter_generator: Optional[torch.Generator] = None   # train-mode stratified jitter (None = torch's global CUDA RNG)
@@ -399,6 +402,14 @@ class Model(nn.Module):
         host_nf = ((rendering_input.z_near, rendering_input.z_far)
                    if rendering_input.z_near.device.type == "cpu" and not pe.extrinsics.is_cuda else None)
         with torch.cuda.device(dev):
+            if getattr(self, "precise_proposal", False) and "final_bins" not in kw:
+                from . import precise
+
+                fb, lb, li, pw = precise.proposal_bins_fp32(
+                    [n.density_head for n in self.proposal_networks], pe.features, keep[0], keep[1],
+                    mv(rendering_input.origins), mv(rendering_input.directions), mv(rendering_input.z_near),
+                    mv(rendering_input.z_far), tuple(r.num_proposal_samples), r.num_nerf_samples, anneal=self._anneal)
+                kw["final_bins"] = fb
             res = render(self.field(), pe.hoisted, Hf, Wf, cams, mv(rendering_input.origins),
                          mv(rendering_input.directions), mv(rendering_input.z_near), mv(rendering_input.z_far),
                          mv(robot_input.robot_action), tuple(r.num_proposal_samples), r.num_nerf_samples,
@@ -413,6 +424,8 @@ class Model(nn.Module):
         if self.training:
             return self._forward_train(camera_input, rendering_input, robot_input, compute_vis_features)
         out_dev = self.output_device or rendering_input.origins.device
+        if self.cuda_graph and getattr(self, "precise_proposal", False):
+            raise _lib.NjfError("precise_proposal runs outside the CUDA-graph frame: set cuda_graph = False")
         if self.cuda_graph:
             res = self._graph_frame(camera_input, rendering_input, robot_input, compute_vis_features)
             if out_dev.type == "cuda":   # the graph's outputs are static buffers: hand CUDA callers their own copy
