@@ -701,7 +701,23 @@ def main():
                                                       "sample": f"{grays} rays/step (the reference's patch size), eager torch fp32 on cuda:0, {gdt * 1e3:.0f} ms/step"}
         except Exception as ex:  # noqa: BLE001 -- a baseline leg must not break the bench line
             line["cpu_baseline"]["torch_gpu_port"] = {"error": repr(ex)[:200]}
+        # the opt-in fp32 proposal mode (njf_b200/precise.py) on the same rays, and its cost on the whole frame
+        from njf_b200 import precise
+        trunks = [n.density_head for n in model.proposal_networks]
+        pidx = idx.to(dev)
+        pargs = (sc["z_near"], sc["z_far"], S_PROP, S_NERF)
+        _, _, pinds, _ = precise.proposal_bins_fp32(trunks, ofeat.to(dev), keep[0], keep[1], sc["origins"][:, pidx].contiguous(),
+                                                    sc["dirs"][:, pidx].contiguous(), *pargs)
+        mism_p = float((pinds[0].cpu() != oref["inds_1"]).float().mean())
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        precise.proposal_bins_fp32(trunks, ofeat.to(dev), keep[0], keep[1], sc["origins"], sc["dirs"], *pargs)
+        pe1.record()
+        torch.cuda.synchronize()
         line["quality"] = {"psnr_rgb_vs_oracle_db": 10 * math.log10(1.0 / max(mse, 1e-12)),
+                           "precise_proposal": {"index_mismatch_rate": mism_p, "proposal_levels_ms_per_frame": pe0.elapsed_time(pe1),
+                                                "note": "Model.precise_proposal = True: proposal levels in fp32 (csrc/trunk_train.cu "
+                                                        "SIMT kernels), final level on the fused field pass"},
                            "jacobian_rel_l2_vs_oracle": jr, "index_mismatch_rate": mism,
                            "index_mismatch_note": "fraction of PDF-sampler searchsorted indices that differ from the fp32 "
                                                   "oracle end to end (fp16 sigma moves a few CDF ties; the sampler is "
