@@ -268,8 +268,9 @@ int njf_flow_backward(const float* g_flow, const float* g_pw_in, const float* jb
  * njf_train_sample_setup: world points [B][N][3] -> context-camera point -> NeRFEncoding enc [B*N][64] (63 columns in
  *   nerfstudio's order + one zero) and the four bilinear taps of F.grid_sample(align_corners=True, border)
  *   (pixel_aligned_features.py:11-35): tap_pix [B*N][4] pixel indices view*Hf*Wf + y*Wf + x, tap_w [B*N][4].
- * njf_train_gather / njf_train_scatter: out[m][c] = sum_t tap_w[m][t] map[tap_pix[m][t]][c] and its adjoint
- *   dmap[tap_pix[m][t]][c] += tap_w[m][t] g[m][c] (dmap is accumulated into); CH a multiple of 128.
+ * njf_train_gather / njf_train_scatter: a window [ch0, ch0 + CW) of the CH map channels (one lin_z layer = 128 of 384):
+ *   out[m][c] = sum_t tap_w[m][t] map[tap_pix[m][t]][ch0 + c], out [M][CW], and its adjoint
+ *   dmap[tap_pix[m][t]][ch0 + c] += tap_w[m][t] g[m][c], g [M][CW] (dmap [pixels][CH] is accumulated into); CW a multiple of 128.
  * njf_train_linear: c[M][n_out] = mask(act(a[M][k_red]) . Wm + bias) + residual, act = ReLU when relu_in, mask zeroes
  *   entries whose mask_src[M][n_out] <= 0; bias / residual / mask_src may be NULL.
  *   trans_w = 1: w is a Linear weight [n_out][k_red] (forward, y = x W^T + b);
@@ -282,8 +283,10 @@ int njf_flow_backward(const float* g_flow, const float* g_pw_in, const float* jb
  *   optionally rounded through fp16 like tiny-cuda-nn's output. */
 int njf_train_sample_setup(const float* ctxt_w2c, const float* ctxt_k, const float* points, int B, int N, int Hf, int Wf,
                            float* enc, int* tap_pix, float* tap_w, void* stream);
-int njf_train_gather(const float* map, const int* tap_pix, const float* tap_w, int M, int CH, float* out, void* stream);
-int njf_train_scatter(const float* g, const int* tap_pix, const float* tap_w, int M, int CH, float* dmap, void* stream);
+int njf_train_gather(const float* map, const int* tap_pix, const float* tap_w, int M, int CH, int ch0, int CW, float* out,
+                     void* stream);
+int njf_train_scatter(const float* g, const int* tap_pix, const float* tap_w, int M, int CH, int ch0, int CW, float* dmap,
+                      void* stream);
 int njf_train_linear(const float* a, const float* w, const float* bias, const float* residual, const float* mask_src,
                      float* c, int M, int n_out, int k_red, int trans_w, int relu_in, int tensor_cores, void* stream);
 int njf_train_linear_wgrad(const float* gy, const float* x, int M, int N, int K, int relu_in, float* gw, float* gb,

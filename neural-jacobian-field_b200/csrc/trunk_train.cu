@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) tt_setup_kernel(const __grid_constant__ T
 // ----------------------------------------------------------------------------- gather / scatter on the lin_z maps
 // one warp per sample row; a lane owns 4 consecutive channels of every 128-channel group
 __global__ void __launch_bounds__(256) tt_gather_kernel(const float* __restrict__ map, const int* __restrict__ tap_pix,
-                                                        const float* __restrict__ tap_w, int M, int CH,
+                                                        const float* __restrict__ tap_w, int M, int CH, int ch0, int CW,
                                                         float* __restrict__ out) {
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= M) return;
@@ -91,22 +91,22 @@ __global__ void __launch_bounds__(256) tt_gather_kernel(const float* __restrict_
   const float4 w = __ldg(reinterpret_cast<const float4*>(tap_w) + m);
   const int pix[4] = {px.x, px.y, px.z, px.w};
   const float wt[4] = {w.x, w.y, w.z, w.w};
-  for (int c = lane * 4; c < CH; c += 128) {
+  for (int c = lane * 4; c < CW; c += 128) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(map + static_cast<size_t>(pix[t]) * CH + c));
+      const float4 v = __ldg(reinterpret_cast<const float4*>(map + static_cast<size_t>(pix[t]) * CH + ch0 + c));
       acc.x = fmaf(wt[t], v.x, acc.x);
       acc.y = fmaf(wt[t], v.y, acc.y);
       acc.z = fmaf(wt[t], v.z, acc.z);
       acc.w = fmaf(wt[t], v.w, acc.w);
     }
-    *reinterpret_cast<float4*>(out + static_cast<size_t>(m) * CH + c) = acc;
+    *reinterpret_cast<float4*>(out + static_cast<size_t>(m) * CW + c) = acc;
   }
 }
 
 __global__ void __launch_bounds__(256) tt_scatter_kernel(const float* __restrict__ g, const int* __restrict__ tap_pix,
-                                                         const float* __restrict__ tap_w, int M, int CH,
+                                                         const float* __restrict__ tap_w, int M, int CH, int ch0, int CW,
                                                          float* __restrict__ dmap) {
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= M) return;
@@ -114,12 +114,12 @@ __global__ void __launch_bounds__(256) tt_scatter_kernel(const float* __restrict
   const float4 w = __ldg(reinterpret_cast<const float4*>(tap_w) + m);
   const int pix[4] = {px.x, px.y, px.z, px.w};
   const float wt[4] = {w.x, w.y, w.z, w.w};
-  for (int c = lane * 4; c < CH; c += 128) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(g + static_cast<size_t>(m) * CH + c));
+  for (int c = lane * 4; c < CW; c += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g + static_cast<size_t>(m) * CW + c));
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       if (wt[t] == 0.f) continue;
-      atomicAdd(reinterpret_cast<float4*>(dmap + static_cast<size_t>(pix[t]) * CH + c),
+      atomicAdd(reinterpret_cast<float4*>(dmap + static_cast<size_t>(pix[t]) * CH + ch0 + c),
                 make_float4(wt[t] * v.x, wt[t] * v.y, wt[t] * v.z, wt[t] * v.w));
     }
   }
@@ -714,19 +714,23 @@ int njf_train_sample_setup(const float* ctxt_w2c, const float* ctxt_k, const flo
   return 0;
 }
 
-int njf_train_gather(const float* map, const int* tap_pix, const float* tap_w, int M, int CH, float* out, void* stream) {
+int njf_train_gather(const float* map, const int* tap_pix, const float* tap_w, int M, int CH, int ch0, int CW, float* out,
+                     void* stream) {
   if (!map || !tap_pix || !tap_w || !out) NJF_FAIL("njf_train_gather: null argument");
-  if (M <= 0 || CH <= 0 || CH % 128) NJF_FAIL("njf_train_gather: CH=%d must be a positive multiple of 128", CH);
-  tt_gather_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(map, tap_pix, tap_w, M, CH, out);
+  if (M <= 0 || CH <= 0 || CH % 4 || ch0 < 0 || ch0 % 4 || CW <= 0 || CW % 128 || ch0 + CW > CH)
+    NJF_FAIL("njf_train_gather: channel window [%d, %d) of %d (CW must be a positive multiple of 128)", ch0, ch0 + CW, CH);
+  tt_gather_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(map, tap_pix, tap_w, M, CH, ch0, CW, out);
   NJF_CUDA(cudaGetLastError());
   count_launch();
   return 0;
 }
 
-int njf_train_scatter(const float* g, const int* tap_pix, const float* tap_w, int M, int CH, float* dmap, void* stream) {
+int njf_train_scatter(const float* g, const int* tap_pix, const float* tap_w, int M, int CH, int ch0, int CW, float* dmap,
+                      void* stream) {
   if (!g || !tap_pix || !tap_w || !dmap) NJF_FAIL("njf_train_scatter: null argument");
-  if (M <= 0 || CH <= 0 || CH % 128) NJF_FAIL("njf_train_scatter: CH=%d must be a positive multiple of 128", CH);
-  tt_scatter_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, tap_pix, tap_w, M, CH, dmap);
+  if (M <= 0 || CH <= 0 || CH % 4 || ch0 < 0 || ch0 % 4 || CW <= 0 || CW % 128 || ch0 + CW > CH)
+    NJF_FAIL("njf_train_scatter: channel window [%d, %d) of %d (CW must be a positive multiple of 128)", ch0, ch0 + CW, CH);
+  tt_scatter_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, tap_pix, tap_w, M, CH, ch0, CW, dmap);
   NJF_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -362,6 +362,22 @@ class Model(nn.Module):
                 return self.field()
         return self._field
 
+    def _field_for_head_queries(self) -> api.Field:
+        """A packed field whose CROSS-ATTENTION HEAD (query MLP, attention / feed-forward layers, index embedding,
+        jacobian_head) is current, whatever the state of the trunks: what the trunk-training forward needs to evaluate
+        the per-sample Jacobians for the (gradient-free) flow output without re-packing every trunk after every
+        optimiser step -- the Jacobian head's output does not depend on the density trunk."""
+        if (self._field is None or self.cfg.action_decoder.name != "jacobian_transformer" or self._mode() != "regular"
+                or self._field_key[:4] != (self._device(), self._mode(), bool(self.sh_fp16_round), self.sh_convention)):
+            return self.field()
+        is_head = lambda n: n.startswith("decoder.") and "jacobian" in n and "jacobian_head_arm" not in n
+        key_head = tuple((p.data_ptr(), p._version) for n, p in self.named_parameters()
+                         if not n.startswith("encoder.") and is_head(n))
+        if self._field_key_head != key_head:
+            self._field.update_head({n: p for n, p in self.state_dict().items() if is_head(n)})
+            self._field_key_head = key_head
+        return self._field
+
     def _device(self) -> torch.device:
         dev = next(self.parameters()).device
         if dev.type != "cuda":

@@ -42,7 +42,7 @@ def _declare():
                                          c_void_p, c_void_p]
     for fn in (L.njf_train_gather, L.njf_train_scatter):
         fn.restype = c_int
-        fn.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+        fn.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     L.njf_train_linear.restype = c_int
     L.njf_train_linear.argtypes = [c_void_p] * 6 + [c_int] * 6 + [c_void_p]
     L.njf_train_linear_wgrad.restype = c_int
@@ -110,7 +110,9 @@ class _Linear(torch.autograd.Function):
 
 
 class _GatherMaps(torch.autograd.Function):
-    """z[m, c] = sum_t tap_w[m, t] maps[tap_pix[m, t], c]; backward scatters into a zeroed map-shaped gradient."""
+    """z_b[m, c] = sum_t tap_w[m, t] maps[tap_pix[m, t], 128 b + c] for every 128-channel group b of the maps (one
+    contiguous (M,128) tensor per lin_z layer); backward scatters the groups' gradients into one zeroed map-shaped
+    gradient."""
 
     @staticmethod
     def forward(ctx, maps, tap_pix, tap_w):
@@ -118,22 +120,29 @@ class _GatherMaps(torch.autograd.Function):
         maps = _f32c(maps)
         CH = maps.shape[-1]
         M = tap_pix.shape[0]
-        out = torch.empty(M, CH, device=maps.device, dtype=torch.float32)
-        _lib.check(L.njf_train_gather(api.dptr(maps), api.dptr(tap_pix), api.dptr(tap_w), M, CH, api.dptr(out),
-                                      api.stream_ptr()))
+        outs = []
+        for b in range(CH // 128):
+            out = torch.empty(M, 128, device=maps.device, dtype=torch.float32)
+            _lib.check(L.njf_train_gather(api.dptr(maps), api.dptr(tap_pix), api.dptr(tap_w), M, CH, 128 * b, 128,
+                                          api.dptr(out), api.stream_ptr()))
+            outs.append(out)
         ctx.save_for_backward(tap_pix, tap_w)
         ctx.map_shape = tuple(maps.shape)
-        return out
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, *gs):
         L = _declare()
         tap_pix, tap_w = ctx.saved_tensors
-        g = _f32c(g)
-        M, CH = g.shape
-        dmap = torch.zeros(ctx.map_shape, device=g.device, dtype=torch.float32)
-        _lib.check(L.njf_train_scatter(api.dptr(g), api.dptr(tap_pix), api.dptr(tap_w), M, CH, api.dptr(dmap),
-                                       api.stream_ptr()))
+        CH = ctx.map_shape[-1]
+        dmap = torch.zeros(ctx.map_shape, device=tap_w.device, dtype=torch.float32)
+        for b, g in enumerate(gs):
+            if g is None:
+                continue
+            g = _f32c(g)
+            _lib.check(L.njf_train_scatter(api.dptr(g), api.dptr(tap_pix), api.dptr(tap_w), g.shape[0], CH, 128 * b, 128,
+                                           api.dptr(dmap), api.stream_ptr()))
         return dmap, None, None
 
 
@@ -198,11 +207,11 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor], relu_in: bool, residual: O
 
 def resnet_fc(trunk, enc: Tensor, z: Tensor) -> Tensor:
     """ResnetFC.forward (model_components/resnet_fc.py:130-154; block :70-79; beta = 0 -> ReLU) on M sample rows:
-    enc (M,64) positional encoding (63 + zero column), z (M, 128 * len(lin_z)) the gathered lin_z maps."""
+    enc (M,64) positional encoding (63 + zero column), z = one (M,128) gathered lin_z map per combine layer."""
     x = linear(enc, trunk.lin_in.weight, trunk.lin_in.bias, False)
     for b, blk in enumerate(trunk.blocks):
         if b < len(trunk.lin_z):
-            x = x + z[:, 128 * b:128 * (b + 1)]
+            x = x + z[b]
         net = linear(x, blk.fc_0.weight, blk.fc_0.bias, True)
         x = linear(net, blk.fc_1.weight, blk.fc_1.bias, True, residual=x)
     return linear(x, trunk.lin_out.weight, trunk.lin_out.bias, True)
@@ -303,7 +312,7 @@ def forward_train(model, camera_input, rendering_input, robot_input, compute_vis
         # the cross-attention head carries no gradient on this path (the perception losses do not see it; its action
         # phase trains through train._RenderJacobianHead): evaluated by the fused query kernel
         with torch.no_grad():
-            fld = model.field()
+            fld = model._field_for_head_queries()   # trunks may be stale: the Jacobian head does not read them
             maps16 = fld.hoist(feats.detach().contiguous())
             _, _, jac = api.query_points(fld, cw, ck, maps16, Hf, Wf, pos.reshape(B, R * s_nerf, 3).contiguous())
         jac = jac.reshape(B, R, s_nerf, 3 * A)

@@ -104,7 +104,7 @@ def test_padded_linear_and_gather_scatter_vs_torch():
     pix = torch.randint(0, P, (M, 4), generator=g, dtype=torch.int32).to(DEV)
     tw = torch.rand(M, 4, generator=g).to(DEV)
     tw[::7, 1] = 0.0
-    z = TT._GatherMaps.apply(maps, pix, tw)
+    z = torch.cat(TT._GatherMaps.apply(maps, pix, tw), 1)
     zr = (maps[pix.long()] * tw[..., None]).sum(1)
     np.testing.assert_allclose(z.detach().cpu().numpy(), zr.detach().cpu().numpy(), atol=1e-5, rtol=1e-5)
     gz = torch.randn(M, CH, generator=g).to(DEV)
