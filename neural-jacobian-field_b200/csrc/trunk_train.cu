@@ -364,28 +364,38 @@ __device__ __forceinline__ uint32_t sw128_f32(uint32_t row, uint32_t col, uint32
 }
 
 constexpr int kTcABytes = 4 * 128 * 128;  // one A buffer: 4 K-blocks x 128 rows x 128 B
-constexpr int kTcGemmSmem = 3 * kTcABytes + 64 + 1024;
+constexpr int kTcGemmSmem = 3 * kTcABytes + 128 + 1024;
+constexpr int kTcGemmThreads = 288;       // warps 0-3 stage A tiles, warps 4-7 run the epilogue, warp 8 issues the MMAs
 
-__global__ void __launch_bounds__(kTtThreads, 1) tt_gemm_tc_kernel(const __grid_constant__ TtGemm p) {
+// Warp-specialised: the three roles only meet at mbarriers (a_full / a_empty per A buffer, acc_full / acc_empty per
+// accumulator), so the global loads of tile j+1, the MMAs of tile j and the stores of tile j-1 are all in flight.
+__global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __grid_constant__ TtGemm p) {
   extern __shared__ uint8_t tc_raw[];
   uint8_t* base = tc_raw + ((1024u - (smem_u32(tc_raw) & 1023u)) & 1023u);
   uint8_t* Bt = base + 2 * kTcABytes;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 3 * kTcABytes);   // MMA-done, one per accumulator
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(base + 3 * kTcABytes);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* acc_full = a_full + 4;
+  uint64_t* acc_empty = a_full + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 8);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NO = p.NO, KR = p.KR;
   const int NOp = (NO + 15) & ~15, KRp = (KR + 7) & ~7, nkb = (KRp + 31) >> 5, kc = KR >> 2;
   const uint32_t b_kb = static_cast<uint32_t>(NOp) * 128u;
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 128);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
-  for (int i = tid; i < 3 * kTcABytes / 16; i += kTtThreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  for (int i = tid; i < 3 * kTcABytes / 16; i += kTcGemmThreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   if (p.trans_w) {  // B[no][kr] = W[no][kr]
-    for (int i = tid; i < NO * kc; i += kTtThreads) {
+    for (int i = tid; i < NO * kc; i += kTcGemmThreads) {
       const int no = i / kc, c4 = i - no * kc;
       const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(no) * KR + c4 * 4));
       *reinterpret_cast<uint4*>(Bt + sw128_f32(no, c4 * 4, b_kb)) =
@@ -393,7 +403,7 @@ __global__ void __launch_bounds__(kTtThreads, 1) tt_gemm_tc_kernel(const __grid_
     }
   } else {  // B[no][kr] = W[kr][no]
     const int nc = NO >> 2;
-    for (int i = tid; i < KR * nc; i += kTtThreads) {
+    for (int i = tid; i < KR * nc; i += kTcGemmThreads) {
       const int kr = i / nc, no = (i - kr * nc) * 4;
       const float4 v = __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(kr) * NO + no));
       *reinterpret_cast<uint32_t*>(Bt + sw128_f32(no + 0, kr, b_kb)) = f32_to_tf32(v.x);
@@ -402,256 +412,269 @@ __global__ void __launch_bounds__(kTtThreads, 1) tt_gemm_tc_kernel(const __grid_
       *reinterpret_cast<uint32_t*>(Bt + sw128_f32(no + 3, kr, b_kb)) = f32_to_tf32(v.w);
     }
   }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(NOp));
   const int ntiles = (p.M + kTtBM - 1) / kTtBM;
   const int n_my = (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
-  // eight 16-byte loads in flight per thread before the first shared-memory store (one CTA of 8 warps per SM: the
-  // memory-level parallelism has to come from the unrolling)
-  const int dr = kTtThreads / kc, dc = kTtThreads - dr * kc;
-  auto load_a = [&](int buf, int tile) {
-    uint8_t* A = base + buf * kTcABytes;
+  if (warp < 4) {
+    // ---- loaders: 128 threads, eight 16-byte loads in flight per thread before the first shared-memory store
+    const int dr = 128 / kc, dc = 128 - dr * kc;
     const int total = kTtBM * kc;
-    int r = tid / kc, c4 = tid - r * kc;
-    for (int i0 = tid; i0 < total; i0 += 8 * kTtThreads) {
-      float4 v[8];
-      uint32_t off[8];
+    for (int j = 0; j < n_my; ++j) {
+      const int s = j & 1, tile = blockIdx.x + j * gridDim.x;
+      uint8_t* A = base + s * kTcABytes;
+      if (j >= 2) mbar_wait(&a_empty[s], ((j >> 1) & 1) ^ 1);  // the MMAs of tile j-2 are done reading this buffer
+      int r = tid / kc, c4 = tid - r * kc;
+      for (int i0 = tid; i0 < total; i0 += 8 * 128) {
+        float4 v[8];
+        uint32_t off[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int m = tile * kTtBM + r;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i0 + u * kTtThreads < total && m < p.M)
-          v[u] = __ldg(reinterpret_cast<const float4*>(p.a + static_cast<size_t>(m) * KR + c4 * 4));
-        off[u] = sw128_f32(r, c4 * 4, 128u * 128u);
-        r += dr;
-        c4 += dc;
-        if (c4 >= kc) {
-          c4 -= kc;
-          ++r;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (i0 + u * kTtThreads >= total) break;
-        float4 t = v[u];
-        if (p.relu_in) {
-          t.x = fmaxf(t.x, 0.f);
-          t.y = fmaxf(t.y, 0.f);
-          t.z = fmaxf(t.z, 0.f);
-          t.w = fmaxf(t.w, 0.f);
-        }
-        *reinterpret_cast<uint4*>(A + off[u]) = make_uint4(f32_to_tf32(t.x), f32_to_tf32(t.y), f32_to_tf32(t.z), f32_to_tf32(t.w));
-      }
-    }
-  };
-  auto issue = [&](int buf, int acc_slot) {  // one thread
-    const uint32_t a0 = smem_u32(base + buf * kTcABytes), b0 = smem_u32(Bt);
-    uint32_t acc = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int ks = min(4, (KRp - kb * 32) >> 3);
-      for (int k = 0; k < ks; ++k) {
-        umma_tf32(tmem + acc_slot * 128, make_sw128_desc(a0 + kb * (128 * 128) + k * 32),
-                  make_sw128_desc(b0 + kb * b_kb + k * 32), idesc, acc);
-        acc = 1;
-      }
-    }
-  };
-
-  if (n_my > 0) {
-    load_a(0, blockIdx.x);
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue(0, 0);
-      umma_commit(&bar[0]);
-    }
-  }
-  const int q = warp & 3, h = warp >> 2;
-  const int nch = NOp >> 4, ch_begin = h ? (nch + 1) / 2 : 0, ch_end = h ? nch : (nch + 1) / 2;
-  for (int j = 0; j < n_my; ++j) {
-    const int s = j & 1;
-    const int tile = blockIdx.x + j * gridDim.x;
-    if (j + 1 < n_my) load_a(s ^ 1, tile + gridDim.x);  // that buffer's MMAs (tile j-1) completed: waited on below
-    mbar_wait(&bar[s], (j >> 1) & 1);
-    tc_fence_after();
-    fence_proxy_async_smem();
-    __syncthreads();  // tile j+1 staged by everybody; everybody is done reading accumulator s^1 (tile j-1)
-    if (tid == 0 && j + 1 < n_my) {
-      tc_fence_after();
-      issue(s ^ 1, s ^ 1);
-      umma_commit(&bar[s ^ 1]);
-    }
-    const int m = tile * kTtBM + 32 * q + lane;
-    for (int ch = ch_begin; ch < ch_end; ++ch) {
-      uint32_t r[16];
-      tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + s * 128 + ch * 16, r);
-      tmem_ld_wait();
-      if (m < p.M) {
-        // the (up to 8) reads of mask source / residual first, then the arithmetic and the stores
-        const size_t o0 = static_cast<size_t>(m) * NO + ch * 16;
-        float4 sg[4], rr[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const bool in = ch * 16 + jj * 4 < NO;
-          sg[jj] = (p.mask_src && in) ? __ldg(reinterpret_cast<const float4*>(p.mask_src + o0 + jj * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
-          rr[jj] = (p.residual && in) ? __ldg(reinterpret_cast<const float4*>(p.residual + o0 + jj * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int no = ch * 16 + jj * 4;
-          if (no >= NO) break;
-          float4 v = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
-                                 __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
-          if (p.bias) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + no));
-            v.x += bb.x, v.y += bb.y, v.z += bb.z, v.w += bb.w;
+        for (int u = 0; u < 8; ++u) {
+          const int m = tile * kTtBM + r;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i0 + u * 128 < total && m < p.M)
+            v[u] = __ldg(reinterpret_cast<const float4*>(p.a + static_cast<size_t>(m) * KR + c4 * 4));
+          off[u] = sw128_f32(r, c4 * 4, 128u * 128u);
+          r += dr;
+          c4 += dc;
+          if (c4 >= kc) {
+            c4 -= kc;
+            ++r;
           }
-          v.x = (sg[jj].x > 0.f ? v.x : 0.f) + rr[jj].x;
-          v.y = (sg[jj].y > 0.f ? v.y : 0.f) + rr[jj].y;
-          v.z = (sg[jj].z > 0.f ? v.z : 0.f) + rr[jj].z;
-          v.w = (sg[jj].w > 0.f ? v.w : 0.f) + rr[jj].w;
-          *reinterpret_cast<float4*>(p.c + o0 + jj * 4) = v;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (i0 + u * 128 >= total) break;
+          float4 t = v[u];
+          if (p.relu_in) {
+            t.x = fmaxf(t.x, 0.f);
+            t.y = fmaxf(t.y, 0.f);
+            t.z = fmaxf(t.z, 0.f);
+            t.w = fmaxf(t.w, 0.f);
+          }
+          *reinterpret_cast<uint4*>(A + off[u]) = make_uint4(f32_to_tf32(t.x), f32_to_tf32(t.y), f32_to_tf32(t.z), f32_to_tf32(t.w));
         }
       }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[s]);
     }
-    tc_fence_before();
+  } else if (warp == 8) {
+    // ---- issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(NOp));
+      const uint32_t b0 = smem_u32(Bt);
+      for (int j = 0; j < n_my; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&a_full[s], ph);
+        if (j >= 2) mbar_wait(&acc_empty[s], ph ^ 1);  // the epilogue of tile j-2 has drained this accumulator
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(base + s * kTcABytes);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int ks = min(4, (KRp - kb * 32) >> 3);
+          for (int k = 0; k < ks; ++k) {
+            umma_tf32(tmem + s * 128, make_sw128_desc(a0 + kb * (128 * 128) + k * 32), make_sw128_desc(b0 + kb * b_kb + k * 32),
+                      idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&a_empty[s]);
+        umma_commit(&acc_full[s]);
+      }
+    }
+  } else {
+    // ---- epilogue: warp 4 + q owns TMEM lanes 32 q .. 32 q + 31, a thread one output row
+    const int q = warp & 3;
+    const int nch = NOp >> 4;
+    for (int j = 0; j < n_my; ++j) {
+      const int s = j & 1, tile = blockIdx.x + j * gridDim.x;
+      mbar_wait(&acc_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      const int m = tile * kTtBM + 32 * q + lane;
+      for (int ch = 0; ch < nch; ++ch) {
+        uint32_t r[16];
+        tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + s * 128 + ch * 16, r);
+        tmem_ld_wait();
+        if (m < p.M) {
+          // the (up to 8) reads of mask source / residual first, then the arithmetic and the stores
+          const size_t o0 = static_cast<size_t>(m) * NO + ch * 16;
+          float4 sg[4], rr[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const bool in = ch * 16 + jj * 4 < NO;
+            sg[jj] = (p.mask_src && in) ? __ldg(reinterpret_cast<const float4*>(p.mask_src + o0 + jj * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            rr[jj] = (p.residual && in) ? __ldg(reinterpret_cast<const float4*>(p.residual + o0 + jj * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int no = ch * 16 + jj * 4;
+            if (no >= NO) break;
+            float4 v = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
+                                   __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
+            if (p.bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + no));
+              v.x += bb.x, v.y += bb.y, v.z += bb.z, v.w += bb.w;
+            }
+            v.x = (sg[jj].x > 0.f ? v.x : 0.f) + rr[jj].x;
+            v.y = (sg[jj].y > 0.f ? v.y : 0.f) + rr[jj].y;
+            v.z = (sg[jj].z > 0.f ? v.z : 0.f) + rr[jj].z;
+            v.w = (sg[jj].w > 0.f ? v.w : 0.f) + rr[jj].w;
+            *reinterpret_cast<float4*>(p.c + o0 + jj * 4) = v;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[s]);
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
 // weight gradient: D[n][k] (n on the 128 TMEM lanes) += gY^T[n][m] . act(X)^T[k][m]^T over 64-sample tiles; an extra
 // all-ones row k = K of the B operand makes column K of D the bias gradient.
 constexpr int kTcWgA = 2 * 128 * 128;      // gY^T tile: 2 K-blocks (32 samples each) x 128 rows x 128 B
 constexpr int kTcWgB = 2 * 144 * 128;      // act(X)^T tile: 2 K-blocks x (K + 16 <= 144 rows) x 128 B
-constexpr int kTcWgradSmem = 2 * (kTcWgA + kTcWgB) + 64 + 1024;
+constexpr int kTcWgStages = 3;
+constexpr int kTcWgradSmem = kTcWgStages * (kTcWgA + kTcWgB) + 128 + 1024;
+constexpr int kTcWgradThreads = 288;       // warps 0-7 stage (and transpose) the operand tiles, warp 8 issues the MMAs
 
-__global__ void __launch_bounds__(kTtThreads, 1) tt_wgrad_tc_kernel(const __grid_constant__ TtWgrad p) {
+__global__ void __launch_bounds__(kTcWgradThreads, 1) tt_wgrad_tc_kernel(const __grid_constant__ TtWgrad p) {
   extern __shared__ uint8_t tc_raw[];
   uint8_t* base = tc_raw + ((1024u - (smem_u32(tc_raw) & 1023u)) & 1023u);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(base + 2 * (kTcWgA + kTcWgB));   // [0],[1]: buffer free; [2]: all done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 3);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + kTcWgStages * (kTcWgA + kTcWgB));
+  uint64_t* empty = full + kTcWgStages;
+  uint64_t* done = full + 2 * kTcWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 2 * kTcWgStages + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, K = p.K;
   const int Kp = (K + 1 + 15) & ~15;   // MMA N: the K weight columns + the ones row, rounded up to 16
   const uint32_t b_kb = static_cast<uint32_t>(Kp) * 128u;
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    mbar_init(&bar[2], 1);
+    for (int i = 0; i < kTcWgStages; ++i) {
+      mbar_init(&full[i], 256);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
-  for (int i = tid; i < 2 * (kTcWgA + kTcWgB) / 16; i += kTtThreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  for (int i = tid; i < kTcWgStages * (kTcWgA + kTcWgB) / 16; i += kTcWgradThreads)
+    reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  if (tid < 128) {  // the ones row of both B buffers (never overwritten: the X rows are k < K)
+  if (tid < kTcWgStages * 64) {  // the ones row of every B buffer (never overwritten: the X rows are k < K)
     const int buf = tid >> 6, ml = tid & 63;
     *reinterpret_cast<uint32_t*>(base + buf * (kTcWgA + kTcWgB) + kTcWgA + sw128_f32(K, ml, b_kb)) = 0x3f800000u;
   }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(Kp));
   const int m_begin = blockIdx.x * p.rows_per_cta, m_end = min(p.M, m_begin + p.rows_per_cta);
   const int n_my = m_end > m_begin ? (m_end - m_begin + 63) / 64 : 0;
-  // transposing loads: a lane owns one sample row (conflict-free stores: 32 lanes fill one 128-byte operand row),
-  // warp pair wq = warp >> 1 owns a quarter of the 16-byte column chunks
-  const int rg = warp & 1, wq = warp >> 1;
-  const int ncn = N >> 2, nck = K >> 2;
-  for (int j = 0; j < n_my; ++j) {
-    const int s = j & 1;
-    uint8_t* A = base + s * (kTcWgA + kTcWgB);
-    uint8_t* Bm = A + kTcWgA;
-    if (j >= 2) {
-      mbar_wait(&bar[s], ((j - 2) >> 1) & 1);  // the MMAs of tile j-2 are done with this buffer
-      tc_fence_after();
-    }
-    const int ml = rg * 32 + lane;
-    const int m = m_begin + j * 64 + ml;
-    const bool valid = m < m_end;
-    // all (up to 16) 16-byte loads of this lane's sample row are issued before the first shared-memory store
+
+  if (warp < 8) {
+    // transposing loads: a lane owns one sample row (conflict-free stores: 32 lanes fill one 128-byte operand row),
+    // warp pair wq = warp >> 1 owns a quarter of the 16-byte column chunks
+    const int rg = warp & 1, wq = warp >> 1;
+    const int ncn = N >> 2, nck = K >> 2;
     const int ca0 = (wq * ncn) >> 2, ca1 = ((wq + 1) * ncn) >> 2, cx0 = (wq * nck) >> 2, cx1 = ((wq + 1) * nck) >> 2;
-    float4 va[8], vx[8];
+    const int ml = rg * 32 + lane;
+    for (int j = 0; j < n_my; ++j) {
+      const int s = j % kTcWgStages;
+      const uint32_t use = static_cast<uint32_t>(j / kTcWgStages);
+      uint8_t* A = base + s * (kTcWgA + kTcWgB);
+      uint8_t* Bm = A + kTcWgA;
+      const int m = m_begin + j * 64 + ml;
+      const bool valid = m < m_end;
+      // all (up to 16) 16-byte loads of this lane's sample row are issued before the buffer is even known to be free
+      float4 va[8], vx[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid && ca0 + u < ca1) va[u] = __ldg(reinterpret_cast<const float4*>(p.gy + static_cast<size_t>(m) * N + (ca0 + u) * 4));
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      vx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid && cx0 + u < cx1) vx[u] = __ldg(reinterpret_cast<const float4*>(p.x + static_cast<size_t>(m) * K + (cx0 + u) * 4));
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c4 = ca0 + u;
-      if (c4 >= ca1) break;
-      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 0, ml, 128u * 128u)) = f32_to_tf32(va[u].x);
-      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 1, ml, 128u * 128u)) = f32_to_tf32(va[u].y);
-      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 2, ml, 128u * 128u)) = f32_to_tf32(va[u].z);
-      *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 3, ml, 128u * 128u)) = f32_to_tf32(va[u].w);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c4 = cx0 + u;
-      if (c4 >= cx1) break;
-      float4 v = vx[u];
-      if (p.relu_in) {
-        v.x = fmaxf(v.x, 0.f);
-        v.y = fmaxf(v.y, 0.f);
-        v.z = fmaxf(v.z, 0.f);
-        v.w = fmaxf(v.w, 0.f);
+      for (int u = 0; u < 8; ++u) {
+        va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && ca0 + u < ca1) va[u] = __ldg(reinterpret_cast<const float4*>(p.gy + static_cast<size_t>(m) * N + (ca0 + u) * 4));
       }
-      *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 0, ml, b_kb)) = f32_to_tf32(v.x);
-      *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 1, ml, b_kb)) = f32_to_tf32(v.y);
-      *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 2, ml, b_kb)) = f32_to_tf32(v.z);
-      *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 3, ml, b_kb)) = f32_to_tf32(v.w);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        vx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && cx0 + u < cx1) vx[u] = __ldg(reinterpret_cast<const float4*>(p.x + static_cast<size_t>(m) * K + (cx0 + u) * 4));
+      }
+      if (use > 0) mbar_wait(&empty[s], (use & 1) ^ 1);  // the MMAs of tile j - stages are done with this buffer
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c4 = ca0 + u;
+        if (c4 >= ca1) break;
+        *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 0, ml, 128u * 128u)) = f32_to_tf32(va[u].x);
+        *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 1, ml, 128u * 128u)) = f32_to_tf32(va[u].y);
+        *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 2, ml, 128u * 128u)) = f32_to_tf32(va[u].z);
+        *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 3, ml, 128u * 128u)) = f32_to_tf32(va[u].w);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c4 = cx0 + u;
+        if (c4 >= cx1) break;
+        float4 v = vx[u];
+        if (p.relu_in) {
+          v.x = fmaxf(v.x, 0.f);
+          v.y = fmaxf(v.y, 0.f);
+          v.z = fmaxf(v.z, 0.f);
+          v.w = fmaxf(v.w, 0.f);
+        }
+        *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 0, ml, b_kb)) = f32_to_tf32(v.x);
+        *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 1, ml, b_kb)) = f32_to_tf32(v.y);
+        *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 2, ml, b_kb)) = f32_to_tf32(v.z);
+        *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 3, ml, b_kb)) = f32_to_tf32(v.w);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&full[s]);
     }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
+    if (n_my > 0) {
+      mbar_wait(done, 0);
       tc_fence_after();
-      const uint32_t a0 = smem_u32(A), b0 = smem_u32(Bm);
+      const int q = warp & 3, h = warp >> 2;
+      const int n = 32 * q + lane;
+      const int nch = Kp >> 4, ch_begin = h ? (nch + 1) / 2 : 0, ch_end = h ? nch : (nch + 1) / 2;
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        uint32_t r[16];
+        tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + ch * 16, r);
+        tmem_ld_wait();
+        if (n < N) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int k = ch * 16 + jj;
+            if (k < K)
+              atomicAdd(p.gw + static_cast<size_t>(n) * K + k, __uint_as_float(r[jj]));
+            else if (k == K && p.gb)
+              atomicAdd(p.gb + n, __uint_as_float(r[jj]));
+          }
+        }
+      }
+    }
+  } else if (lane == 0) {
+    const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(Kp));
+    for (int j = 0; j < n_my; ++j) {
+      const int s = j % kTcWgStages;
+      mbar_wait(&full[s], (j / kTcWgStages) & 1);
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(base + s * (kTcWgA + kTcWgB)), b0 = a0 + kTcWgA;
       for (int kb = 0; kb < 2; ++kb)
         for (int k = 0; k < 4; ++k)
           umma_tf32(tmem, make_sw128_desc(a0 + kb * (128 * 128) + k * 32), make_sw128_desc(b0 + kb * b_kb + k * 32), idesc,
                     (j | kb | k) ? 1u : 0u);
-      umma_commit(&bar[s]);
-      if (j == n_my - 1) umma_commit(&bar[2]);
-    }
-  }
-  if (n_my > 0) {
-    mbar_wait(&bar[2], 0);
-    tc_fence_after();
-    const int q = warp & 3, h = warp >> 2;
-    const int n = 32 * q + lane;
-    const int nch = Kp >> 4, ch_begin = h ? (nch + 1) / 2 : 0, ch_end = h ? nch : (nch + 1) / 2;
-    for (int ch = ch_begin; ch < ch_end; ++ch) {
-      uint32_t r[16];
-      tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + ch * 16, r);
-      tmem_ld_wait();
-      if (n < N) {
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const int k = ch * 16 + jj;
-          if (k < K)
-            atomicAdd(p.gw + static_cast<size_t>(n) * K + k, __uint_as_float(r[jj]));
-          else if (k == K && p.gb)
-            atomicAdd(p.gb + n, __uint_as_float(r[jj]));
-        }
-      }
+      umma_commit(&empty[s]);
+      if (j == n_my - 1) umma_commit(done);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
 // ----------------------------------------------------------------------------- SH-16 of the view direction
@@ -745,7 +768,7 @@ int njf_train_linear(const float* a, const float* w, const float* bias, const fl
   const int grid = std::min((M + kTtBM - 1) / kTtBM, tt_sms());
   if (tensor_cores) {
     if (tt_set_smem(tt_gemm_tc_kernel, kTcGemmSmem)) return 1;
-    tt_gemm_tc_kernel<<<grid, kTtThreads, kTcGemmSmem, static_cast<cudaStream_t>(stream)>>>(p);
+    tt_gemm_tc_kernel<<<grid, kTcGemmThreads, kTcGemmSmem, static_cast<cudaStream_t>(stream)>>>(p);
     NJF_CUDA(cudaGetLastError());
     count_launch();
     return 0;
@@ -774,7 +797,7 @@ int njf_train_linear_wgrad(const float* gy, const float* x, int M, int N, int K,
     const int grid_tc = std::min(chunks, tt_sms());
     TtWgrad ptc{gy, x, gw, gb, M, N, K, relu_in, ((chunks + grid_tc - 1) / grid_tc) * 64};
     if (tt_set_smem(tt_wgrad_tc_kernel, kTcWgradSmem)) return 1;
-    tt_wgrad_tc_kernel<<<grid_tc, kTtThreads, kTcWgradSmem, st>>>(ptc);
+    tt_wgrad_tc_kernel<<<grid_tc, kTcWgradThreads, kTcWgradSmem, st>>>(ptc);
     NJF_CUDA(cudaGetLastError());
     count_launch();
     return 0;
