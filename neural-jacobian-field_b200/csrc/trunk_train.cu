@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __g
   const int n_my = (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp < 4) {
-    // ---- loaders: 128 threads, eight 16-byte loads in flight per thread before the first shared-memory store
+    // ---- loaders: 128 threads, sixteen 16-byte loads in flight per thread before the first shared-memory store
     const int dr = 128 / kc, dc = 128 - dr * kc;
     const int total = kTtBM * kc;
     for (int j = 0; j < n_my; ++j) {
@@ -429,11 +429,11 @@ __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __g
       uint8_t* A = base + s * kTcABytes;
       if (j >= 2) mbar_wait(&a_empty[s], ((j >> 1) & 1) ^ 1);  // the MMAs of tile j-2 are done reading this buffer
       int r = tid / kc, c4 = tid - r * kc;
-      for (int i0 = tid; i0 < total; i0 += 8 * 128) {
-        float4 v[8];
-        uint32_t off[8];
+      for (int i0 = tid; i0 < total; i0 += 16 * 128) {
+        float4 v[16];
+        uint32_t off[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
           const int m = tile * kTtBM + r;
           v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (i0 + u * 128 < total && m < p.M)
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __g
           }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
           if (i0 + u * 128 >= total) break;
           float4 t = v[u];
           if (p.relu_in) {
@@ -496,22 +496,31 @@ __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __g
       mbar_wait(&acc_full[s], (j >> 1) & 1);
       tc_fence_after();
       const int m = tile * kTtBM + 32 * q + lane;
-      for (int ch = 0; ch < nch; ++ch) {
-        uint32_t r[16];
-        tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + s * 128 + ch * 16, r);
-        tmem_ld_wait();
-        if (m < p.M) {
-          // the (up to 8) reads of mask source / residual first, then the arithmetic and the stores
-          const size_t o0 = static_cast<size_t>(m) * NO + ch * 16;
-          float4 sg[4], rr[4];
+      for (int ch = 0; ch < nch; ch += 2) {   // 32 columns per step: 16 mask / residual reads in flight per thread
+        const bool two = ch + 1 < nch;
+        uint32_t r[32];
+        {
+          uint32_t r0[16], r1[16];
+          tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + s * 128 + ch * 16, r0);
+          if (two) tmem_ld16(tmem + (static_cast<uint32_t>(32 * q) << 16) + s * 128 + ch * 16 + 16, r1);
+          tmem_ld_wait();
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
+          for (int i = 0; i < 16; ++i) {
+            r[i] = r0[i];
+            r[16 + i] = two ? r1[i] : 0u;
+          }
+        }
+        if (m < p.M) {
+          const size_t o0 = static_cast<size_t>(m) * NO + ch * 16;
+          float4 sg[8], rr[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
             const bool in = ch * 16 + jj * 4 < NO;
             sg[jj] = (p.mask_src && in) ? __ldg(reinterpret_cast<const float4*>(p.mask_src + o0 + jj * 4)) : make_float4(1.f, 1.f, 1.f, 1.f);
             rr[jj] = (p.residual && in) ? __ldg(reinterpret_cast<const float4*>(p.residual + o0 + jj * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
+          for (int jj = 0; jj < 8; ++jj) {
             const int no = ch * 16 + jj * 4;
             if (no >= NO) break;
             float4 v = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
