@@ -292,3 +292,47 @@ def test_pose_interpolation_and_camera_rig_conventions():
     k[:2] /= torch.tensor([cams[7]["w"], cams[7]["h"]])[:, None].float()   # dataset.py:283-294
     assert torch.allclose(pair.trgt_intrinsics[0], k)
     assert torch.allclose(pair.trgt_intrinsics_px, C.denormalize_intrinsics(pair.trgt_intrinsics, width=640, height=480))
+
+
+def test_trunk_training_host_pieces():
+    """The torch-level pieces of njf_b200/train_trunk.py and precise.py that need no kernel (transmittance weights,
+    projection, trunc_exp backward, state-dict trunk views) against the oracle, the argument validation of the
+    training entry points, and the absence of a CPU path."""
+    import ctypes
+
+    from helpers import O
+    from njf_b200 import _lib, precise, train_trunk as TT
+    from njf_b200.model import CameraInput, Model, RenderingInput, RobotInput
+
+    g = torch.Generator().manual_seed(0)
+    deltas = torch.rand(2, 5, 9, 1, generator=g) * 0.1
+    deltas[0, 0, 3] = 0.0
+    sig = torch.rand(2, 5, 9, 1, generator=g) * 30
+    torch.testing.assert_close(TT.transmittance_weights(deltas, sig), O.transmittance_weights(deltas, sig), rtol=0, atol=0)
+    p = torch.randn(2, 7, 3, generator=g) + torch.tensor([0.0, 0.0, 3.0])
+    c2w = torch.stack([synth.relative_target_pose(1), synth.relative_target_pose(2)])
+    k = synth.normalized_intrinsics(**synth.ALLEGRO_INTRINSICS_PX)[None].repeat(2, 1, 1)
+    torch.testing.assert_close(TT.project(p, torch.inverse(c2w), k), O.project_px(p, c2w, k), rtol=1e-5, atol=1e-6)
+    x = torch.tensor([-20.0, -1.0, 0.5, 20.0], requires_grad=True)
+    TT._TruncExp.apply(x).sum().backward()   # activations.py:23-26: gradient exp(clamp(x, -15, 15))
+    torch.testing.assert_close(x.grad, torch.exp(torch.clamp(x.detach(), -15, 15)))
+    sd = synth.synth_state_dict(synth.field_shapes("jacobian_mlp", 6, n_proposal=2), 3)
+    t = precise.trunk_from_state_dict(sd, "proposal_networks.1.density_head", "cpu")
+    assert len(t.blocks) == 5 and len(t.lin_z) == 3 and t.lin_in.weight.shape == (128, 63) and t.lin_out.weight.shape == (1, 128)
+    assert TT.lin_z_maps(t, torch.zeros(1, 2, 3, 512)).shape == (1, 2, 3, 384)
+    L = TT._declare()
+    err = lambda: L.njf_last_error().decode()
+    assert L.njf_train_linear(None, None, None, None, None, None, 8, 8, 8, 1, 0, 0, None) != 0 and "null" in err()
+    one = ctypes.c_void_p(16)
+    assert L.njf_train_linear(one, one, None, None, None, one, 8, 130, 8, 1, 0, 0, None) != 0 and "multiples of 4" in err()
+    assert L.njf_train_linear_wgrad(one, one, 8, 6, 8, 0, one, None, 0, None) != 0 and "multiples of 4" in err()
+    assert L.njf_train_gather(one, one, one, 8, 384, 128, 100, one, None) != 0 and "multiple of 128" in err()
+    assert L.njf_train_scatter(one, one, one, 8, 384, 300, 128, one, None) != 0
+    assert L.njf_train_sh16(one, 4, 7, 1, one, None) != 0 and "convention" in err()
+    assert L.njf_train_sample_setup(one, one, one, 0, 4, 2, 2, one, one, one, None) != 0
+    # perception-phase forward on a CPU model: no fallback
+    m = Model(_cfg()).train()
+    cam = CameraInput(torch.rand(1, 3, 16, 24), torch.eye(4)[None], torch.eye(3)[None], torch.eye(4)[None], torch.eye(3)[None])
+    with pytest.raises(_lib.NjfError):
+        m.forward(cam, RenderingInput(torch.zeros(1, 4, 3), torch.ones(1, 4, 3), torch.tensor([0.5]), torch.tensor([2.0])),
+                  RobotInput(torch.zeros(1, 8)))
