@@ -147,15 +147,20 @@ def test_inverse_dynamics_gauss_newton(head, A):
     np.testing.assert_allclose(sol.cpu().numpy(), u_true.cpu().numpy(), atol=2e-3 * float(u_true.abs().max()) + 1e-4)
 
 
-def test_training_mode_is_rejected_loudly():
+def test_training_mode_forward_carries_gradients():
+    """Model.forward in .train() mode with every parameter trainable (the perception phase): ModelTrainingOutput is
+    filled and the outputs carry autograd history (parity of the gradients: tests/test_gpu_train_trunks.py)."""
     m, _ = _model("jacobian_transformer", 8, (16,), 16)
     from njf_b200.model import CameraInput, RenderingInput, RobotInput
 
     sc = _scene(8)
     m.train()
-    with pytest.raises(NotImplementedError):
-        m.forward(CameraInput(sc["img"], sc["ctxt"], sc["K"], sc["trgt"], sc["kpx"]),
-                  RenderingInput(sc["o"], sc["d"], sc["zn"], sc["zf"]), RobotInput(sc["act"]))
+    out = m.forward(CameraInput(sc["img"], sc["ctxt"], sc["K"], sc["trgt"], sc["kpx"]),
+                    RenderingInput(sc["o"], sc["d"], sc["zn"], sc["zf"]), RobotInput(sc["act"]))
+    assert out.training_output is not None and len(out.training_output.weights_list) == 2
+    assert out.standard_output.rgb.requires_grad and out.standard_output.depth.requires_grad
+    out.standard_output.rgb.sum().backward()
+    assert m.decoder.color_head[0].weight.grad is not None and m.encoder.model.conv1.weight.grad is not None
 
 
 @pytest.mark.parametrize("head,A", [("jacobian_transformer", 8), ("jacobian_mlp", 6)])
