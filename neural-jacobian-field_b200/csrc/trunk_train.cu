@@ -365,10 +365,14 @@ __device__ __forceinline__ uint32_t sw128_f32(uint32_t row, uint32_t col, uint32
 
 constexpr int kTcABytes = 4 * 128 * 128;  // one A buffer: 4 K-blocks x 128 rows x 128 B
 constexpr int kTcGemmSmem = 3 * kTcABytes + 128 + 1024;
-constexpr int kTcGemmThreads = 288;       // warps 0-3 stage A tiles, warps 4-7 run the epilogue, warp 8 issues the MMAs
+constexpr int kTcGemmThreads = 480;       // warps 0-5 stage A tiles, warps 6-13 run the epilogue, warp 14 issues the MMAs
+constexpr int kTcLoadGroup = 96;          // threads per loader group (15 warps = at most 4 per SM sub-partition: 128 registers each)
 
 // Warp-specialised: the three roles only meet at mbarriers (a_full / a_empty per A buffer, acc_full / acc_empty per
 // accumulator), so the global loads of tile j+1, the MMAs of tile j and the stores of tile j-1 are all in flight.
+// Loaders and epilogue warps each work as TWO groups of four warps that take alternate tiles (group g owns A buffer g /
+// accumulator g): a group is latency-bound on its own loads (issue 16 loads, wait, store), so two groups keep two
+// tiles' worth of requests in flight and one group's shared-memory / global stores overlap the other's load latency.
 __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __grid_constant__ TtGemm p) {
   extern __shared__ uint8_t tc_raw[];
   uint8_t* base = tc_raw + ((1024u - (smem_u32(tc_raw) & 1023u)) & 1023u);
@@ -384,14 +388,14 @@ __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __g
   const uint32_t b_kb = static_cast<uint32_t>(NOp) * 128u;
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 128);
+      mbar_init(&a_full[i], kTcLoadGroup);
       mbar_init(&a_empty[i], 1);
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], 128);
     }
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  if (warp == 14) tmem_alloc(tmem_slot, 256);
   for (int i = tid; i < 3 * kTcABytes / 16; i += kTcGemmThreads) reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   if (p.trans_w) {  // B[no][kr] = W[no][kr]
@@ -420,23 +424,24 @@ __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __g
   const int ntiles = (p.M + kTtBM - 1) / kTtBM;
   const int n_my = (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
-  if (warp < 4) {
-    // ---- loaders: 128 threads, sixteen 16-byte loads in flight per thread before the first shared-memory store
-    const int dr = 128 / kc, dc = 128 - dr * kc;
+  if (warp < 6) {
+    // ---- loaders: two groups of 96 threads, sixteen 16-byte loads in flight per thread before the first store
+    const int grp = warp / 3, ltid = tid - grp * kTcLoadGroup;
+    const int dr = kTcLoadGroup / kc, dc = kTcLoadGroup - dr * kc;
     const int total = kTtBM * kc;
-    for (int j = 0; j < n_my; ++j) {
-      const int s = j & 1, tile = blockIdx.x + j * gridDim.x;
+    for (int j = grp; j < n_my; j += 2) {
+      const int s = grp, tile = blockIdx.x + j * gridDim.x;
       uint8_t* A = base + s * kTcABytes;
       if (j >= 2) mbar_wait(&a_empty[s], ((j >> 1) & 1) ^ 1);  // the MMAs of tile j-2 are done reading this buffer
-      int r = tid / kc, c4 = tid - r * kc;
-      for (int i0 = tid; i0 < total; i0 += 16 * 128) {
+      int r = ltid / kc, c4 = ltid - r * kc;
+      for (int i0 = ltid; i0 < total; i0 += 16 * kTcLoadGroup) {
         float4 v[16];
         uint32_t off[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const int m = tile * kTtBM + r;
           v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i0 + u * 128 < total && m < p.M)
+          if (i0 + u * kTcLoadGroup < total && m < p.M)
             v[u] = __ldg(reinterpret_cast<const float4*>(p.a + static_cast<size_t>(m) * KR + c4 * 4));
           off[u] = sw128_f32(r, c4 * 4, 128u * 128u);
           r += dr;
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __g
         }
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          if (i0 + u * 128 >= total) break;
+          if (i0 + u * kTcLoadGroup >= total) break;
           float4 t = v[u];
           if (p.relu_in) {
             t.x = fmaxf(t.x, 0.f);
@@ -462,7 +467,7 @@ __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __g
       fence_proxy_async_smem();
       mbar_arrive(&a_full[s]);
     }
-  } else if (warp == 8) {
+  } else if (warp == 14) {
     // ---- issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(NOp));
@@ -488,11 +493,12 @@ __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __g
       }
     }
   } else {
-    // ---- epilogue: warp 4 + q owns TMEM lanes 32 q .. 32 q + 31, a thread one output row
-    const int q = warp & 3;
+    // ---- epilogue: two groups of four warps; warp q of a group owns TMEM lanes 32 q .. 32 q + 31, a thread one output row
+    const int ew = warp - 6;   // 0..7
+    const int q = warp & 3, grp = ew >> 2;
     const int nch = NOp >> 4;
-    for (int j = 0; j < n_my; ++j) {
-      const int s = j & 1, tile = blockIdx.x + j * gridDim.x;
+    for (int j = grp; j < n_my; j += 2) {
+      const int s = grp, tile = blockIdx.x + j * gridDim.x;
       mbar_wait(&acc_full[s], (j >> 1) & 1);
       tc_fence_after();
       const int m = tile * kTtBM + 32 * q + lane;
@@ -543,7 +549,7 @@ __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __g
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 256);
+  if (warp == 14) tmem_dealloc(tmem, 256);
 }
 
 // weight gradient: D[n][k] (n on the 128 TMEM lanes) += gY^T[n][m] . act(X)^T[k][m]^T over 64-sample tiles; an extra
