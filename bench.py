@@ -587,6 +587,7 @@ def main():
     e2e_steps = max(3, min(args.steps, 10))
     te = float("nan")
     t_enc = None
+    half_leg = None
     with torch.no_grad():
         if not args.no_e2e:
             for _ in range(3):
@@ -607,6 +608,29 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             t_enc = e0.elapsed_time(e1) / 5
+            if world == 1 and not args.no_extras:
+                # the same call with the opt-in fp16 NHWC encoder (Model.encoder_half), for the record
+                try:
+                    model.encoder_half = True
+                    for _ in range(3):
+                        e2e_step()
+                    torch.cuda.synchronize()
+                    t0h = time.perf_counter()
+                    for _ in range(e2e_steps):
+                        e2e_step()
+                    torch.cuda.synchronize()
+                    te_half = (time.perf_counter() - t0h) / e2e_steps * 1e3
+                    e0.record()
+                    for _ in range(5):
+                        model.encoder.forward_nhwc_half(img_d)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    half_leg = {"ms_per_step": te_half, "value": R / (te_half * 1e-3), "encoder_ms": e0.elapsed_time(e1) / 5,
+                                "note": "Model.encoder_half = True: encoder under fp16 autocast, njf_hoist_features_nhwc16"}
+                except Exception as ex:  # noqa: BLE001 -- an extra leg must not break the headline line
+                    half_leg = {"error": repr(ex)[:300]}
+                finally:
+                    model.encoder_half = False
     te = max_over_ranks(te, dev, dist)
     e2e_value = world * R * e2e_steps / te
     h2d = world * sum(hs[k].numel() * 4 for k in hs)      # every rank copies its view's inputs in
@@ -673,7 +697,8 @@ def main():
                 "ms_per_step": te / e2e_steps * 1e3, "encoder_ms": t_enc,
                 "path": "Model.forward(compute_vis_features=True), one CUDA-graph launch per frame (encoder + hoist + render), "
                         "pinned host inputs, rgb/depth/flow/Jbar/p/p' read back to pinned host memory"
-                        + ("; per-rank frames gathered to rank 0 first" if world > 1 else "")},
+                        + ("; per-rank frames gathered to rank 0 first" if world > 1 else ""),
+                "half_encoder": half_leg},
         "gpu_launches": launches,
         "clocks": clk,
     }

@@ -87,6 +87,11 @@ int njf_hoist_features(const NjfField* f, const float* feat_nchw, int B, int Hf,
  * a rank of a ray-sharded multi-view call encodes and hoists only the views its ray range touches */
 int njf_hoist_features_views(const NjfField* f, const float* feat_nchw, int B_local, int view0, int B_total, int Hf,
                              int Wf, void* maps_out, void* stream);
+/* The same from a channels-last HALF-PRECISION encoder output: feat [B_local][Hf*Wf][512] fp16 (NHWC,
+ * 16-byte aligned) -- already the K-major operand layout, so the kernel copies 16-byte chunks instead of transposing
+ * and converting, and reads half the bytes. */
+int njf_hoist_features_nhwc16(const NjfField* f, const void* feat_nhwc_f16, int B_local, int view0, int B_total, int Hf,
+                              int Wf, void* maps_out, void* stream);
 
 /* ---- cameras ---------------------------------------------------------------------------------- */
 typedef struct NjfCameras {

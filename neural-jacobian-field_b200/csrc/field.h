@@ -57,6 +57,6 @@ struct NjfField {
 // hoist_tc.cu
 int njf_hoist_build(NjfField* f, const std::vector<float>& w, const std::vector<float>& b);
 int njf_hoist_launch(const NjfField* f, const float* feat_nchw, int B, int Hf, int Wf, void* maps_out,
-                     cudaStream_t stream, int view0 = 0, int B_total = -1);
+                     cudaStream_t stream, int view0 = 0, int B_total = -1, const void* feat_nhwc_f16 = nullptr);
 // xf_head.cu (prog / blob / A are taken from the field)
 int njf_xf_launch(const NjfField* f, const njf::XfParams& params, cudaStream_t stream);

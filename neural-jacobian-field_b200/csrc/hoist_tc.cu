@@ -29,13 +29,15 @@ struct HoistJob {
   int bias_off;         // offset into the hoist bias vector
 };
 struct HoistParams {
-  const float* feat;    // [B][512][HW]
+  const float* feat;    // [B][512][HW] fp32 (NCHW), or
+  const __half* feat_h; // [B][HW][512] fp16 (NHWC: what a channels-last half-precision encoder emits; already K-major)
   const uint8_t* wimg;  // packed weight images
   const float* bias;
   int HW;
   HoistJob job[8];
 };
 
+template <bool kNhwcHalf>
 __global__ void __launch_bounds__(128, 1) hoist_tc_kernel(const __grid_constant__ HoistParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -47,7 +49,10 @@ __global__ void __launch_bounds__(128, 1) hoist_tc_kernel(const __grid_constant_
   const int tid = threadIdx.x, warp = tid >> 5;
   const int px = blockIdx.x * 128 + tid;
   const bool live = px < p.HW;
-  const float* F = p.feat + static_cast<size_t>(blockIdx.z) * 512 * p.HW + (live ? px : 0);
+  const float* F = kNhwcHalf ? nullptr : p.feat + static_cast<size_t>(blockIdx.z) * 512 * p.HW + (live ? px : 0);
+  // NHWC fp16: the pixel's 512 channels are contiguous, a K block is 8 ready-made 16-byte chunks of the A row
+  const uint4* Fh = kNhwcHalf ? reinterpret_cast<const uint4*>(p.feat_h + (static_cast<size_t>(blockIdx.z) * p.HW + (live ? px : 0)) * 512)
+                              : nullptr;
   const uint32_t bbytes = static_cast<uint32_t>(job.N) * 128u;
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
@@ -62,9 +67,15 @@ __global__ void __launch_bounds__(128, 1) hoist_tc_kernel(const __grid_constant_
     mbar_arrive_expect_tx(&bars[0], bbytes);
     bulk_g2s(sB, p.wimg + job.w_off, bbytes, &bars[0]);
   }
-  float f[64];
+  float f[kNhwcHalf ? 1 : 64];
+  uint4 fv[kNhwcHalf ? 8 : 1];
+  if constexpr (kNhwcHalf) {
 #pragma unroll
-  for (int c = 0; c < 64; ++c) f[c] = live ? __ldg(F + static_cast<size_t>(c) * p.HW) : 0.f;
+    for (int j = 0; j < 8; ++j) fv[j] = live ? __ldg(Fh + j) : make_uint4(0u, 0u, 0u, 0u);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 64; ++c) f[c] = live ? __ldg(F + static_cast<size_t>(c) * p.HW) : 0.f;
+  }
   uint32_t full_par[2] = {0, 0}, free_par[2] = {0, 0};
   for (int kb = 0; kb < 8; ++kb) {
     const int buf = kb & 1;
@@ -87,16 +98,25 @@ __global__ void __launch_bounds__(128, 1) hoist_tc_kernel(const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         uint4 v;
-        v.x = pack_f16x2(f[8 * j + 0], f[8 * j + 1]);
-        v.y = pack_f16x2(f[8 * j + 2], f[8 * j + 3]);
-        v.z = pack_f16x2(f[8 * j + 4], f[8 * j + 5]);
-        v.w = pack_f16x2(f[8 * j + 6], f[8 * j + 7]);
+        if constexpr (kNhwcHalf) {
+          v = fv[j];
+        } else {
+          v.x = pack_f16x2(f[8 * j + 0], f[8 * j + 1]);
+          v.y = pack_f16x2(f[8 * j + 2], f[8 * j + 3]);
+          v.z = pack_f16x2(f[8 * j + 4], f[8 * j + 5]);
+          v.w = pack_f16x2(f[8 * j + 6], f[8 * j + 7]);
+        }
         *reinterpret_cast<uint4*>(row + ((j ^ (tid & 7)) << 4)) = v;
       }
     }
     if (kb + 1 < 8) {
+      if constexpr (kNhwcHalf) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) f[c] = live ? __ldg(F + static_cast<size_t>((kb + 1) * 64 + c) * p.HW) : 0.f;
+        for (int j = 0; j < 8; ++j) fv[j] = live ? __ldg(Fh + (kb + 1) * 8 + j) : make_uint4(0u, 0u, 0u, 0u);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) f[c] = live ? __ldg(F + static_cast<size_t>((kb + 1) * 64 + c) * p.HW) : 0.f;
+      }
     }
     fence_proxy_async_smem();
     __syncthreads();
@@ -192,18 +212,21 @@ int njf_hoist_build(NjfField* f, const std::vector<float>& w, const std::vector<
 }
 
 int njf_hoist_launch(const NjfField* f, const float* feat_nchw, int B, int Hf, int Wf, void* maps_out,
-                     cudaStream_t stream, int view0, int B_total) {
+                     cudaStream_t stream, int view0, int B_total, const void* feat_nhwc_f16) {
   int dev = 0;
   cudaGetDevice(&dev);
   static std::atomic<bool> attr[64];  // the opt-in applies to the current device only
   if (dev >= 0 && dev < 64 && !attr[dev].load(std::memory_order_acquire)) {
-    NJF_CUDA(cudaFuncSetAttribute(hoist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NJF_CUDA(cudaFuncSetAttribute(hoist_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(kHoistSmem)));
+    NJF_CUDA(cudaFuncSetAttribute(hoist_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(kHoistSmem)));
     attr[dev].store(true, std::memory_order_release);
   }
   if (B_total < 0) B_total = B;
   HoistParams p{};
   p.feat = feat_nchw;
+  p.feat_h = static_cast<const __half*>(feat_nhwc_f16);
   p.wimg = f->d_hoist_img;
   p.bias = f->d_hoist_b;
   p.HW = Hf * Wf;
@@ -225,7 +248,10 @@ int njf_hoist_launch(const NjfField* f, const float* feat_nchw, int B, int Hf, i
     d.bias_off = j.bias_off;
   }
   dim3 grid((p.HW + 127) / 128, nj, B);
-  hoist_tc_kernel<<<grid, 128, kHoistSmem, stream>>>(p);
+  if (feat_nhwc_f16)
+    hoist_tc_kernel<true><<<grid, 128, kHoistSmem, stream>>>(p);
+  else
+    hoist_tc_kernel<false><<<grid, 128, kHoistSmem, stream>>>(p);
   njf::count_launch();
   NJF_CUDA(cudaGetLastError());
   return 0;

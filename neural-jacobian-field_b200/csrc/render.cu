@@ -1189,6 +1189,14 @@ extern "C" int njf_hoist_features_views(const NjfField* f, const float* feat_nch
   return njf_hoist_launch(f, feat_nchw, B_local, Hf, Wf, maps_out, static_cast<cudaStream_t>(stream_), view0, B_total);
 }
 
+extern "C" int njf_hoist_features_nhwc16(const NjfField* f, const void* feat_nhwc_f16, int B_local, int view0, int B_total,
+                                         int Hf, int Wf, void* maps_out, void* stream_) {
+  if (!f || !feat_nhwc_f16 || !maps_out) NJF_FAIL("njf_hoist_features_nhwc16: null argument");
+  if (B_local < 1 || view0 < 0 || view0 + B_local > B_total) NJF_FAIL("njf_hoist_features_nhwc16: views [%d, %d) outside %d", view0, view0 + B_local, B_total);
+  if (reinterpret_cast<uintptr_t>(feat_nhwc_f16) & 15) NJF_FAIL("njf_hoist_features_nhwc16: the feature map must be 16-byte aligned");
+  return njf_hoist_launch(f, nullptr, B_local, Hf, Wf, maps_out, static_cast<cudaStream_t>(stream_), view0, B_total, feat_nhwc_f16);
+}
+
 extern "C" int njf_proposal_pass(const NjfField* f, const NjfCameras* cams, const NjfRenderArgs* a, int level,
                                  const float* bins_in, int bins_in_stride, void* stream_) {
   if (check_args(f, cams, a)) return 1;

@@ -68,6 +68,8 @@ def _declare():
     L.njf_hoisted_bytes.argtypes = [c_void_p, c_int, c_int, c_int]
     L.njf_hoist_features.restype = c_int
     L.njf_hoist_features.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    L.njf_hoist_features_nhwc16.restype = c_int
+    L.njf_hoist_features_nhwc16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     L.njf_hoist_features_views.restype = c_int
     L.njf_hoist_features_views.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
     for name in ("njf_render_forward", "njf_finish_pass"):
@@ -209,6 +211,23 @@ class Field:
         nbytes = L.njf_hoisted_bytes(self._h, B, Hf, Wf)
         maps = torch.empty(nbytes, dtype=torch.uint8, device=feat_nchw.device)
         _lib.check(L.njf_hoist_features(self._h, feat_nchw.data_ptr(), B, Hf, Wf, maps.data_ptr(), stream_ptr()))
+        return maps
+
+    def hoist_nhwc16(self, feat_nhwc: torch.Tensor, view0: int = 0, n_views_total: Optional[int] = None,
+                     maps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(B,Hf,Wf,512) fp16 NHWC encoder output (EncoderResnet.forward_nhwc_half) -> hoisted maps."""
+        L = _declare()
+        assert feat_nhwc.is_cuda and feat_nhwc.dtype == torch.float16
+        self._check_device(feat_nhwc, "feature map")
+        feat_nhwc = feat_nhwc.contiguous()
+        Bl, Hf, Wf, C = feat_nhwc.shape
+        if C != 512:
+            raise _lib.NjfError(f"feature map has {C} channels, kernels are built for 512")
+        n_views_total = Bl if n_views_total is None else int(n_views_total)
+        if maps is None:
+            maps = torch.empty(L.njf_hoisted_bytes(self._h, n_views_total, Hf, Wf), dtype=torch.uint8, device=feat_nhwc.device)
+        _lib.check(L.njf_hoist_features_nhwc16(self._h, feat_nhwc.data_ptr(), Bl, int(view0), n_views_total, Hf, Wf,
+                                               maps.data_ptr(), stream_ptr()))
         return maps
 
     def hoist_views(self, feat_nchw: torch.Tensor, view0: int, n_views_total: int,

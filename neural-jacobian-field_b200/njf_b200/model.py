@@ -249,8 +249,13 @@ class _FrameGraph:
 
     def _body(self, model, fld, vis) -> RenderResult:
         i = self.inp
-        feats = model.encoder.forward(i["image"]).float().contiguous()
-        maps = fld.hoist(feats)
+        if getattr(model, "encoder_half", False):
+            fh = model.encoder.forward_nhwc_half(i["image"])
+            maps = fld.hoist_nhwc16(fh)
+            feats = fh.permute(0, 3, 1, 2)
+        else:
+            feats = model.encoder.forward(i["image"]).float().contiguous()
+            maps = fld.hoist(feats)
         cams, keep = api.make_cameras(i["ctxt_c2w"], i["ctxt_k"], i["trgt_c2w"], i["trgt_k"], self.dev)
         Hf, Wf = feats.shape[-2:]
         res = render(fld, maps, Hf, Wf, cams, i["origins"], i["dirs"], i["z_near"], i["z_far"], i["action"], self.s_prop,
@@ -289,6 +294,9 @@ class Model(nn.Module):
         # eval-mode proposal levels in fp32 (njf_b200/precise.py): sample indices follow the fp32 reference to ~1e-5
         # instead of ~2e-3, at ~10x the frame time; the final level stays on the fused tcgen05 field pass
         self.precise_proposal = False
+        # eval-mode encoder under fp16 autocast, emitting the NHWC fp16 map the hoist kernel copies straight into its
+        # operand tiles; features differ from the fp32 / TF32 encoder at the 1e-3 level
+        self.encoder_half = False
         self._graphs: Dict[tuple, "_FrameGraph"] = {}
         self.output_device: Optional[torch.device] = None   # None: results go back to where the rays came from (reference)
         self.jitter_generator: Optional[torch.Generator] = None   # train-mode stratified jitter (None = torch's global CUDA RNG)
@@ -399,8 +407,13 @@ class Model(nn.Module):
         dev = self._device()
         img = camera_input.input_image.to(dev, non_blocking=True)
         with torch.no_grad():
-            feats = self.encoder.forward(img).float().contiguous()
-            hoisted = self.field().hoist(feats)
+            if getattr(self, "encoder_half", False) and not self.training:
+                fh = self.encoder.forward_nhwc_half(img)
+                hoisted = self.field().hoist_nhwc16(fh)
+                feats = fh.permute(0, 3, 1, 2)   # (B,512,Hf,Wf)-shaped fp16 view; by-product consumers convert on demand
+            else:
+                feats = self.encoder.forward(img).float().contiguous()
+                hoisted = self.field().hoist(feats)
         return PixelEncoding(features=feats, extrinsics=camera_input.ctxt_extrinsics,
                              intrinsics=camera_input.ctxt_intrinsics, action=robot_input.robot_action, hoisted=hoisted)
 
@@ -564,7 +577,7 @@ class Model(nn.Module):
         dev = self._device()
         fld = self.field()
         B, R = rendering_input.origins.shape[:2]
-        key = (tuple(camera_input.input_image.shape), B, R, bool(vis), float(self._anneal),
+        key = (tuple(camera_input.input_image.shape), B, R, bool(vis), float(self._anneal), bool(getattr(self, "encoder_half", False)),
                tuple((p.data_ptr(), p._version) for p in self.encoder.parameters()))
         g = self._graphs.get(key)
         if g is None:

@@ -415,6 +415,15 @@ class EncoderResnet(nn.Module):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
 
+    def forward_nhwc_half(self, rgb: torch.Tensor) -> torch.Tensor:
+        """The same trunk under fp16 autocast, returned as the (B,Hf,Wf,512) fp16 NHWC tensor that
+        njf_hoist_features_nhwc16 consumes.  The convolutions then multiply fp16 operands with fp32
+        accumulation -- the operand precision cuDNN's default TF32 convolutions already have -- and the hoist GEMM,
+        which rounds its input to fp16 anyway, reads the map without a conversion pass."""
+        with torch.autocast("cuda", dtype=torch.float16):
+            f = self.forward(rgb)
+        return f.to(torch.float16).permute(0, 2, 3, 1).contiguous()   # a view when the storage is channels-last
+
     def forward(self, rgb: torch.Tensor) -> torch.Tensor:
         m = self.model
         if rgb.is_cuda:   # NHWC storage: the layout cuDNN's tensor-core convolutions run in natively (values unchanged)

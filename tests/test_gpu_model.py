@@ -240,3 +240,45 @@ def test_validation_video_renderer():
                                 RenderingInput(o, d, sc["zn"].to(DEV), sc["zf"].to(DEV)), RobotInput(sc["act"].to(DEV)))
             ref = out.standard_output.rgb.reshape(1, H, W, 3).permute(0, 3, 1, 2)
             np.testing.assert_allclose(vid["rgb"][:, idx].cpu().numpy(), ref.cpu().numpy(), atol=2e-4)
+
+
+def test_half_precision_encoder_and_nhwc_hoist():
+    """Model.encoder_half: the encoder under fp16 autocast emits the NHWC fp16 map that
+    njf_hoist_features_nhwc16 copies into its operand tiles.  The NHWC kernel path is checked bit for bit against the
+    NCHW fp32 path on the same (fp16-representable) features; the half encoder against the fp32 / TF32 one at the
+    stated tolerance (features 1e-2 of their scale, rgb 5e-3)."""
+    from njf_b200.model import CameraInput, RenderingInput, RobotInput
+
+    s_prop, s_nerf = (32,), 32
+    m, sd = _model("jacobian_transformer", 8, s_prop, s_nerf)
+    sc = _scene(8, H=48, W=64)
+    img = sc["img"].to(DEV)
+    with torch.no_grad():
+        f32 = m.encoder(img).float()
+        fh = m.encoder.forward_nhwc_half(img)
+        assert fh.dtype == torch.float16 and fh.shape == (1, 24, 32, 512) and fh.is_contiguous()
+        scale = float(f32.abs().max())
+        assert float((fh.permute(0, 3, 1, 2).float() - f32).abs().max()) < 1e-2 * scale
+        fld = m.field()
+        a = fld.hoist_nhwc16(fh)
+        b = fld.hoist(fh.permute(0, 3, 1, 2).float().contiguous())
+        assert torch.equal(a, b)
+        # two views into slots of a four-view buffer
+        fh2 = torch.cat([fh, fh.flip(1)], 0).contiguous()
+        nbytes = fld.hoist_nhwc16(fh2, view0=1, n_views_total=4).numel()
+        big = fld.hoist_nhwc16(fh2, view0=1, n_views_total=4, maps=torch.zeros(nbytes, dtype=torch.uint8, device=DEV))
+        ref = fld.hoist_views(fh2.permute(0, 3, 1, 2).float().contiguous(), 1, 4,
+                              maps=torch.zeros(nbytes, dtype=torch.uint8, device=DEV))
+        assert torch.equal(big, ref) and int(big.count_nonzero()) > 0
+        cam = CameraInput(sc["img"], sc["ctxt"], sc["K"], sc["trgt"], sc["kpx"])
+        rin, rob = RenderingInput(sc["o"], sc["d"], sc["zn"], sc["zf"]), RobotInput(sc["act"])
+        full = m.forward(cam, rin, rob, compute_vis_features=True)
+        m.encoder_half = True
+        half = m.forward(cam, rin, rob, compute_vis_features=True)
+        m.cuda_graph = True
+        graphed = m.forward(cam, rin, rob, compute_vis_features=True)
+    np.testing.assert_allclose(half.standard_output.rgb.numpy(), full.standard_output.rgb.numpy(), atol=5e-3)
+    np.testing.assert_allclose(half.standard_output.depth.numpy(), full.standard_output.depth.numpy(), atol=2e-2)
+    jm = float(full.vis_output.action_features.abs().max())
+    np.testing.assert_allclose(half.vis_output.action_features.numpy(), full.vis_output.action_features.numpy(), atol=3e-2 * jm)
+    np.testing.assert_allclose(graphed.standard_output.rgb.numpy(), half.standard_output.rgb.numpy(), atol=1e-6)
