@@ -370,6 +370,20 @@ class Model(nn.Module):
                 return self.field()
         return self._field
 
+    def _field_with_current_trunks(self) -> api.Field:
+        """A packed field whose TRUNKS (proposal networks, density head, colour head) are current while its Jacobian head
+        may be stale: what the MLP head's action phase renders densities / weights / colours with (everything but the
+        head is frozen there, model_wrapper.py:75-85) without re-packing the field after every optimiser step.  The
+        Jacobian outputs of such a render are not used."""
+        if self._field is not None and self._mode() == "regular":
+            is_head = lambda n: n.startswith("decoder.") and "jacobian" in n and "jacobian_head_arm" not in n
+            key = (self._device(), self._mode(), bool(self.sh_fp16_round), self.sh_convention,
+                   tuple((p.data_ptr(), p._version) for n, p in self.named_parameters()
+                         if not n.startswith("encoder.") and not is_head(n)))
+            if self._field_key == key:
+                return self._field
+        return self.field()
+
     def _field_for_head_queries(self) -> api.Field:
         """A packed field whose CROSS-ATTENTION HEAD (query MLP, attention / feed-forward layers, index embedding,
         jacobian_head) is current, whatever the state of the trunks: what the trunk-training forward needs to evaluate

@@ -23,7 +23,7 @@ There is no CPU path: every entry point needs the CUDA library.
 from __future__ import annotations
 
 import ctypes
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 import torch.nn.functional as F
@@ -251,6 +251,11 @@ def forward_train(model, camera_input, rendering_input, robot_input, compute_vis
     head, A = model._head_and_dim()
     arm = model._mode() == "arm"
 
+    if (head == "jacobian_mlp" and not arm and torch.is_grad_enabled()
+            and not any(p.requires_grad for n, p in model.named_parameters() if not n.startswith("decoder.jacobian_head."))):
+        return _forward_train_mlp_head(model, camera_input, robot_input, o, d, zn, zf, action, A, s_prop, s_nerf,
+                                       compute_vis_features)
+
     feats = model.encoder.forward(camera_input.input_image.to(dev)).float()       # (B,512,Hf,Wf), autograd as configured
     Hf, Wf = feats.shape[-2:]
     fmap = feats.permute(0, 2, 3, 1).contiguous()                                  # NHWC view of channels-last storage
@@ -331,3 +336,51 @@ def forward_train(model, camera_input, rendering_input, robot_input, compute_vis
                 jbar=torch.sum(weights * jac, dim=-2) if compute_vis_features else None,
                 steps=steps.squeeze(-1), weights=weights.squeeze(-1), p=p, pw=pw,
                 weights_list=weights_list, bins_list=bins_list, near=near, far=far)
+
+
+def _forward_train_mlp_head(model, camera_input, robot_input, o, d, zn, zf, action, A, s_prop, s_nerf, compute_vis_features):
+    """Action phase of the MLP Jacobian head (models/model_wrapper.py:75-85, 148-163): everything but
+    ``decoder.jacobian_head`` is frozen, so sample placement, densities, weights and colours carry no gradient and come
+    from the FUSED render (same kernels as inference, jittered tables); only the Jacobian trunk runs layer by layer under
+    autograd, at the fused render's final sample positions."""
+    from .render import render
+    from .train import stratified_tables
+
+    dev = o.device
+    r = model.cfg.rendering
+    B, R = o.shape[:2]
+    with torch.no_grad():
+        feats = model.encoder.forward(camera_input.input_image.to(dev)).float().contiguous()
+        Hf, Wf = feats.shape[-2:]
+        fld = model._field_with_current_trunks()
+        maps16 = fld.hoist(feats)
+        cams, keep = api.make_cameras(camera_input.ctxt_extrinsics, camera_input.ctxt_intrinsics,
+                                      camera_input.trgt_extrinsics, camera_input.trgt_intrinsics, dev)
+        cw, ck, tw, tk = keep[:4]
+        bins0, us = stratified_tables(s_prop, s_nerf, B, R, r.single_jitter, dev,
+                                      generator=getattr(model, "jitter_generator", None))
+        res = render(fld, maps16, Hf, Wf, cams, o, d, zn, zf, action.detach().contiguous(), s_prop, s_nerf, vis=True,
+                     sampler_outputs=True, bins0=bins0, us=us, anneal=model._anneal)
+        res._cams = keep
+        near, far = zn[:, None, None], zf[:, None, None]
+        fb = res.level_bins[-1]
+        e = fb * far + (1 - fb) * near
+        starts, ends = e[..., :-1, None], e[..., 1:, None]
+        pos = o[..., None, :] + d[..., None, :] * (starts + ends) / 2
+        enc, pix, tapw = sample_setup(cw, ck, pos.reshape(B, R * s_nerf, 3), Hf, Wf)
+        fmap = feats.permute(0, 2, 3, 1).contiguous()
+        weights = res.weights[..., None]
+    jt = model.decoder.jacobian_head
+    zj = _GatherMaps.apply(lin_z_maps(jt, fmap).reshape(-1, 384), pix, tapw)     # d lin_z through the map GEMM's backward
+    jac = resnet_fc(jt, enc, zj).reshape(B, R, s_nerf, 3 * A)
+    flow_s = torch.einsum("brsad,ba->brsd", jac.reshape(B, R, s_nerf, A, 3), action)
+    p = torch.sum(weights * pos, dim=-2)
+    pw = torch.sum(weights * (pos + flow_s), dim=-2)
+    flow = project(pw, tw, tk) - project(p, tw, tk)
+    if model._steps_since_update > model._update_schedule(model._step) or model._step < 10:
+        model._steps_since_update = 0
+    return dict(rgb=res.rgb, depth=res.depth, flow=flow,
+                jbar=torch.sum(weights * jac, dim=-2) if compute_vis_features else None,
+                steps=res.steps, weights=res.weights, p=p, pw=pw,
+                weights_list=[w[..., None] for w in res.prop_weights] + [weights],
+                bins_list=[bins0] + list(res.level_bins), near=near, far=far)

@@ -7,7 +7,8 @@
   the density head, the colour head and the encoder against torch autograd through the CPU oracle on the same jitter
   tables -- relative L2 error per tensor <= 2e-3 (both sides are fp32; what remains is summation order and the
   occasional PDF-sample tie that falls the other way);
-* action phase with the MLP Jacobian head (model_wrapper.py:75-85, 148-163): the same check for jacobian_head.*.
+* action phase with the MLP Jacobian head (model_wrapper.py:75-85, 148-163): the same check for jacobian_head.* (frozen
+  trunks render on the fused kernels, only the Jacobian trunk runs on the layer kernels; tolerance 1e-2, measured 6e-3).
 """
 import numpy as np
 import pytest
@@ -261,11 +262,16 @@ def test_mlp_head_action_phase_gradients_vs_oracle_autograd():
                            bins0=bins0.cpu(), us=[u.cpu() for u in us])
     ref_loss = _flow_loss(ref["optical_flow"], target, mask)
     ref_loss.backward()
-    np.testing.assert_allclose(float(loss), float(ref_loss), rtol=1e-3)
+    # sample placement, weights and colours of this phase come from the fused (fp16-operand) render, the Jacobian trunk
+    # and its gradients from the fp32 layer kernels: tolerances as in the cross-attention head's action-phase test
+    np.testing.assert_allclose(float(loss), float(ref_loss), rtol=5e-2)
     jm = float(ref["action_features"].abs().max())
     np.testing.assert_allclose(out.vis_output.action_features.detach().numpy(), ref["action_features"].detach().numpy(),
-                               atol=1e-4 * jm)
-    worst = _grad_report(got, {n: w[n].grad for n in got}, 2e-3)
+                               atol=2e-2 * jm)
+    assert not out.standard_output.rgb.requires_grad and out.training_output.weights_list[-1].shape == (B, R, s_nerf, 1)
+    # measured worst 6.2e-3 (lin_in.weight: its input is the positional encoding up to sin(2 pi 512 x), the tensor most
+    # sensitive to the ~0.2 % of samples the fp16 proposal places one bin over)
+    worst = _grad_report(got, {n: w[n].grad for n in got}, 1e-2)
     print(f"MLP-head action-phase gradients, {len(got)} tensors: worst relative L2 error {worst[1]:.2e} ({worst[0]})")
 
 
