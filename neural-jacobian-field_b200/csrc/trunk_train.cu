@@ -552,13 +552,38 @@ __global__ void __launch_bounds__(kTcGemmThreads, 1) tt_gemm_tc_kernel(const __g
   if (warp == 14) tmem_dealloc(tmem, 256);
 }
 
-// weight gradient: D[n][k] (n on the 128 TMEM lanes) += gY^T[n][m] . act(X)^T[k][m]^T over 64-sample tiles; an extra
-// all-ones row k = K of the B operand makes column K of D the bias gradient.
-constexpr int kTcWgA = 2 * 128 * 128;      // gY^T tile: 2 K-blocks (32 samples each) x 128 rows x 128 B
-constexpr int kTcWgB = 2 * 144 * 128;      // act(X)^T tile: 2 K-blocks x (K + 16 <= 144 rows) x 128 B
+// weight gradient: D[n][k] (n on the 128 TMEM lanes) += sum_m gY[m][n] . act(X)[m][k] over 64-sample tiles; an extra
+// all-ones column k = K of the B operand makes column K of D the bias gradient.  Both operands are reduced over the
+// SAMPLE index, i.e. they are needed "MN-major" (the M / N index contiguous in memory) -- exactly how the row-major
+// gY [M][N] and X [M][K] tiles lie in global memory, so the loaders copy coalesced 16-byte chunks (no transposition)
+// into the canonical MN-major SWIZZLE_128B layout (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>):
+//   atom = 4 samples x 128 B (32 consecutive n), 32-byte unit u of sample row r at unit u ^ (r & 3);
+//   atoms of the next 4 samples follow at SBO = 512 B, the next 32 n at LBO = 8 KB (64 samples per tile);
+// one kind::tf32 MMA consumes K = 8 samples = two atoms, so the descriptor start address advances by 1 KB.
+constexpr int kTcWgTile = 64;                            // samples per tile
+constexpr int kTcWgSlab = (kTcWgTile / 4) * 512;         // one 32-column slab of a tile: 8 KB (= LBO)
+constexpr int kTcWgA = 4 * kTcWgSlab;                    // gY tile: 128 n = 4 slabs
+constexpr int kTcWgB = 5 * kTcWgSlab;                    // act(X) tile + ones column: K + 16 <= 144 -> 5 slabs
 constexpr int kTcWgStages = 3;
 constexpr int kTcWgradSmem = kTcWgStages * (kTcWgA + kTcWgB) + 128 + 1024;
-constexpr int kTcWgradThreads = 288;       // warps 0-7 stage (and transpose) the operand tiles, warp 8 issues the MMAs
+constexpr int kTcWgradThreads = 288;       // warps 0-7 stage the operand tiles, warp 8 issues the MMAs
+
+// byte offset of fp32 element (sample r < 64, column c) inside an MN-major tile.  For 32-bit MN-major operands the
+// only layout the tensor core accepts is SWIZZLE_128B_BASE32B (cutlass sm100_common.inl: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout"): atoms of 4 samples x 128 B whose 32-byte units are XOR-swizzled with
+// the sample index (Swizzle<2,5,2> on the byte address: bits [5,7) ^= bits [7,9)).
+__device__ __forceinline__ uint32_t mn128_f32(uint32_t r, uint32_t c) {
+  return (c >> 5) * kTcWgSlab + (r >> 2) * 512u + (r & 3u) * 128u + (((((c & 31u) >> 3) ^ (r & 3u)) << 5) | ((c & 7u) << 2));
+}
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);        // start address
+  d |= static_cast<uint64_t>(kTcWgSlab >> 4) << 16;           // LBO: next 32 columns of the M / N dimension
+  d |= static_cast<uint64_t>(512 >> 4) << 32;                 // SBO: next 4 samples of the reduction dimension
+  d |= static_cast<uint64_t>(1) << 46;                        // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(1) << 61;                        // layout: SWIZZLE_128B_BASE32B
+  return d;
+}
 
 __global__ void __launch_bounds__(kTcWgradThreads, 1) tt_wgrad_tc_kernel(const __grid_constant__ TtWgrad p) {
   extern __shared__ uint8_t tc_raw[];
@@ -569,8 +594,7 @@ __global__ void __launch_bounds__(kTcWgradThreads, 1) tt_wgrad_tc_kernel(const _
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 2 * kTcWgStages + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, K = p.K;
-  const int Kp = (K + 1 + 15) & ~15;   // MMA N: the K weight columns + the ones row, rounded up to 16
-  const uint32_t b_kb = static_cast<uint32_t>(Kp) * 128u;
+  const int Kp = (K + 1 + 15) & ~15;   // MMA N: the K weight columns + the ones column, rounded up to 16
   if (tid == 0) {
     for (int i = 0; i < kTcWgStages; ++i) {
       mbar_init(&full[i], 256);
@@ -581,11 +605,11 @@ __global__ void __launch_bounds__(kTcWgradThreads, 1) tt_wgrad_tc_kernel(const _
   }
   if (warp == 8) tmem_alloc(tmem_slot, 256);
   for (int i = tid; i < kTcWgStages * (kTcWgA + kTcWgB) / 16; i += kTcWgradThreads)
-    reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(base)[i] = make_uint4(0, 0, 0, 0);   // columns past N / K stay zero
   __syncthreads();
-  if (tid < kTcWgStages * 64) {  // the ones row of every B buffer (never overwritten: the X rows are k < K)
-    const int buf = tid >> 6, ml = tid & 63;
-    *reinterpret_cast<uint32_t*>(base + buf * (kTcWgA + kTcWgB) + kTcWgA + sw128_f32(K, ml, b_kb)) = 0x3f800000u;
+  if (tid < kTcWgStages * kTcWgTile) {  // the ones column of every B buffer (never overwritten: the X chunks end at K)
+    const int buf = tid / kTcWgTile, r = tid % kTcWgTile;
+    *reinterpret_cast<uint32_t*>(base + buf * (kTcWgA + kTcWgB) + kTcWgA + mn128_f32(r, K)) = 0x3f800000u;
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -593,59 +617,43 @@ __global__ void __launch_bounds__(kTcWgradThreads, 1) tt_wgrad_tc_kernel(const _
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int m_begin = blockIdx.x * p.rows_per_cta, m_end = min(p.M, m_begin + p.rows_per_cta);
-  const int n_my = m_end > m_begin ? (m_end - m_begin + 63) / 64 : 0;
+  const int n_my = m_end > m_begin ? (m_end - m_begin + kTcWgTile - 1) / kTcWgTile : 0;
 
   if (warp < 8) {
-    // transposing loads: a lane owns one sample row (conflict-free stores: 32 lanes fill one 128-byte operand row),
-    // warp pair wq = warp >> 1 owns a quarter of the 16-byte column chunks
-    const int rg = warp & 1, wq = warp >> 1;
-    const int ncn = N >> 2, nck = K >> 2;
-    const int ca0 = (wq * ncn) >> 2, ca1 = ((wq + 1) * ncn) >> 2, cx0 = (wq * nck) >> 2, cx1 = ((wq + 1) * nck) >> 2;
-    const int ml = rg * 32 + lane;
+    // loaders: warp w copies sample rows 8 w .. 8 w + 7 of the tile, lane = 16-byte chunk of the row (coalesced)
+    const bool has_y = 4 * lane < N, has_x = 4 * lane < K;
     for (int j = 0; j < n_my; ++j) {
       const int s = j % kTcWgStages;
       const uint32_t use = static_cast<uint32_t>(j / kTcWgStages);
       uint8_t* A = base + s * (kTcWgA + kTcWgB);
       uint8_t* Bm = A + kTcWgA;
-      const int m = m_begin + j * 64 + ml;
-      const bool valid = m < m_end;
-      // all (up to 16) 16-byte loads of this lane's sample row are issued before the buffer is even known to be free
-      float4 va[8], vx[8];
+      float4 vy[8], vx[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && ca0 + u < ca1) va[u] = __ldg(reinterpret_cast<const float4*>(p.gy + static_cast<size_t>(m) * N + (ca0 + u) * 4));
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        vx[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && cx0 + u < cx1) vx[u] = __ldg(reinterpret_cast<const float4*>(p.x + static_cast<size_t>(m) * K + (cx0 + u) * 4));
+      for (int i = 0; i < 8; ++i) {
+        const int m = m_begin + j * kTcWgTile + warp * 8 + i;
+        vy[i] = (has_y && m < m_end) ? __ldg(reinterpret_cast<const float4*>(p.gy + static_cast<size_t>(m) * N + 4 * lane))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        vx[i] = (has_x && m < m_end) ? __ldg(reinterpret_cast<const float4*>(p.x + static_cast<size_t>(m) * K + 4 * lane))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (use > 0) mbar_wait(&empty[s], (use & 1) ^ 1);  // the MMAs of tile j - stages are done with this buffer
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int c4 = ca0 + u;
-        if (c4 >= ca1) break;
-        *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 0, ml, 128u * 128u)) = f32_to_tf32(va[u].x);
-        *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 1, ml, 128u * 128u)) = f32_to_tf32(va[u].y);
-        *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 2, ml, 128u * 128u)) = f32_to_tf32(va[u].z);
-        *reinterpret_cast<uint32_t*>(A + sw128_f32(c4 * 4 + 3, ml, 128u * 128u)) = f32_to_tf32(va[u].w);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int c4 = cx0 + u;
-        if (c4 >= cx1) break;
-        float4 v = vx[u];
-        if (p.relu_in) {
-          v.x = fmaxf(v.x, 0.f);
-          v.y = fmaxf(v.y, 0.f);
-          v.z = fmaxf(v.z, 0.f);
-          v.w = fmaxf(v.w, 0.f);
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t r = warp * 8 + i;
+        if (has_y)
+          *reinterpret_cast<uint4*>(A + mn128_f32(r, 4 * lane)) =
+              make_uint4(f32_to_tf32(vy[i].x), f32_to_tf32(vy[i].y), f32_to_tf32(vy[i].z), f32_to_tf32(vy[i].w));
+        if (has_x) {
+          float4 v = vx[i];
+          if (p.relu_in) {
+            v.x = fmaxf(v.x, 0.f);
+            v.y = fmaxf(v.y, 0.f);
+            v.z = fmaxf(v.z, 0.f);
+            v.w = fmaxf(v.w, 0.f);
+          }
+          *reinterpret_cast<uint4*>(Bm + mn128_f32(r, 4 * lane)) =
+              make_uint4(f32_to_tf32(v.x), f32_to_tf32(v.y), f32_to_tf32(v.z), f32_to_tf32(v.w));
         }
-        *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 0, ml, b_kb)) = f32_to_tf32(v.x);
-        *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 1, ml, b_kb)) = f32_to_tf32(v.y);
-        *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 2, ml, b_kb)) = f32_to_tf32(v.z);
-        *reinterpret_cast<uint32_t*>(Bm + sw128_f32(c4 * 4 + 3, ml, b_kb)) = f32_to_tf32(v.w);
       }
       fence_proxy_async_smem();
       mbar_arrive(&full[s]);
@@ -673,16 +681,14 @@ __global__ void __launch_bounds__(kTcWgradThreads, 1) tt_wgrad_tc_kernel(const _
       }
     }
   } else if (lane == 0) {
-    const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(Kp));
+    const uint32_t idesc = make_idesc_tf32(static_cast<uint32_t>(Kp)) | (1u << 15) | (1u << 16);   // A and B MN-major
     for (int j = 0; j < n_my; ++j) {
       const int s = j % kTcWgStages;
       mbar_wait(&full[s], (j / kTcWgStages) & 1);
       tc_fence_after();
       const uint32_t a0 = smem_u32(base + s * (kTcWgA + kTcWgB)), b0 = a0 + kTcWgA;
-      for (int kb = 0; kb < 2; ++kb)
-        for (int k = 0; k < 4; ++k)
-          umma_tf32(tmem, make_sw128_desc(a0 + kb * (128 * 128) + k * 32), make_sw128_desc(b0 + kb * b_kb + k * 32), idesc,
-                    (j | kb | k) ? 1u : 0u);
+      for (int kg = 0; kg < kTcWgTile / 8; ++kg)
+        umma_tf32(tmem, make_sw128_mn_desc(a0 + kg * 1024), make_sw128_mn_desc(b0 + kg * 1024), idesc, (j | kg) ? 1u : 0u);
       umma_commit(&empty[s]);
       if (j == n_my - 1) umma_commit(done);
     }
