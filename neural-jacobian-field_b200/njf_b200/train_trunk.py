@@ -4,11 +4,12 @@ colour head, the proposal networks and, through the feature map, the encoder) an
 head (model_wrapper.py:75-85, 148-163 with ``jacobian_mlp``).
 
 The fused tcgen05 render kernels keep no activations, so a training step evaluates the trunks layer by layer with the
-fp32 kernels of ``csrc/trunk_train.cu`` (activations stay in HBM tensors) and ``torch.autograd`` does the book-keeping
+kernels of ``csrc/trunk_train.cu`` (fp32 SIMT, or tcgen05 kind::tf32 when torch's float32 matmul precision is not
+"highest" -- see ``tensor_cores``; activations stay in HBM tensors) and ``torch.autograd`` does the book-keeping
 between them, the way it chains ``nn.Linear`` calls in the reference (model_components/resnet_fc.py:70-79, 130-154):
 
 * ``_Linear``      y = relu?(x) W^T + b (+ residual)      njf_train_linear / njf_train_linear_wgrad
-* ``_GatherMaps``  z = bilinear taps of the lin_z maps    njf_train_gather / njf_train_scatter (adjoint, atomics)
+* ``_GatherMaps``  z_b = bilinear taps of lin_z map b     njf_train_gather / njf_train_scatter (adjoint, atomics)
 * ``sample_setup`` world point -> NeRFEncoding + taps     njf_train_sample_setup (no gradient: cameras are data)
 * ``_TruncExp``    trunc_exp (model_components/activations.py:13-38, clamped backward)
 
@@ -17,6 +18,8 @@ per-pixel maps being ONE plain library GEMM over the NHWC encoder output per tru
 produces d lin_z and the gradient that flows on into the encoder).  Sample placement (stratified jitter, PDF
 resampling on the detached proposal weights: ray_samplers.py:219-233, 351-451) runs on the sampler kernels; transmittance
 weights, compositing and the flow projection are the reference's own few elementwise torch ops on (B,R,S) tensors.
+When only ``decoder.jacobian_head`` (MLP head) is trainable, the frozen trunks render on the fused kernels and only the
+Jacobian trunk runs here (``_forward_train_mlp_head``).
 
 There is no CPU path: every entry point needs the CUDA library.
 """
