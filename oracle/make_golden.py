@@ -198,9 +198,74 @@ def joint_sensitivity_fixture():
     print("joint_sensitivity")
 
 
+def train_loss(rgb, flow, weights_list, mids_list, target_rgb, target_depth, target_flow):
+    """The scalar both sides differentiate: an rgb MSE, the flow MSE of the action phase (model_wrapper.py:148-163) and
+    two functions of every level's weights standing in for the DS-depth / interlevel / distortion terms (:116-140;
+    nerfstudio's losses are not installed here) -- every trainable tensor of the model receives a gradient."""
+    loss = torch.nn.functional.mse_loss(rgb, target_rgb) + 0.01 * torch.nn.functional.mse_loss(flow, target_flow)
+    for w, mid in zip(weights_list, mids_list):
+        loss = loss + 0.08 * ((w * mid).sum(-2) - target_depth).pow(2).mean() / len(weights_list) + 0.01 * (w * w).sum(-2).mean()
+    return loss
+
+
+def train_fixture(name, head, action_dim, s_prop, s_nerf, wseed, seed=1234, stride=53, **scene_kw):
+    """TRAIN-MODE forward + backward of the unmodified reference (Model.train(): stratified jitter from torch's global
+    CPU generator after torch.manual_seed(seed), ray_samplers.py:219-233, 389-401): outputs, the jittered bins and the
+    gradient of ``train_loss`` w.r.t. every decoder / proposal-network parameter and w.r.t. the encoder output (norm
+    + the whole tensor up to 8192 elements, else every ``stride``-th element)."""
+    m = ref_shim.reference_modules()
+    cfg = ref_shim.build_reference_cfg(action_dim, head, s_prop, s_nerf)
+    model = m.Model(cfg).train()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(synth.synth_state_dict(shapes, wseed, "trained"))
+    sc = scene(action_dim, **scene_kw)
+    B, R = sc["origins"].shape[:2]
+    g = torch.Generator().manual_seed(seed + 1)
+    target_rgb, target_depth = torch.rand(B, R, 3, generator=g), 0.5 + 2.0 * torch.rand(B, R, 1, generator=g)
+    target_flow = 2.0 * torch.randn(B, R, 2, generator=g)
+    # the encoder runs once, outside the seeded region, in eval mode (its output is an input of the fixture)
+    model.encoder.eval()
+    with torch.no_grad():
+        feat = model.encoder(sc["image"])
+    feat = feat.clone().requires_grad_(True)
+    model.encoder.forward = lambda image: feat          # the render path sees the stored features (a leaf with a gradient)
+    cam = m.CameraInput(sc["image"], sc["ctxt_c2w"], sc["ctxt_k"], sc["trgt_c2w"], sc["trgt_k_px"])
+    rin = m.RenderingInput(sc["origins"], sc["dirs"], sc["z_near"], sc["z_far"])
+    torch.manual_seed(seed)
+    out = model.forward(cam, rin, m.RobotInput(sc["action"]))
+    to = out.training_output
+    mids = [(rs.starts + rs.ends) / 2 for rs in to.ray_samples_list]
+    loss = train_loss(out.standard_output.rgb, out.standard_output.optical_flow, to.weights_list, mids, target_rgb,
+                      target_depth, target_flow)
+    loss.backward()
+    fix = {k: v.numpy() for k, v in sc.items()}
+    fix.update(feat=feat.detach().numpy(), head=head, action_dim=action_dim, s_prop=np.array(s_prop), s_nerf=s_nerf, wseed=wseed,
+               seed=seed, stride=stride, target_rgb=target_rgb.numpy(), target_depth=target_depth.numpy(),
+               target_flow=target_flow.numpy(), loss=float(loss), rgb=out.standard_output.rgb.detach().numpy(),
+               depth=out.standard_output.depth.detach().numpy(), optical_flow=out.standard_output.optical_flow.detach().numpy())
+    for i, (w, rs) in enumerate(zip(to.weights_list, to.ray_samples_list)):
+        fix[f"weights_{i}"] = w[..., 0].detach().numpy()
+        fix[f"bins_{i}"] = torch.cat([rs.spacing_starts[..., 0], rs.spacing_ends[..., -1:, 0]], -1).detach().numpy()
+    names = []
+    grads = {"feat": feat.grad}
+    grads.update({n: p.grad for n, p in model.named_parameters() if not n.startswith("encoder.")})
+    for n, gr in grads.items():
+        assert gr is not None, n
+        names.append(n)
+        fix["gnorm/" + n] = float(gr.norm())
+        fix["gsub/" + n] = gr.reshape(-1)[::(1 if gr.numel() <= 8192 else stride)].numpy().copy()
+    fix["grad_names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **fix)
+    print(name, "loss", float(loss), len(names), "gradient tensors")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        train_fixture("train_transformer", "jacobian_transformer", 8, (16,), 24, wseed=11)
+        train_fixture("train_mlp_2prop", "jacobian_mlp", 6, (16, 12), 20, wseed=5, batch=2, rays_hw=(4, 6))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "rays":
         rays_fixture()
         sys.exit(0)
@@ -216,3 +281,5 @@ if __name__ == "__main__":
                    rays_hw=(4, 6))
     render_fixture("render_transformer_initlike", "jacobian_transformer", 8, (32,), 32, wseed=14,
                    regime="init_like", rays_hw=(4, 4), view=0)
+    train_fixture("train_transformer", "jacobian_transformer", 8, (16,), 24, wseed=11)
+    train_fixture("train_mlp_2prop", "jacobian_mlp", 6, (16, 12), 20, wseed=5, batch=2, rays_hw=(4, 6))
