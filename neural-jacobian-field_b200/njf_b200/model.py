@@ -300,6 +300,9 @@ class Model(nn.Module):
         self._graphs: Dict[tuple, "_FrameGraph"] = {}
         self.output_device: Optional[torch.device] = None   # None: results go back to where the rays came from (reference)
         self.jitter_generator: Optional[torch.Generator] = None   # train-mode stratified jitter (None = torch's global CUDA RNG)
+        # (bins0, [u per level]) to use INSTEAD of drawing jitter (train.stratified_tables' layout): replays a step of
+        # another implementation, e.g. tables drawn on the CPU with the reference's seed (tests/golden/train_*.npz)
+        self.jitter_tables = None
 
     # ------------------------------------------------------------------ training-schedule hooks (model.py:201-213)
     def step_before_iter(self, step):
@@ -512,8 +515,7 @@ class Model(nn.Module):
         zn, zf = mv(rendering_input.z_near), mv(rendering_input.z_far)
         B, R = o.shape[:2]
         # RNG stays in torch: seed torch / set `jitter_generator` to reproduce a step
-        bins0, us = T.stratified_tables(s_prop, s_nerf, B, R, r.single_jitter, dev,
-                                        generator=getattr(self, "jitter_generator", None))
+        bins0, us = T.train_tables(self, s_prop, s_nerf, B, R, dev)
         action = robot_input.robot_action.to(dev, torch.float32)
         cams, keep = api.make_cameras(pe.extrinsics, pe.intrinsics, camera_input.trgt_extrinsics,
                                       camera_input.trgt_intrinsics, dev)

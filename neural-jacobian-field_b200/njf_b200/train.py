@@ -170,3 +170,14 @@ def stratified_tables(s_prop: Sequence[int], s_nerf: int, B: int, R: int, single
         u = u.expand((B, R, nb))
         us.append((u + rand(n + 1) / nb).contiguous())
     return bins0, us
+
+
+def train_tables(model, s_prop: Sequence[int], s_nerf: int, B: int, R: int, device):
+    """The step's sampling tables: ``model.jitter_tables`` when set (moved to the device), else freshly drawn."""
+    jt = getattr(model, "jitter_tables", None)
+    if jt is not None:
+        bins0, us = jt
+        f = lambda t: t.detach().to(device, torch.float32).contiguous()
+        return f(bins0), [f(u) for u in us]
+    return stratified_tables(s_prop, s_nerf, B, R, model.cfg.rendering.single_jitter, device,
+                             generator=getattr(model, "jitter_generator", None))

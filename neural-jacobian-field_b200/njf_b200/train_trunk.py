@@ -241,7 +241,7 @@ def forward_train(model, camera_input, rendering_input, robot_input, compute_vis
     """Model.forward (models/model.py:316-396) with autograd through every ResnetFC trunk, the colour head and the
     encoder.  Returns what njf_b200.Model._forward_train assembles into a ModelOutput:
     dict(rgb, depth, flow, jbar, steps, weights, p, pw, weights_list, bins_list)."""
-    from .train import stratified_tables
+    from .train import train_tables
 
     dev = model._device()
     r = model.cfg.rendering
@@ -265,8 +265,7 @@ def forward_train(model, camera_input, rendering_input, robot_input, compute_vis
     cams, keep = api.make_cameras(camera_input.ctxt_extrinsics, camera_input.ctxt_intrinsics,
                                   camera_input.trgt_extrinsics, camera_input.trgt_intrinsics, dev)
     cw, ck, tw, tk = keep[:4]
-    bins, us = stratified_tables(s_prop, s_nerf, B, R, r.single_jitter, dev,
-                                 generator=getattr(model, "jitter_generator", None))
+    bins, us = train_tables(model, s_prop, s_nerf, B, R, dev)
     near, far = zn[:, None, None], zf[:, None, None]
     euclid = lambda b: b * far + (1 - b) * near                                    # ray_samplers.py:242-245
 
@@ -347,7 +346,7 @@ def _forward_train_mlp_head(model, camera_input, robot_input, o, d, zn, zf, acti
     from the FUSED render (same kernels as inference, jittered tables); only the Jacobian trunk runs layer by layer under
     autograd, at the fused render's final sample positions."""
     from .render import render
-    from .train import stratified_tables
+    from .train import train_tables
 
     dev = o.device
     r = model.cfg.rendering
@@ -360,8 +359,7 @@ def _forward_train_mlp_head(model, camera_input, robot_input, o, d, zn, zf, acti
         cams, keep = api.make_cameras(camera_input.ctxt_extrinsics, camera_input.ctxt_intrinsics,
                                       camera_input.trgt_extrinsics, camera_input.trgt_intrinsics, dev)
         cw, ck, tw, tk = keep[:4]
-        bins0, us = stratified_tables(s_prop, s_nerf, B, R, r.single_jitter, dev,
-                                      generator=getattr(model, "jitter_generator", None))
+        bins0, us = train_tables(model, s_prop, s_nerf, B, R, dev)
         res = render(fld, maps16, Hf, Wf, cams, o, d, zn, zf, action.detach().contiguous(), s_prop, s_nerf, vis=True,
                      sampler_outputs=True, bins0=bins0, us=us, anneal=model._anneal)
         res._cams = keep
