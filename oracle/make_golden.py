@@ -208,13 +208,13 @@ def train_loss(rgb, flow, weights_list, mids_list, target_rgb, target_depth, tar
     return loss
 
 
-def train_fixture(name, head, action_dim, s_prop, s_nerf, wseed, seed=1234, stride=53, **scene_kw):
+def train_fixture(name, head, action_dim, s_prop, s_nerf, wseed, seed=1234, stride=53, single_jitter=False, **scene_kw):
     """TRAIN-MODE forward + backward of the unmodified reference (Model.train(): stratified jitter from torch's global
     CPU generator after torch.manual_seed(seed), ray_samplers.py:219-233, 389-401): outputs, the jittered bins and the
     gradient of ``train_loss`` w.r.t. every decoder / proposal-network parameter and w.r.t. the encoder output (norm
     + the whole tensor up to 8192 elements, else every ``stride``-th element)."""
     m = ref_shim.reference_modules()
-    cfg = ref_shim.build_reference_cfg(action_dim, head, s_prop, s_nerf)
+    cfg = ref_shim.build_reference_cfg(action_dim, head, s_prop, s_nerf, single_jitter)
     model = m.Model(cfg).train()
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     model.load_state_dict(synth.synth_state_dict(shapes, wseed, "trained"))
@@ -240,7 +240,7 @@ def train_fixture(name, head, action_dim, s_prop, s_nerf, wseed, seed=1234, stri
     loss.backward()
     fix = {k: v.numpy() for k, v in sc.items()}
     fix.update(feat=feat.detach().numpy(), head=head, action_dim=action_dim, s_prop=np.array(s_prop), s_nerf=s_nerf, wseed=wseed,
-               seed=seed, stride=stride, target_rgb=target_rgb.numpy(), target_depth=target_depth.numpy(),
+               seed=seed, stride=stride, single_jitter=int(single_jitter), target_rgb=target_rgb.numpy(), target_depth=target_depth.numpy(),
                target_flow=target_flow.numpy(), loss=float(loss), rgb=out.standard_output.rgb.detach().numpy(),
                depth=out.standard_output.depth.detach().numpy(), optical_flow=out.standard_output.optical_flow.detach().numpy())
     for i, (w, rs) in enumerate(zip(to.weights_list, to.ray_samples_list)):
@@ -248,7 +248,8 @@ def train_fixture(name, head, action_dim, s_prop, s_nerf, wseed, seed=1234, stri
         fix[f"bins_{i}"] = torch.cat([rs.spacing_starts[..., 0], rs.spacing_ends[..., -1:, 0]], -1).detach().numpy()
     names = []
     grads = {"feat": feat.grad}
-    grads.update({n: p.grad for n, p in model.named_parameters() if not n.startswith("encoder.")})
+    if not single_jitter:   # the single-jitter fixture pins the sampling tables only
+        grads.update({n: p.grad for n, p in model.named_parameters() if not n.startswith("encoder.")})
     for n, gr in grads.items():
         assert gr is not None, n
         names.append(n)
@@ -265,6 +266,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         train_fixture("train_transformer", "jacobian_transformer", 8, (16,), 24, wseed=11)
         train_fixture("train_mlp_2prop", "jacobian_mlp", 6, (16, 12), 20, wseed=5, batch=2, rays_hw=(4, 6))
+        train_fixture("train_single_jitter", "jacobian_mlp", 6, (16, 12), 20, wseed=5, seed=77, single_jitter=True, rays_hw=(3, 4))
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "rays":
         rays_fixture()
@@ -283,3 +285,4 @@ if __name__ == "__main__":
                    regime="init_like", rays_hw=(4, 4), view=0)
     train_fixture("train_transformer", "jacobian_transformer", 8, (16,), 24, wseed=11)
     train_fixture("train_mlp_2prop", "jacobian_mlp", 6, (16, 12), 20, wseed=5, batch=2, rays_hw=(4, 6))
+    train_fixture("train_single_jitter", "jacobian_mlp", 6, (16, 12), 20, wseed=5, seed=77, single_jitter=True, rays_hw=(3, 4))

@@ -141,7 +141,7 @@ def reference_modules():
     return ref_model
 
 
-def build_reference_cfg(action_dim: int, head: str, s_prop, s_nerf: int):
+def build_reference_cfg(action_dim: int, head: str, s_prop, s_nerf: int, single_jitter: bool = False):
     """ModelCfg with the shipped values (configurations/model/model_allegro.yaml / model_toy_arm.yaml)."""
     install()
     ref_model = reference_modules()
@@ -164,7 +164,7 @@ def build_reference_cfg(action_dim: int, head: str, s_prop, s_nerf: int):
         raise ValueError(head)
     return ref_model.ModelCfg(
         action_dim=action_dim,
-        rendering=ref_model.RenderingCfg(tuple(s_prop), s_nerf, False, 5000, 5, True, 1000, 10.0),
+        rendering=ref_model.RenderingCfg(tuple(s_prop), s_nerf, bool(single_jitter), 5000, 5, True, 1000, 10.0),
         encoder=EncoderResnetCfg("resnet", "bilinear", 4, True, "batch"),
         density_decoder=DensityDecoderMlpCfg("density_mlp", mlp),
         action_decoder=dec,

@@ -88,7 +88,7 @@ def test_ray_generation_matches_reference():
     np.testing.assert_allclose(d.numpy(), z["dirs_full"], atol=2e-7, rtol=0)
 
 
-@pytest.mark.parametrize("name", ["train_transformer", "train_mlp_2prop"])
+@pytest.mark.parametrize("name", ["train_transformer", "train_mlp_2prop", "train_single_jitter"])
 def test_train_mode_forward_and_gradients_match_reference(name):
     """Train-mode parity of the oracle AND of njf_b200.train.stratified_tables with the unmodified reference
     (oracle/make_golden.py train_fixture): the reference's Model.train() forward draws its stratified jitter from
@@ -114,7 +114,7 @@ def test_train_mode_forward_and_gradients_match_reference(name):
     o, d = t("origins"), t("dirs")
     B, R = o.shape[:2]
     torch.manual_seed(int(z["seed"]))
-    bins0, us = stratified_tables(s_prop, s_nerf, B, R, False, "cpu")
+    bins0, us = stratified_tables(s_prop, s_nerf, B, R, bool(int(z["single_jitter"])) if "single_jitter" in z.files else False, "cpu")
     out = O.render_forward(w, O.FieldSpec(head, A), feat, t("ctxt_c2w"), t("ctxt_k"), t("trgt_c2w"), t("trgt_k_px"), o, d,
                            t("z_near"), t("z_far"), t("action"), s_prop, s_nerf, bins0=bins0, us=us)
     near, far = t("z_near")[:, None, None], t("z_far")[:, None, None]
